@@ -1,0 +1,183 @@
+/*
+ * rappas_b200.h -- C ABI of the B200-native RAPPAS placement engine.
+ *
+ * This header is the drop-in boundary.  The reference (phylo42/RAPPAS, Java) has no
+ * FFI of its own; the seam is the call
+ *     Main_PLACEMENT_v07.java:255-257  ->  PlacementProcess.processQueries
+ *     (src/core/algos/PlacementProcess.java:471-483)
+ * and every entry point below names the reference code it replaces.  The ABI is plain
+ * C: flat pointers + sizes, POD structs passed by pointer, no callbacks, so that it
+ * binds from JNI, Panama FFM (java.lang.foreign), ctypes and cgo alike.  INTEGRATION.md
+ * shows the Java-side binding.
+ *
+ * Two libraries export symbols declared here:
+ *   librappas_b200.so   (rappas_b200/csrc, CUDA sm_100a)  -> every rp_* symbol
+ *   librappas_oracle.so (oracle/, plain C, TEST ONLY)      -> the rpo_* mirror (oracle/rappas_oracle.h)
+ *
+ * Threading: every call is re-entrant per rp_db handle; rp_last_error() is thread-local.
+ * Errors: non-zero return (RP_E_*) + rp_last_error(); the library never aborts the
+ * process (the reference calls System.exit(1) from inside the loop,
+ * AmbigSequenceKnife.java:124-128 -- here the read gets RP_STATUS_BAD_CHAR instead).
+ */
+#ifndef RAPPAS_B200_H
+#define RAPPAS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RP_ABI_VERSION 1
+
+/* return codes */
+#define RP_OK            0
+#define RP_E_INVALID     1   /* bad argument / unsupported parameter combination      */
+#define RP_E_CUDA        2   /* CUDA runtime error (message in rp_last_error)          */
+#define RP_E_NOMEM       3   /* host or device allocation failed                       */
+#define RP_E_IO          4   /* file could not be read / written / parsed              */
+#define RP_E_UNSUPPORTED 5   /* feature compiled out or not available on this box      */
+
+/* alphabets (SessionNext_v2.states: DNAStatesShifted | AAStates) */
+#define RP_ALPHA_NUCL      0 /* A=0 T/U=1 C=2 G=3, DNAStatesShifted.java:182-209       */
+#define RP_ALPHA_AMINO     1 /* RHKDESTNQCGPAILMFWYV = 0..19, AAStates.java:23-34      */
+#define RP_ALPHA_AMINO_UO  2 /* amino, DB built with --convertUO (U->C, O->L), AAStates.java:118-123 */
+
+/* per-read status (out_status) */
+#define RP_STATUS_PLACED    0 /* >=1 row emitted (or rows suppressed only by ns_bound)  */
+#define RP_STATUS_UNPLACED  1 /* no k-mer hit: PlacementProcess.java:797-806            */
+#define RP_STATUS_TOO_SHORT 2 /* len < k-1; the reference throws NegativeArraySizeException (AmbigSequenceKnife.java:145) */
+#define RP_STATUS_BAD_CHAR  3 /* unsupported character; the reference exits(1) (AmbigSequenceKnife.java:124-128) */
+
+/* per-window kind (rp_extract_kmers) */
+#define RP_WIN_PLAIN   0     /* no ambiguity: one k-mer                                */
+#define RP_WIN_AMBIG   1     /* 1..maxAmbigPerMer ambiguities: n alternatives          */
+#define RP_WIN_SKIPPED 2     /* > maxAmbigPerMer ambiguities: AmbigSequenceKnife.java:230-232 */
+
+/* out_counts columns, PlacementProcess.java:646-649, 790 */
+#define RP_CNT_WINDOWS  0    /* queryKmerCount = Q                                     */
+#define RP_CNT_MATCHED  1    /* queryKmerMatchingDB (plain windows only) */
+#define RP_CNT_AMBIG    2    /* ambiguousMerTreated                                    */
+#define RP_CNT_SKIPPED  3    /* skippedKmer                                            */
+
+typedef struct rp_db rp_db; /* opaque: owns the device-resident DB on every selected GPU */
+
+/* What the hot path consumes from SessionNext_v2 (SessionNext_v2.java:43-66, 163-195) */
+typedef struct rp_db_desc {
+  int32_t  alphabet;    /* RP_ALPHA_*                                                   */
+  int32_t  k;           /* session.k ; nucl 2..31, amino 2..12                          */
+  int32_t  n_nodes;     /* session.originalTree.getNodeCount(), 1..65535 (char keys)    */
+  float    thr_log10;   /* session.PPStarThresholdAsLog10  (T)                          */
+  float    thr_lin;     /* session.PPStarThreshold         (T_lin)                      */
+  int32_t  reserved0;
+  uint64_t n_keys;      /* distinct k-mers                                              */
+  uint64_t n_postings;  /* total (node, score) pairs                                    */
+} rp_db_desc;
+
+/* Placement flags, ArgumentsParser_v2.java:86-91 + PlacementProcess ctor :73-77 */
+typedef struct rp_place_cfg {
+  int32_t keep_at_most; /* --keep-at-most, default 7, 1..RP_MAX_KEEP                    */
+  float   keep_factor;  /* --keep-factor, default 0.01f                                 */
+  int32_t treat_amb;    /* !--noamb, default 1                                          */
+  int32_t amb_with_max; /* --ambwithmax, default 0                                      */
+  float   ns_bound;     /* --nsbound / calibrationNormScore, default -INFINITY          */
+  int32_t reserved0;
+} rp_place_cfg;
+
+#define RP_MAX_KEEP 32
+
+/* Threshold exactly as Main_DBBUILD_3.java:165-166 computes it (float/double sequence). */
+void rp_threshold(float omega, int32_t alphabet, int32_t k, float* thr_lin, float* thr_log10);
+
+/* k-mer code of k state bytes.  nucl: DNAStatesShifted.compressMer (DNAStatesShifted.java:115-143)
+ * read as a little-endian integer, code = sum b_i * 4^i; amino: sum b_i * 32^i (the
+ * reference keys on the raw byte[k], AAStates.java:195-197; equality is the same). */
+uint64_t rp_pack_kmer(int32_t alphabet, const uint8_t* states, int32_t k);
+
+/* ---- DB: replaces the in-JVM CustomHash_v4_FastUtil81 (CustomHash_v4_FastUtil81.java:36)
+ * by a GPU-resident open-addressing table + posting blocks.  Input is the flat CSR export
+ * of hash.getHash() (walk pattern: SessionNext_v2.java:250-261):
+ *   keys[n_keys]        k-mer codes (rp_pack_kmer), distinct, any order
+ *   offsets[n_keys+1]   CSR offsets into the posting arrays
+ *   post_node/score     postings of key i at [offsets[i], offsets[i+1]), in
+ *                       char2FloatEntrySet() iteration order; node ids distinct within a key
+ * devices[n_devices]    CUDA ordinals; the DB is replicated on each (partitioned = 0).
+ * partitioned = 1       keys are hash-partitioned over the devices (DBs > one GPU's HBM).
+ */
+int  rp_db_load(const rp_db_desc* desc, const uint64_t* keys, const uint64_t* offsets,
+                const uint16_t* post_node, const float* post_score,
+                const int32_t* devices, int32_t n_devices, int32_t partitioned, rp_db** out);
+/* Same, from an .rgdb file written by the Java exporter (format: DESIGN.md). */
+int  rp_db_load_file(const char* path, const int32_t* devices, int32_t n_devices,
+                     int32_t partitioned, rp_db** out);
+int  rp_db_save_file(const char* path, const rp_db_desc* desc, const uint64_t* keys,
+                     const uint64_t* offsets, const uint16_t* post_node, const float* post_score);
+void rp_db_free(rp_db* db);
+int  rp_db_describe(const rp_db* db, rp_db_desc* out);
+/* bytes of HBM the DB occupies on one device (table + posting blocks) */
+int  rp_db_device_bytes(const rp_db* db, uint64_t* table_bytes, uint64_t* block_bytes);
+
+/* ---- placement of one batch of reads: replaces the per-read body of
+ * PlacementProcess.processQueries (PlacementProcess.java:645-838) and the LWR / keep-factor
+ * loop (PlacementProcess.java:974-1000).
+ *   seq, seq_off[n_reads+1]   concatenated ASCII reads exactly as Fasta.getSequence(false)
+ *                             returns them (gaps kept, Main_PLACEMENT_v07.java:195)
+ * outputs (caller-allocated, host memory):
+ *   out_n_rows[n]             rows emitted for the read (0 if unplaced / below ns_bound)
+ *   out_node/score/lwr        [n][keep_at_most], best first; unused slots: 0xFFFF / -inf / 0
+ *   out_counts[n][4]          RP_CNT_* (may be NULL)
+ *   out_status[n]             RP_STATUS_*
+ * Reads are sharded over the DB's devices in contiguous slices; no inter-GPU traffic
+ * when the DB is replicated.
+ */
+int  rp_place_batch(rp_db* db, const rp_place_cfg* cfg,
+                    const uint8_t* seq, const uint64_t* seq_off, int64_t n_reads,
+                    int32_t* out_n_rows, uint16_t* out_node, float* out_score, double* out_lwr,
+                    int32_t* out_counts, int32_t* out_status);
+
+/* Same work with every buffer already resident on devices[device_index] and the kernels
+ * enqueued on `stream` (a cudaStream_t; NULL = default stream).  Asynchronous: returns
+ * after launch.  This is what bench.py times as the kernel-only number. */
+int  rp_place_batch_device(rp_db* db, int32_t device_index, const rp_place_cfg* cfg,
+                           const uint8_t* d_seq, const uint64_t* d_seq_off, int64_t n_reads,
+                           int32_t* d_out_n_rows, uint16_t* d_out_node, float* d_out_score,
+                           double* d_out_lwr, int32_t* d_out_counts, int32_t* d_out_status,
+                           void* stream);
+
+/* ---- parity diagnostics for k-mer extraction + lookup (K1 + K2):
+ * AmbigSequenceKnife.initTables/getNextByteWord (AmbigSequenceKnife.java:98-174, 209-272),
+ * DNAStatesShifted.compressMer, CustomHash_v4_FastUtil81.getPairsOfTopPosition2 (:146-153).
+ * win_off[n_reads+1] = prefix sum of max(len-k+1, 0).  Per window:
+ *   out_code    code of the plain window / of alternative 0 of an ambiguous window; ~0 if skipped
+ *   out_kind    RP_WIN_*
+ *   out_nalt    1, n (= product of alternative counts), or 0 if skipped
+ *   out_hits    postings found: plain -> len of the posting list or -1 on a miss;
+ *               ambiguous -> sum over alternatives found, -1 if none matched; skipped -> -1
+ * Windows of reads with status != 0 are filled with (~0, SKIPPED, 0, -1).
+ */
+int  rp_extract_kmers(rp_db* db, const uint8_t* seq, const uint64_t* seq_off, int64_t n_reads,
+                      const uint64_t* win_off, uint64_t* out_code, uint8_t* out_kind,
+                      int32_t* out_nalt, int32_t* out_hits, int32_t* out_status);
+
+/* ---- parity diagnostic for the scoring stage (K3): the full per-node vector S[] of every
+ * read after its last window (PlacementProcess.java:719-735, 1161-1172, 1223-1234).
+ *   out_scores[n_reads][n_nodes]   NaN where the node was never touched (C[x]==0)
+ *   out_hitcount                   C[x]; the CUDA library does not keep C[] (only first-touch
+ *                                  matters to S) and requires NULL here; the oracle fills it.
+ */
+int  rp_node_scores(rp_db* db, const rp_place_cfg* cfg, const uint8_t* seq, const uint64_t* seq_off,
+                    int64_t n_reads, float* out_scores, int32_t* out_hitcount);
+
+/* ---- introspection used by bench.py / tests */
+int  rp_device_count(void);
+/* number of kernels this library launched since load (all threads); bench.py's gpu_launches */
+uint64_t rp_kernel_launch_count(void);
+/* device-event time (ms) of the placement kernel of the last rp_place_batch call, max over devices */
+double rp_last_kernel_ms(const rp_db* db);
+const char* rp_version(void);
+const char* rp_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAPPAS_B200_H */
