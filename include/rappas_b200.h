@@ -27,6 +27,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
 
 #define RP_ABI_VERSION 1
 
@@ -177,6 +180,9 @@ double rp_last_kernel_ms(const rp_db* db);
 const char* rp_version(void);
 const char* rp_last_error(void);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,161 @@
+// rp_common.h -- internal declarations shared by the CUDA translation units of librappas_b200.so.
+// Nothing here is part of the C ABI (that is include/rappas_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/rappas_b200.h"
+
+namespace rp {
+
+// ---------------------------------------------------------------------------------------------
+// HBM layout of the phylo-kmer DB (one copy per device; see DESIGN.md "Data layout")
+//
+//  table   : open-addressing, linear probing, capacity = pow2 >= 2*n_keys, 16 B slots
+//            slot = { u64 key, u64 meta },  meta = (block_offset_in_32B_units << 16) | n_postings
+//            empty slot: key == kEmptyKey.  One LDG.128 per probe.
+//  blocks  : posting blocks, 32 B aligned.  A key with P postings (sorted by node id at load) is a
+//            run of sub-blocks of up to 32 postings; sub-block i starts at block + 192*i and holds
+//            m = min(32, P-32i) entries as [m x f32 score][m x u16 node]  (SoA inside the sub-block:
+//            a warp reads 128 B of scores + 64 B of nodes, both coalesced).  The block is padded to
+//            a multiple of 32 B so that a gather touches whole sectors only.
+// ---------------------------------------------------------------------------------------------
+constexpr uint64_t kEmptyKey = ~0ull;
+constexpr int kSubBlock = 32;             // postings per sub-block
+constexpr int kSubBlockBytes = 32 * 6;    // 192
+constexpr int kBlockAlign = 32;           // bytes
+
+__host__ __device__ inline uint64_t block_bytes_for(uint64_t n_postings) {
+  uint64_t b = (n_postings / kSubBlock) * kSubBlockBytes + (n_postings % kSubBlock) * 6;
+  return (b + kBlockAlign - 1) / kBlockAlign * kBlockAlign;
+}
+
+__host__ __device__ inline uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+  return x;
+}
+
+// ---------------------------------------------------------------------------------------------
+// character classes (one byte per query character)
+//   0..19        state byte (DNAStatesShifted.java:182-209 / AAStates.java:74-93)
+//   0x40 | id    ambiguous, id indexes the alternative-set table
+//   0x80         padding past the end of the read (never part of a valid window)
+//   0xFF         unsupported character (reference: System.exit(1), AmbigSequenceKnife.java:124-128)
+// ---------------------------------------------------------------------------------------------
+constexpr uint8_t kClsAmb = 0x40;
+constexpr uint8_t kClsPad = 0x80;
+constexpr uint8_t kClsBad = 0xFF;
+constexpr int kMaxAltSets = 16;
+constexpr int kMaxAltStates = 20;
+
+struct AlphabetTables {
+  uint8_t cls[256];
+  uint8_t alt_n[kMaxAltSets];
+  uint8_t alt_states[kMaxAltSets][kMaxAltStates];
+};
+// fills the tables for RP_ALPHA_*; host side, uploaded once per device into __constant__ memory
+void build_alphabet_tables(int alphabet, AlphabetTables* t);
+int  alphabet_bits(int alphabet);
+int  alphabet_states(int alphabet);
+int  max_ambig_per_mer(int alphabet, int k);  // AmbigSequenceKnife.java:95
+
+// ---------------------------------------------------------------------------------------------
+// device-side views passed to kernels by value
+// ---------------------------------------------------------------------------------------------
+struct DbView {
+  const uint4* table;
+  uint64_t mask;
+  const uint8_t* blocks;
+  int alphabet, k, bits, n_nodes, max_amb;
+  float T, Tlin;
+};
+
+struct CfgView {
+  int K;
+  float keep_factor;
+  int treat_amb, amb_with_max;
+  float ns_bound;
+};
+
+struct BatchView {
+  const uint8_t* seq;       // device, bytes [seq_base, ...)
+  const uint64_t* seq_off;  // device, [n_reads+1], absolute offsets (seq_base is subtracted)
+  uint64_t seq_base;
+  long long n_reads;
+  int32_t* n_rows;
+  uint16_t* node;
+  float* score;
+  double* lwr;
+  int32_t* counts;  // may be null
+  int32_t* status;
+  float* dump_scores;  // may be null: [n_reads][n_nodes]
+};
+
+// per (device, stream) resources
+struct StreamCtx {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;
+  unsigned long long* d_counter = nullptr;  // dynamic read scheduler
+  float* d_amb_S = nullptr;                 // ambiguity scratch: [total_warps][n_nodes_pad]
+  int* d_amb_C = nullptr;
+  // device staging for host-buffer calls (grown on demand)
+  uint8_t* d_seq = nullptr; size_t cap_seq = 0;
+  uint64_t* d_off = nullptr; size_t cap_reads = 0;
+  int32_t* d_n_rows = nullptr; uint16_t* d_node = nullptr; float* d_score = nullptr; double* d_lwr = nullptr;
+  int32_t* d_counts = nullptr; int32_t* d_status = nullptr; int cap_K = 0;
+  float kernel_ms = 0.f;
+};
+
+struct LaunchGeom {
+  int warps_per_cta = 0, ctas_per_sm = 0, grid = 0;
+  size_t smem_bytes = 0, per_warp_bytes = 0;
+  int n_pad = 0;
+};
+
+struct DeviceCtx {
+  int device = -1;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+  uint4* d_table = nullptr;
+  uint8_t* d_blocks = nullptr;
+  LaunchGeom geom;
+  StreamCtx sc[2];  // double buffering for host-buffer calls (rp_place_batch)
+  StreamCtx sc_dev; // scheduler counter + scratch of device-buffer calls (rp_place_batch_device)
+  std::mutex mu;
+};
+
+}  // namespace rp
+
+struct rp_db {
+  rp_db_desc desc{};
+  uint64_t table_cap = 0;
+  uint64_t block_bytes = 0;
+  int partitioned = 0;
+  rp::AlphabetTables alpha{};
+  std::vector<rp::DeviceCtx*> dev;
+  std::atomic<double> last_kernel_ms{0.0};
+};
+
+namespace rp {
+
+int set_error(int code, const char* fmt, ...);
+#define RP_CUDA_TRY(expr)                                                                         \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      return rp::set_error(RP_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+extern std::atomic<uint64_t> g_kernel_launches;
+
+DbView make_db_view(const rp_db* db, const DeviceCtx* dc);
+int compute_geometry(const rp_db* db, DeviceCtx* dc);  // rp_place.cu
+int ensure_stream_ctx(const rp_db* db, DeviceCtx* dc, StreamCtx* sc);  // rp_place.cu
+
+}  // namespace rp

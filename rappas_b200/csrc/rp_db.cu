@@ -1,0 +1,419 @@
+// rp_db.cu -- host side of the device-resident phylo-kmer DB: alphabet tables, threshold,
+// flat CSR -> (open-addressing table + posting blocks), upload, .rgdb file I/O, error plumbing.
+//
+// Replaces, for the placement path only, the in-JVM CustomHash_v4_FastUtil81
+// (core/hash/CustomHash_v4_FastUtil81.java:36: Object2ObjectOpenCustomHashMap<byte[],Char2FloatOpenHashMap>)
+// and the part of SessionNext_v2.load (main_v2/SessionNext_v2.java:158-207) the hot path consumes.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <fcntl.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <thread>
+
+#include "rp_common.h"
+
+namespace rp {
+
+static thread_local char t_err[512];
+std::atomic<uint64_t> g_kernel_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof t_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int alphabet_bits(int alphabet) { return alphabet == RP_ALPHA_NUCL ? 2 : 5; }
+int alphabet_states(int alphabet) { return alphabet == RP_ALPHA_NUCL ? 4 : 20; }
+
+// AmbigSequenceKnife ctor (core/algos/AmbigSequenceKnife.java:95):
+//   maxAmbigPerMer=(int)Math.floor(Math.pow(k, 1.0/s.getNonAmbiguousStatesCount()))
+int max_ambig_per_mer(int alphabet, int k) {
+  return (int)floor(pow((double)k, 1.0 / (double)alphabet_states(alphabet)));
+}
+
+// Character classes.  isAmbiguous() is consulted before stateToByte() (AmbigSequenceKnife.java:106,123),
+// so an ambiguity letter wins over a state letter of the same spelling.
+void build_alphabet_tables(int alphabet, AlphabetTables* t) {
+  memset(t->cls, kClsBad, sizeof t->cls);
+  memset(t->alt_n, 0, sizeof t->alt_n);
+  memset(t->alt_states, 0, sizeof t->alt_states);
+  auto both_cases = [&](char upper, uint8_t v) {
+    t->cls[(unsigned char)upper] = v;
+    t->cls[(unsigned char)(upper + 32)] = v;
+  };
+  int next_set = 0;
+  auto add_set = [&](const char* letters_cased, std::initializer_list<int> states) {
+    int id = next_set++;
+    t->alt_n[id] = (uint8_t)states.size();
+    int i = 0;
+    for (int s : states) t->alt_states[id][i++] = (uint8_t)s;
+    for (const char* p = letters_cased; *p; ++p) t->cls[(unsigned char)*p] = (uint8_t)(kClsAmb | id);
+  };
+  if (alphabet == RP_ALPHA_NUCL) {
+    // DNAStatesShifted.charToByte, core/DNAStatesShifted.java:182-209
+    enum { A = 0, T = 1, C = 2, G = 3 };
+    both_cases('A', A); both_cases('T', T); both_cases('U', T); both_cases('C', C); both_cases('G', G);
+    // IUPAC alternatives in the literal array order of core/DNAStatesShifted.java:62-96
+    add_set("Rr", {A, G}); add_set("Yy", {C, T}); add_set("Ss", {C, G}); add_set("Ww", {A, T});
+    add_set("Kk", {G, T}); add_set("Mm", {A, C});
+    add_set("Bb", {C, G, T}); add_set("Dd", {A, G, T}); add_set("Hh", {A, C, T}); add_set("Vv", {A, C, G});
+    add_set("Nn", {A, C, G, T});
+    // '.' and '-' are registered as new byte[4] and never filled (:57-58): four times state 0
+    add_set(".-", {0, 0, 0, 0});
+  } else {
+    // AAStates, core/AAStates.java:23-34, 74-93
+    const char* order = "RHKDESTNQCGPAILMFWYV";
+    for (int i = 0; i < 20; i++) both_cases(order[i], (uint8_t)i);
+    if (alphabet == RP_ALPHA_AMINO_UO) {  // :118-123
+      both_cases('U', 9);
+      both_cases('O', 14);
+    }
+    // :97-107
+    add_set("-*!Xx", {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19});
+    add_set("Bb", {3, 7});
+    add_set("Zz", {4, 8});
+    add_set("Jj", {13, 14});
+  }
+}
+
+DbView make_db_view(const rp_db* db, const DeviceCtx* dc) {
+  DbView v;
+  v.table = dc->d_table;
+  v.mask = db->table_cap - 1;
+  v.blocks = dc->d_blocks;
+  v.alphabet = db->desc.alphabet;
+  v.k = db->desc.k;
+  v.bits = alphabet_bits(db->desc.alphabet);
+  v.n_nodes = db->desc.n_nodes;
+  v.max_amb = max_ambig_per_mer(db->desc.alphabet, db->desc.k);
+  v.T = db->desc.thr_log10;
+  v.Tlin = db->desc.thr_lin;
+  return v;
+}
+
+static int check_desc(const rp_db_desc* d) {
+  if (!d) return set_error(RP_E_INVALID, "desc is NULL");
+  if (d->alphabet < 0 || d->alphabet > 2) return set_error(RP_E_INVALID, "alphabet %d not in {0,1,2}", d->alphabet);
+  int kmax = d->alphabet == RP_ALPHA_NUCL ? 31 : 12;
+  if (d->k < 2 || d->k > kmax) return set_error(RP_E_INVALID, "k=%d out of range [2,%d]", d->k, kmax);
+  if (d->n_nodes < 1 || d->n_nodes > 65535)
+    return set_error(RP_E_INVALID, "n_nodes=%d out of range [1,65535] (node ids are Java chars)", d->n_nodes);
+  return RP_OK;
+}
+
+// ---- host build of table + blocks (multi-threaded over key ranges) ------------------------------
+struct HostImage {
+  std::vector<uint64_t> table;   // 2 u64 per slot
+  uint8_t* blocks = nullptr;     // malloc'd, block_bytes
+  uint64_t table_cap = 0, block_bytes = 0;
+  ~HostImage() { free(blocks); }
+};
+
+static int build_image(const rp_db_desc* d, const uint64_t* keys, const uint64_t* offsets, const uint16_t* post_node,
+                       const float* post_score, HostImage* img) {
+  const uint64_t nk = d->n_keys;
+  if (offsets && nk && offsets[nk] != d->n_postings)
+    return set_error(RP_E_INVALID, "offsets[n_keys]=%llu != n_postings=%llu", (unsigned long long)offsets[nk],
+                     (unsigned long long)d->n_postings);
+  uint64_t cap = 64;
+  while (cap < 2 * nk) cap <<= 1;
+  img->table_cap = cap;
+  img->table.assign(2 * cap, 0);
+  for (uint64_t i = 0; i < cap; i++) img->table[2 * i] = kEmptyKey;
+  // block offsets (32 B units)
+  std::vector<uint64_t> boff(nk + 1, 0);
+  for (uint64_t i = 0; i < nk; i++) {
+    if (offsets[i + 1] < offsets[i]) return set_error(RP_E_INVALID, "offsets not monotone at key %llu", (unsigned long long)i);
+    uint64_t P = offsets[i + 1] - offsets[i];
+    if (P > 65535) return set_error(RP_E_INVALID, "key %llu has %llu postings (> 65535)", (unsigned long long)i, (unsigned long long)P);
+    boff[i + 1] = boff[i] + block_bytes_for(P) / kBlockAlign;
+  }
+  if (boff[nk] >= (1ull << 48)) return set_error(RP_E_INVALID, "posting blocks exceed 2^48 * 32 B");
+  img->block_bytes = boff[nk] * kBlockAlign;
+  img->blocks = (uint8_t*)calloc(img->block_bytes ? img->block_bytes : 32, 1);
+  if (!img->blocks) return set_error(RP_E_NOMEM, "cannot allocate %llu B for posting blocks", (unsigned long long)img->block_bytes);
+
+  unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  if (nk < 4096) nt = 1;
+  std::atomic<int> err{0};
+  const int n_nodes = d->n_nodes;
+  auto pack_range = [&](uint64_t k0, uint64_t k1) {
+    std::vector<std::pair<uint16_t, float>> tmp;
+    for (uint64_t i = k0; i < k1 && !err.load(std::memory_order_relaxed); i++) {
+      const uint64_t lo = offsets[i], P = offsets[i + 1] - offsets[i];
+      if (keys[i] == kEmptyKey) { err = 4; return; }
+      tmp.resize(P);
+      bool sorted = true;
+      for (uint64_t p = 0; p < P; p++) {
+        tmp[p] = {post_node[lo + p], post_score[lo + p]};
+        if (post_node[lo + p] >= n_nodes) { err = 1; return; }
+        if (p && tmp[p].first <= tmp[p - 1].first) sorted = false;
+      }
+      if (!sorted) {
+        // node order inside a key only decides L order (tie-breaks); ascending ids make the
+        // shared-memory accumulation bank-conflict free for contiguous runs
+        std::sort(tmp.begin(), tmp.end(), [](auto& a, auto& b) { return a.first < b.first; });
+        for (uint64_t p = 1; p < P; p++)
+          if (tmp[p].first == tmp[p - 1].first) { err = 2; return; }  // one value per (k-mer,node): CustomHash_v4:76-89
+      }
+      uint8_t* blk = img->blocks + boff[i] * kBlockAlign;
+      for (uint64_t base = 0; base < P; base += kSubBlock) {
+        uint64_t m = std::min<uint64_t>(kSubBlock, P - base);
+        float* sc = (float*)(blk + (base / kSubBlock) * kSubBlockBytes);
+        uint16_t* nd = (uint16_t*)((uint8_t*)sc + 4 * m);
+        for (uint64_t q = 0; q < m; q++) { sc[q] = tmp[base + q].second; nd[q] = tmp[base + q].first; }
+      }
+      // insert into the table (lock-free: CAS on the key word, then publish meta)
+      uint64_t meta = (boff[i] << 16) | P;
+      uint64_t h = mix64(keys[i]) & (cap - 1);
+      for (;;) {
+        uint64_t* slot = &img->table[2 * h];
+        uint64_t expect = kEmptyKey;
+        if (__atomic_compare_exchange_n(slot, &expect, keys[i], false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) {
+          slot[1] = meta;
+          break;
+        }
+        if (expect == keys[i]) { err = 3; return; }
+        h = (h + 1) & (cap - 1);
+      }
+    }
+  };
+  if (nt == 1) {
+    pack_range(0, nk);
+  } else {
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++) th.emplace_back(pack_range, nk * t / nt, nk * (t + 1) / nt);
+    for (auto& x : th) x.join();
+  }
+  switch (err.load()) {
+    case 1: return set_error(RP_E_INVALID, "posting node id >= n_nodes");
+    case 2: return set_error(RP_E_INVALID, "a key lists the same node twice");
+    case 3: return set_error(RP_E_INVALID, "duplicate key");
+    case 4: return set_error(RP_E_INVALID, "key 0xFFFFFFFFFFFFFFFF is reserved");
+    default: break;
+  }
+  return RP_OK;
+}
+
+static void free_device_ctx(DeviceCtx* dc) {
+  if (!dc) return;
+  if (dc->device >= 0 && cudaSetDevice(dc->device) == cudaSuccess) {
+    StreamCtx* all[3] = {&dc->sc[0], &dc->sc[1], &dc->sc_dev};
+    for (StreamCtx* sp : all) {
+      StreamCtx& s = *sp;
+      if (s.stream) cudaStreamSynchronize(s.stream);
+      cudaFree(s.d_counter); cudaFree(s.d_amb_S); cudaFree(s.d_amb_C);
+      cudaFree(s.d_seq); cudaFree(s.d_off); cudaFree(s.d_n_rows); cudaFree(s.d_node); cudaFree(s.d_score);
+      cudaFree(s.d_lwr); cudaFree(s.d_counts); cudaFree(s.d_status);
+      if (s.ev_k0) cudaEventDestroy(s.ev_k0);
+      if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+      if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    cudaFree(dc->d_table);
+    cudaFree(dc->d_blocks);
+  }
+  delete dc;
+}
+
+}  // namespace rp
+
+using namespace rp;
+
+extern "C" {
+
+const char* rp_last_error(void) { return t_err; }
+const char* rp_version(void) { return "rappas_b200 0.1 (sm_100a, abi 1)"; }
+uint64_t rp_kernel_launch_count(void) { return g_kernel_launches.load(); }
+
+int rp_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+// Main_DBBUILD_3.java:165-166 (float/double sequence kept literally)
+void rp_threshold(float omega, int32_t alphabet, int32_t k, float* thr_lin, float* thr_log10) {
+  float ratio = omega / (float)alphabet_states(alphabet);
+  float lin = (float)pow(0.0 + (double)ratio, (double)k);
+  float lg = (float)log10((double)lin);
+  if (thr_lin) *thr_lin = lin;
+  if (thr_log10) *thr_log10 = lg;
+}
+
+uint64_t rp_pack_kmer(int32_t alphabet, const uint8_t* states, int32_t k) {
+  uint64_t code = 0;
+  const int bits = alphabet_bits(alphabet);
+  for (int i = 0; i < k; i++) code |= (uint64_t)states[i] << (bits * i);
+  return code;
+}
+
+int rp_db_load(const rp_db_desc* desc, const uint64_t* keys, const uint64_t* offsets, const uint16_t* post_node,
+               const float* post_score, const int32_t* devices, int32_t n_devices, int32_t partitioned,
+               rp_db** out) {
+  int rc = check_desc(desc);
+  if (rc) return rc;
+  if (!out) return set_error(RP_E_INVALID, "out is NULL");
+  *out = nullptr;
+  if (partitioned) return set_error(RP_E_UNSUPPORTED, "hash-partitioned DB mode is not built in this round (see DESIGN.md)");
+  if (n_devices < 1 || !devices) return set_error(RP_E_INVALID, "need at least one device");
+  if (desc->n_keys && (!keys || !offsets)) return set_error(RP_E_INVALID, "keys/offsets are NULL");
+  if (desc->n_postings && (!post_node || !post_score)) return set_error(RP_E_INVALID, "posting arrays are NULL");
+  int ndev_avail = rp_device_count();
+  if (ndev_avail == 0)
+    return set_error(RP_E_CUDA, "no CUDA device visible: librappas_b200 has no CPU fallback");
+  for (int i = 0; i < n_devices; i++)
+    if (devices[i] < 0 || devices[i] >= ndev_avail) return set_error(RP_E_INVALID, "device %d not present", devices[i]);
+
+  HostImage img;
+  static const uint64_t zero_off[1] = {0};
+  rc = build_image(desc, keys, desc->n_keys ? offsets : zero_off, post_node, post_score, &img);
+  if (rc) return rc;
+
+  rp_db* db = new rp_db();
+  db->desc = *desc;
+  db->table_cap = img.table_cap;
+  db->block_bytes = img.block_bytes;
+  db->partitioned = 0;
+  build_alphabet_tables(desc->alphabet, &db->alpha);
+  for (int i = 0; i < n_devices; i++) {
+    DeviceCtx* dc = new DeviceCtx();
+    db->dev.push_back(dc);
+    dc->device = devices[i];
+    cudaError_t e = cudaSetDevice(dc->device);
+    cudaDeviceProp prop;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, dc->device);
+    if (e == cudaSuccess) {
+      dc->sm_count = prop.multiProcessorCount;
+      dc->smem_optin = prop.sharedMemPerBlockOptin;
+      e = cudaMalloc((void**)&dc->d_table, img.table_cap * 16);
+    }
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dc->d_blocks, img.block_bytes ? img.block_bytes : 32);
+    if (e == cudaSuccess) e = cudaMemcpy(dc->d_table, img.table.data(), img.table_cap * 16, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && img.block_bytes)
+      e = cudaMemcpy(dc->d_blocks, img.blocks, img.block_bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      int code = (e == cudaErrorMemoryAllocation) ? RP_E_NOMEM : RP_E_CUDA;
+      set_error(code, "device %d: %s while uploading the DB (%llu B table + %llu B blocks)", dc->device,
+                cudaGetErrorString(e), (unsigned long long)(img.table_cap * 16), (unsigned long long)img.block_bytes);
+      cudaGetLastError();
+      rp_db_free(db);
+      return code;
+    }
+    rc = compute_geometry(db, dc);
+    if (rc) { rp_db_free(db); return rc; }
+  }
+  *out = db;
+  return RP_OK;
+}
+
+void rp_db_free(rp_db* db) {
+  if (!db) return;
+  for (auto* dc : db->dev) free_device_ctx(dc);
+  delete db;
+}
+
+int rp_db_describe(const rp_db* db, rp_db_desc* out) {
+  if (!db || !out) return set_error(RP_E_INVALID, "NULL argument");
+  *out = db->desc;
+  return RP_OK;
+}
+
+int rp_db_device_bytes(const rp_db* db, uint64_t* table_bytes, uint64_t* block_bytes) {
+  if (!db) return set_error(RP_E_INVALID, "db is NULL");
+  if (table_bytes) *table_bytes = db->table_cap * 16;
+  if (block_bytes) *block_bytes = db->block_bytes;
+  return RP_OK;
+}
+
+double rp_last_kernel_ms(const rp_db* db) { return db ? db->last_kernel_ms.load() : 0.0; }
+
+// ---- .rgdb : flat little-endian export of the phylo-kmer DB (written by the Java exporter, or by
+// rp_db_save_file).  Layout (all sections 64 B aligned):
+//   [0,64)   header: char magic[8]="RGDB\0\0\0\1"; i32 alphabet,k,n_nodes; f32 thr_log10,thr_lin; i32 0;
+//                    u64 n_keys, n_postings; u64 off_keys, off_offsets, off_nodes  (off_scores follows)
+//   keys u64[n_keys] | offsets u64[n_keys+1] | post_node u16[n_postings] | post_score f32[n_postings]
+struct RgdbHeader {
+  char magic[8];
+  int32_t alphabet, k, n_nodes;
+  float thr_log10, thr_lin;
+  int32_t zero;
+  uint64_t n_keys, n_postings;
+  uint64_t off_keys, off_offsets, off_nodes, off_scores;
+};
+static_assert(sizeof(RgdbHeader) == 80, "header layout");
+static const char kMagic[8] = {'R', 'G', 'D', 'B', 0, 0, 0, 1};
+static uint64_t align64(uint64_t x) { return (x + 63) & ~63ull; }
+
+int rp_db_save_file(const char* path, const rp_db_desc* d, const uint64_t* keys, const uint64_t* offsets,
+                    const uint16_t* post_node, const float* post_score) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  RgdbHeader h;
+  memset(&h, 0, sizeof h);
+  memcpy(h.magic, kMagic, 8);
+  h.alphabet = d->alphabet; h.k = d->k; h.n_nodes = d->n_nodes; h.thr_log10 = d->thr_log10; h.thr_lin = d->thr_lin;
+  h.n_keys = d->n_keys; h.n_postings = d->n_postings;
+  h.off_keys = align64(sizeof h);
+  h.off_offsets = align64(h.off_keys + 8 * d->n_keys);
+  h.off_nodes = align64(h.off_offsets + 8 * (d->n_keys + 1));
+  h.off_scores = align64(h.off_nodes + 2 * d->n_postings);
+  FILE* f = fopen(path, "wb");
+  if (!f) return set_error(RP_E_IO, "cannot open %s for writing", path);
+  auto put = [&](uint64_t off, const void* p, uint64_t n) -> bool {
+    if (fseek(f, (long)off, SEEK_SET) != 0) return false;
+    return n == 0 || fwrite(p, 1, n, f) == n;
+  };
+  static const uint64_t zero_off[1] = {0};
+  bool ok = put(0, &h, sizeof h) && put(h.off_keys, keys, 8 * d->n_keys) &&
+            put(h.off_offsets, d->n_keys ? offsets : zero_off, 8 * (d->n_keys + 1)) &&
+            put(h.off_nodes, post_node, 2 * d->n_postings) && put(h.off_scores, post_score, 4 * d->n_postings);
+  ok = (fclose(f) == 0) && ok;
+  if (!ok) return set_error(RP_E_IO, "short write to %s", path);
+  return RP_OK;
+}
+
+int rp_db_load_file(const char* path, const int32_t* devices, int32_t n_devices, int32_t partitioned, rp_db** out) {
+  if (!path || !out) return set_error(RP_E_INVALID, "NULL argument");
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) return set_error(RP_E_IO, "cannot open %s", path);
+  struct stat st;
+  if (fstat(fd, &st) != 0 || (uint64_t)st.st_size < sizeof(RgdbHeader)) {
+    close(fd);
+    return set_error(RP_E_IO, "%s: too short for an .rgdb header", path);
+  }
+  void* m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (m == MAP_FAILED) return set_error(RP_E_IO, "mmap of %s failed", path);
+  const uint8_t* base = (const uint8_t*)m;
+  RgdbHeader h;
+  memcpy(&h, base, sizeof h);
+  int rc = RP_OK;
+  if (memcmp(h.magic, kMagic, 8) != 0) rc = set_error(RP_E_IO, "%s: bad magic (not an .rgdb v1 file)", path);
+  uint64_t need = h.off_scores + 4 * h.n_postings;
+  if (!rc && (h.off_keys < sizeof h || h.off_offsets < h.off_keys + 8 * h.n_keys ||
+              h.off_nodes < h.off_offsets + 8 * (h.n_keys + 1) || h.off_scores < h.off_nodes + 2 * h.n_postings ||
+              need > (uint64_t)st.st_size))
+    rc = set_error(RP_E_IO, "%s: section table inconsistent with file size", path);
+  if (!rc) {
+    rp_db_desc d;
+    memset(&d, 0, sizeof d);
+    d.alphabet = h.alphabet; d.k = h.k; d.n_nodes = h.n_nodes; d.thr_log10 = h.thr_log10; d.thr_lin = h.thr_lin;
+    d.n_keys = h.n_keys; d.n_postings = h.n_postings;
+    rc = rp_db_load(&d, (const uint64_t*)(base + h.off_keys), (const uint64_t*)(base + h.off_offsets),
+                    (const uint16_t*)(base + h.off_nodes), (const float*)(base + h.off_scores), devices, n_devices,
+                    partitioned, out);
+  }
+  munmap(m, (size_t)st.st_size);
+  return rc;
+}
+
+}  // extern "C"

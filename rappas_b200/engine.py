@@ -1,0 +1,138 @@
+"""Host-side handle on the GPU placement engine (thin ctypes layer over the C ABI).
+
+`Database.place()` is the batch equivalent of the per-read body of
+PlacementProcess.processQueries (core/algos/PlacementProcess.java:645-838, 974-1000); argument
+names follow ArgumentsParser_v2 (keep_at_most, keep_factor, ...).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from ._lib import check, load
+from .synth import ReadBatch
+
+
+class Database:
+    def __init__(self, handle, desc):
+        self._h = handle
+        self.desc = desc
+
+    # -- construction -------------------------------------------------------------------------
+    @classmethod
+    def from_arrays(cls, alphabet, k, n_nodes, thr_lin, thr_log10, keys, offsets, post_node, post_score,
+                    devices=(0,), partitioned=False):
+        fn = load()
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        post_node = np.ascontiguousarray(post_node, dtype=np.uint16)
+        post_score = np.ascontiguousarray(post_score, dtype=np.float32)
+        desc = _abi.RpDbDesc(int(alphabet), int(k), int(n_nodes), float(thr_log10), float(thr_lin), 0,
+                             keys.shape[0], post_node.shape[0])
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        h = C.c_void_p()
+        check(fn["db_load"](C.byref(desc), _abi.ptr(keys), _abi.ptr(offsets), _abi.ptr(post_node),
+                            _abi.ptr(post_score), _abi.ptr(dev), dev.shape[0], int(bool(partitioned)), C.byref(h)))
+        return cls(h, desc)
+
+    @classmethod
+    def from_synth(cls, db, devices=(0,)):
+        return cls.from_arrays(db.alphabet, db.k, db.n_nodes, db.thr_lin, db.thr_log10, db.keys, db.offsets,
+                               db.post_node, db.post_score, devices=devices)
+
+    @classmethod
+    def from_file(cls, path, devices=(0,), partitioned=False):
+        fn = load()
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        h = C.c_void_p()
+        check(fn["db_load_file"](str(path).encode(), _abi.ptr(dev), dev.shape[0], int(bool(partitioned)), C.byref(h)))
+        desc = _abi.RpDbDesc()
+        check(fn["db_describe"](h, C.byref(desc)))
+        return cls(h, desc)
+
+    def close(self):
+        if self._h:
+            load()["db_free"](self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- introspection ------------------------------------------------------------------------
+    @property
+    def k(self):
+        return self.desc.k
+
+    @property
+    def n_nodes(self):
+        return self.desc.n_nodes
+
+    def device_bytes(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        check(load()["db_device_bytes"](self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def last_kernel_ms(self):
+        return float(load()["last_kernel_ms"](self._h))
+
+    # -- hot path -----------------------------------------------------------------------------
+    def place(self, reads: ReadBatch, cfg=None, out=None, counts=True):
+        """-> dict(n_rows, node, score, lwr, counts, status) of numpy arrays (host)."""
+        cfg = cfg or _abi.place_cfg()
+        n, K = reads.n_reads, cfg.keep_at_most
+        if out is None:
+            out = {
+                "n_rows": np.empty(n, np.int32), "node": np.empty((n, K), np.uint16),
+                "score": np.empty((n, K), np.float32), "lwr": np.empty((n, K), np.float64),
+                "counts": np.empty((n, 4), np.int32) if counts else None, "status": np.empty(n, np.int32),
+            }
+        check(load()["place_batch"](self._h, C.byref(cfg), _abi.ptr(reads.seq), _abi.ptr(reads.seq_off), n,
+                                    _abi.ptr(out["n_rows"]), _abi.ptr(out["node"]), _abi.ptr(out["score"]),
+                                    _abi.ptr(out["lwr"]), _abi.ptr(out.get("counts")), _abi.ptr(out["status"])))
+        return out
+
+    def place_device(self, cfg, d_seq, d_seq_off, n_reads, d_n_rows, d_node, d_score, d_lwr, d_counts, d_status,
+                     stream=0, device_index=0):
+        """All arguments are raw device pointers (ints); enqueues on `stream` and returns."""
+        check(load()["place_batch_device"](self._h, int(device_index), C.byref(cfg), C.c_void_p(d_seq),
+                                           C.c_void_p(d_seq_off), int(n_reads), C.c_void_p(d_n_rows),
+                                           C.c_void_p(d_node), C.c_void_p(d_score), C.c_void_p(d_lwr),
+                                           C.c_void_p(d_counts) if d_counts else None, C.c_void_p(d_status),
+                                           C.c_void_p(stream) if stream else None))
+
+    def extract(self, reads: ReadBatch):
+        woff = reads.window_offsets(self.k)
+        nw = int(woff[-1])
+        out = {"win_off": woff, "code": np.zeros(nw, np.uint64), "kind": np.zeros(nw, np.uint8),
+               "nalt": np.zeros(nw, np.int32), "hits": np.zeros(nw, np.int32),
+               "status": np.zeros(reads.n_reads, np.int32)}
+        check(load()["extract_kmers"](self._h, _abi.ptr(reads.seq), _abi.ptr(reads.seq_off), reads.n_reads,
+                                      _abi.ptr(woff), _abi.ptr(out["code"]), _abi.ptr(out["kind"]),
+                                      _abi.ptr(out["nalt"]), _abi.ptr(out["hits"]), _abi.ptr(out["status"])))
+        return out
+
+    def node_scores(self, reads: ReadBatch, cfg=None):
+        cfg = cfg or _abi.place_cfg()
+        S = np.empty((reads.n_reads, self.n_nodes), np.float32)
+        check(load()["node_scores"](self._h, C.byref(cfg), _abi.ptr(reads.seq), _abi.ptr(reads.seq_off),
+                                    reads.n_reads, _abi.ptr(S), None))
+        return S
+
+
+def kernel_launch_count() -> int:
+    return int(load()["kernel_launch_count"]())
+
+
+def device_count() -> int:
+    return int(load()["device_count"]())
