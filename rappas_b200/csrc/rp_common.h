@@ -17,28 +17,50 @@ namespace rp {
 // ---------------------------------------------------------------------------------------------
 // HBM layout of the phylo-kmer DB (one copy per device; see DESIGN.md "Data layout")
 //
-//  table   : open-addressing, linear probing, capacity = pow2 >= 2*n_keys, 16 B slots
-//            slot = { u64 key, u64 meta },  meta = (block_offset_in_32B_units << 16) | n_postings
-//            empty slot: key == kEmptyKey.  One LDG.128 per probe.
+//  table   : static open addressing, 2-choice bucketed cuckoo placement.  n_buckets = pow2 >= n_keys,
+//            bucket = 2 slots = 32 B = one DRAM/L2 sector, slot = { u64 key, u64 meta } (16 B),
+//            meta = (block_offset_in_32B_units << 16) | n_postings, empty slot: key == kEmptyKey.
+//            A key lives in bucket b1(key) or b2(key); a lookup issues the four LDG.128 of both
+//            buckets up front and never loops, so all 32 lanes of a warp finish in one memory round
+//            trip (linear probing makes a warp wait for its slowest lane: 4-5 dependent rounds).
+//            Stored keys are in the kernel's PLANAR form (see planar_from_code).
 //  blocks  : posting blocks, 32 B aligned.  A key with P postings (sorted by node id at load) is a
 //            run of sub-blocks of up to 32 postings; sub-block i starts at block + 192*i and holds
 //            m = min(32, P-32i) entries as [m x f32 score][m x u16 node]  (SoA inside the sub-block:
-//            a warp reads 128 B of scores + 64 B of nodes, both coalesced).  The block is padded to
-//            a multiple of 32 B so that a gather touches whole sectors only.
+//            a warp reads 128 B of scores + 64 B of nodes, both conflict-free).  The block is padded
+//            to a multiple of 32 B = roundup32(6*P): whole sectors, and a legal cp.async.bulk size.
 // ---------------------------------------------------------------------------------------------
 constexpr uint64_t kEmptyKey = ~0ull;
 constexpr int kSubBlock = 32;             // postings per sub-block
 constexpr int kSubBlockBytes = 32 * 6;    // 192
 constexpr int kBlockAlign = 32;           // bytes
+constexpr int kBucketSlots = 2;
+constexpr uint64_t kMinBuckets = 32;
 
 __host__ __device__ inline uint64_t block_bytes_for(uint64_t n_postings) {
-  uint64_t b = (n_postings / kSubBlock) * kSubBlockBytes + (n_postings % kSubBlock) * 6;
-  return (b + kBlockAlign - 1) / kBlockAlign * kBlockAlign;
+  return (n_postings * 6 + kBlockAlign - 1) / kBlockAlign * kBlockAlign;
 }
 
-__host__ __device__ inline uint64_t mix64(uint64_t x) {
-  x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+// 32-bit avalanche (lowbias32) of the folded key; the two bucket indices are the top bits of the
+// mix and of a second multiplicative hash of the mix.
+__host__ __device__ inline uint32_t mix_key(uint64_t key) {
+  uint32_t x = (uint32_t)key ^ ((uint32_t)(key >> 32) * 0x9E3779B1u);
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
   return x;
+}
+__host__ __device__ inline uint32_t bucket1(uint32_t mix, int shift) { return mix >> shift; }
+__host__ __device__ inline uint32_t bucket2(uint32_t mix, int shift) { return (mix * 0x9E3779B1u + 0x7F4A7C15u) >> shift; }
+
+// ABI k-mer code (state i in bits [bits*i, bits*i+bits)) -> planar key (bit p of state i at bit
+// p*k + i).  The kernel gets the planes of 32 windows from `bits` pairs of __ballot_sync and one
+// funnel shift each instead of a k-step loop per window.
+__host__ __device__ inline uint64_t planar_from_code(uint64_t code, int bits, int k) {
+  uint64_t key = 0;
+  for (int i = 0; i < k; i++) {
+    const uint64_t st = (code >> (bits * i)) & ((1u << bits) - 1u);
+    for (int p = 0; p < bits; p++) key |= ((st >> p) & 1ull) << (p * k + i);
+  }
+  return key;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -69,8 +91,8 @@ int  max_ambig_per_mer(int alphabet, int k);  // AmbigSequenceKnife.java:95
 // device-side views passed to kernels by value
 // ---------------------------------------------------------------------------------------------
 struct DbView {
-  const uint4* table;
-  uint64_t mask;
+  const uint4* table;       // [n_buckets][2] slots
+  int bucket_shift;         // 32 - log2(n_buckets)
   const uint8_t* blocks;
   int alphabet, k, bits, n_nodes, max_amb;
   float T, Tlin;
@@ -115,7 +137,8 @@ struct StreamCtx {
 struct LaunchGeom {
   int warps_per_cta = 0, ctas_per_sm = 0, grid = 0;
   size_t smem_bytes = 0, per_warp_bytes = 0;
-  int n_pad = 0;
+  int n_pad = 0;        // S[] entries per warp, multiple of 128
+  int stage_bytes = 0;  // one posting staging buffer (two per warp), multiple of 128
 };
 
 struct DeviceCtx {
@@ -134,8 +157,9 @@ struct DeviceCtx {
 
 struct rp_db {
   rp_db_desc desc{};
-  uint64_t table_cap = 0;
+  uint64_t n_buckets = 0;
   uint64_t block_bytes = 0;
+  uint64_t max_block_bytes = 0;
   int partitioned = 0;
   rp::AlphabetTables alpha{};
   std::vector<rp::DeviceCtx*> dev;

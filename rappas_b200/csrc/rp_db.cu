@@ -85,10 +85,12 @@ void build_alphabet_tables(int alphabet, AlphabetTables* t) {
   }
 }
 
+static int log2_u64(uint64_t x) { int l = 0; while ((1ull << l) < x) l++; return l; }
+
 DbView make_db_view(const rp_db* db, const DeviceCtx* dc) {
   DbView v;
   v.table = dc->d_table;
-  v.mask = db->table_cap - 1;
+  v.bucket_shift = 32 - log2_u64(db->n_buckets);
   v.blocks = dc->d_blocks;
   v.alphabet = db->desc.alphabet;
   v.k = db->desc.k;
@@ -112,11 +114,31 @@ static int check_desc(const rp_db_desc* d) {
 
 // ---- host build of table + blocks (multi-threaded over key ranges) ------------------------------
 struct HostImage {
-  std::vector<uint64_t> table;   // 2 u64 per slot
+  std::vector<uint64_t> table;   // 2 u64 per slot, 2 slots per bucket
   uint8_t* blocks = nullptr;     // malloc'd, block_bytes
-  uint64_t table_cap = 0, block_bytes = 0;
+  uint64_t n_buckets = 0, block_bytes = 0, max_block_bytes = 0;
   ~HostImage() { free(blocks); }
 };
+
+// Serial cuckoo insertion of the keys the greedy parallel pass could not place: random-walk
+// eviction between a key's two buckets.  At load <= 0.5 with 2x2 buckets this is a handful of keys.
+static bool cuckoo_insert(std::vector<uint64_t>& tab, int shift, uint64_t key, uint64_t meta, uint64_t* rng) {
+  for (int kick = 0; kick < 2000; kick++) {
+    const uint32_t m = mix_key(key);
+    const uint32_t b[2] = {bucket1(m, shift), bucket2(m, shift)};
+    for (int c = 0; c < 2; c++)
+      for (int s = 0; s < kBucketSlots; s++) {
+        uint64_t* slot = &tab[2 * ((uint64_t)b[c] * kBucketSlots + s)];
+        if (slot[0] == kEmptyKey) { slot[0] = key; slot[1] = meta; return true; }
+      }
+    *rng = *rng * 6364136223846793005ull + 1442695040888963407ull;
+    const uint32_t pick = (uint32_t)(*rng >> 33);
+    uint64_t* victim = &tab[2 * ((uint64_t)b[pick & 1] * kBucketSlots + ((pick >> 1) & 1))];
+    std::swap(key, victim[0]);
+    std::swap(meta, victim[1]);
+  }
+  return false;
+}
 
 static int build_image(const rp_db_desc* d, const uint64_t* keys, const uint64_t* offsets, const uint16_t* post_node,
                        const float* post_score, HostImage* img) {
@@ -124,21 +146,27 @@ static int build_image(const rp_db_desc* d, const uint64_t* keys, const uint64_t
   if (offsets && nk && offsets[nk] != d->n_postings)
     return set_error(RP_E_INVALID, "offsets[n_keys]=%llu != n_postings=%llu", (unsigned long long)offsets[nk],
                      (unsigned long long)d->n_postings);
-  uint64_t cap = 64;
-  while (cap < 2 * nk) cap <<= 1;
-  img->table_cap = cap;
-  img->table.assign(2 * cap, 0);
-  for (uint64_t i = 0; i < cap; i++) img->table[2 * i] = kEmptyKey;
+  uint64_t nb = kMinBuckets;
+  while (nb < nk) nb <<= 1;  // 2 slots per bucket -> load factor in (0.25, 0.5]
+  if (nb > (1ull << 31)) return set_error(RP_E_UNSUPPORTED, "n_keys=%llu: more than 2^31 buckets", (unsigned long long)nk);
+  const int shift = 32 - log2_u64(nb);
+  img->n_buckets = nb;
+  const uint64_t n_slots = nb * kBucketSlots;
+  img->table.assign(2 * n_slots, 0);
+  for (uint64_t i = 0; i < n_slots; i++) img->table[2 * i] = kEmptyKey;
   // block offsets (32 B units)
   std::vector<uint64_t> boff(nk + 1, 0);
+  uint64_t max_bb = 0;
   for (uint64_t i = 0; i < nk; i++) {
     if (offsets[i + 1] < offsets[i]) return set_error(RP_E_INVALID, "offsets not monotone at key %llu", (unsigned long long)i);
     uint64_t P = offsets[i + 1] - offsets[i];
     if (P > 65535) return set_error(RP_E_INVALID, "key %llu has %llu postings (> 65535)", (unsigned long long)i, (unsigned long long)P);
     boff[i + 1] = boff[i] + block_bytes_for(P) / kBlockAlign;
+    max_bb = std::max(max_bb, block_bytes_for(P));
   }
   if (boff[nk] >= (1ull << 48)) return set_error(RP_E_INVALID, "posting blocks exceed 2^48 * 32 B");
   img->block_bytes = boff[nk] * kBlockAlign;
+  img->max_block_bytes = max_bb;
   img->blocks = (uint8_t*)calloc(img->block_bytes ? img->block_bytes : 32, 1);
   if (!img->blocks) return set_error(RP_E_NOMEM, "cannot allocate %llu B for posting blocks", (unsigned long long)img->block_bytes);
 
@@ -146,11 +174,14 @@ static int build_image(const rp_db_desc* d, const uint64_t* keys, const uint64_t
   if (nk < 4096) nt = 1;
   std::atomic<int> err{0};
   const int n_nodes = d->n_nodes;
-  auto pack_range = [&](uint64_t k0, uint64_t k1) {
+  const int bits = alphabet_bits(d->alphabet), k = d->k;
+  const uint64_t code_limit = (bits * k >= 64) ? ~0ull : (1ull << (bits * k));
+  std::vector<std::vector<std::pair<uint64_t, uint64_t>>> leftover(nt);
+  auto pack_range = [&](unsigned tid, uint64_t k0, uint64_t k1) {
     std::vector<std::pair<uint16_t, float>> tmp;
     for (uint64_t i = k0; i < k1 && !err.load(std::memory_order_relaxed); i++) {
       const uint64_t lo = offsets[i], P = offsets[i + 1] - offsets[i];
-      if (keys[i] == kEmptyKey) { err = 4; return; }
+      if (keys[i] == kEmptyKey || keys[i] >= code_limit) { err = 4; return; }
       tmp.resize(P);
       bool sorted = true;
       for (uint64_t p = 0; p < P; p++) {
@@ -172,33 +203,51 @@ static int build_image(const rp_db_desc* d, const uint64_t* keys, const uint64_t
         uint16_t* nd = (uint16_t*)((uint8_t*)sc + 4 * m);
         for (uint64_t q = 0; q < m; q++) { sc[q] = tmp[base + q].second; nd[q] = tmp[base + q].first; }
       }
-      // insert into the table (lock-free: CAS on the key word, then publish meta)
-      uint64_t meta = (boff[i] << 16) | P;
-      uint64_t h = mix64(keys[i]) & (cap - 1);
-      for (;;) {
-        uint64_t* slot = &img->table[2 * h];
-        uint64_t expect = kEmptyKey;
-        if (__atomic_compare_exchange_n(slot, &expect, keys[i], false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) {
-          slot[1] = meta;
-          break;
+      // greedy 2-choice placement (lock-free: CAS on the key word, then publish meta)
+      const uint64_t key = planar_from_code(keys[i], bits, k);
+      const uint64_t meta = (boff[i] << 16) | P;
+      const uint32_t m32 = mix_key(key);
+      const uint32_t bk[2] = {bucket1(m32, shift), bucket2(m32, shift)};
+      bool placed = false;
+      for (int c = 0; c < 2 && !placed; c++)
+        for (int s = 0; s < kBucketSlots && !placed; s++) {
+          uint64_t* slot = &img->table[2 * ((uint64_t)bk[c] * kBucketSlots + s)];
+          uint64_t expect = kEmptyKey;
+          if (__atomic_compare_exchange_n(slot, &expect, key, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) {
+            slot[1] = meta;
+            placed = true;
+          } else if (expect == key) { err = 3; return; }
         }
-        if (expect == keys[i]) { err = 3; return; }
-        h = (h + 1) & (cap - 1);
-      }
+      if (!placed) leftover[tid].push_back({key, meta});
     }
   };
   if (nt == 1) {
-    pack_range(0, nk);
+    pack_range(0, 0, nk);
   } else {
     std::vector<std::thread> th;
-    for (unsigned t = 0; t < nt; t++) th.emplace_back(pack_range, nk * t / nt, nk * (t + 1) / nt);
+    for (unsigned t = 0; t < nt; t++) th.emplace_back(pack_range, t, nk * t / nt, nk * (t + 1) / nt);
     for (auto& x : th) x.join();
+  }
+  if (!err.load()) {
+    uint64_t rng = 0x243F6A8885A308D3ull;
+    for (auto& lv : leftover)
+      for (auto& kv : lv) {
+        // a key stays inside its own two buckets for ever, so a duplicate is visible there
+        const uint32_t m32 = mix_key(kv.first);
+        const uint32_t bk[2] = {bucket1(m32, shift), bucket2(m32, shift)};
+        for (int c = 0; c < 2; c++)
+          for (int s = 0; s < kBucketSlots; s++)
+            if (img->table[2 * ((uint64_t)bk[c] * kBucketSlots + s)] == kv.first) err = 3;
+        if (err.load()) break;
+        if (!cuckoo_insert(img->table, shift, kv.first, kv.second, &rng)) { err = 5; break; }
+      }
   }
   switch (err.load()) {
     case 1: return set_error(RP_E_INVALID, "posting node id >= n_nodes");
     case 2: return set_error(RP_E_INVALID, "a key lists the same node twice");
     case 3: return set_error(RP_E_INVALID, "duplicate key");
-    case 4: return set_error(RP_E_INVALID, "key 0xFFFFFFFFFFFFFFFF is reserved");
+    case 4: return set_error(RP_E_INVALID, "key out of range for this alphabet and k (or the reserved 0xFFFFFFFFFFFFFFFF)");
+    case 5: return set_error(RP_E_NOMEM, "cuckoo placement failed (table too dense)");
     default: break;
   }
   return RP_OK;
@@ -280,8 +329,9 @@ int rp_db_load(const rp_db_desc* desc, const uint64_t* keys, const uint64_t* off
 
   rp_db* db = new rp_db();
   db->desc = *desc;
-  db->table_cap = img.table_cap;
+  db->n_buckets = img.n_buckets;
   db->block_bytes = img.block_bytes;
+  db->max_block_bytes = img.max_block_bytes;
   db->partitioned = 0;
   build_alphabet_tables(desc->alphabet, &db->alpha);
   for (int i = 0; i < n_devices; i++) {
@@ -294,16 +344,16 @@ int rp_db_load(const rp_db_desc* desc, const uint64_t* keys, const uint64_t* off
     if (e == cudaSuccess) {
       dc->sm_count = prop.multiProcessorCount;
       dc->smem_optin = prop.sharedMemPerBlockOptin;
-      e = cudaMalloc((void**)&dc->d_table, img.table_cap * 16);
+      e = cudaMalloc((void**)&dc->d_table, img.n_buckets * 32);
     }
     if (e == cudaSuccess) e = cudaMalloc((void**)&dc->d_blocks, img.block_bytes ? img.block_bytes : 32);
-    if (e == cudaSuccess) e = cudaMemcpy(dc->d_table, img.table.data(), img.table_cap * 16, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dc->d_table, img.table.data(), img.n_buckets * 32, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && img.block_bytes)
       e = cudaMemcpy(dc->d_blocks, img.blocks, img.block_bytes, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {
       int code = (e == cudaErrorMemoryAllocation) ? RP_E_NOMEM : RP_E_CUDA;
       set_error(code, "device %d: %s while uploading the DB (%llu B table + %llu B blocks)", dc->device,
-                cudaGetErrorString(e), (unsigned long long)(img.table_cap * 16), (unsigned long long)img.block_bytes);
+                cudaGetErrorString(e), (unsigned long long)(img.n_buckets * 32), (unsigned long long)img.block_bytes);
       cudaGetLastError();
       rp_db_free(db);
       return code;
@@ -329,7 +379,7 @@ int rp_db_describe(const rp_db* db, rp_db_desc* out) {
 
 int rp_db_device_bytes(const rp_db* db, uint64_t* table_bytes, uint64_t* block_bytes) {
   if (!db) return set_error(RP_E_INVALID, "db is NULL");
-  if (table_bytes) *table_bytes = db->table_cap * 16;
+  if (table_bytes) *table_bytes = db->n_buckets * 32;
   if (block_bytes) *block_bytes = db->block_bytes;
   return RP_OK;
 }

@@ -10,16 +10,23 @@
 //   K4  selection + LWR         fillBestScoreList (:396-451), computeWeightRatio[Shift] (:384-394),
 //                               row loop (:974-1000)
 //
-// Execution model: ONE WARP OWNS ONE READ.  The warp keeps the read's score
-// vector S[n_nodes] in shared memory, walks the windows in order, and for every matched k-mer
-// gathers the posting block and adds it into S with plain (non-atomic) shared-memory
-// read-modify-writes: node ids are distinct inside a k-mer's posting list, so the 32 lanes of one
-// instruction never collide, and because a node receives at most one posting per window and the
-// windows are visited in order, every S[x] is accumulated in exactly the reference's f32 order
-// (bit-exact scores, no atomics).  Untouched entries hold a NaN sentinel; "first touch"
-// (C[x]==0 in the reference) is `S[x] is the sentinel`.
+// Execution model: ONE WARP OWNS ONE READ and runs a two-stage software pipeline over
+// GROUPS of up to 32 consecutive windows:
+//   front(i+1)  classify 64 characters, build the 32 planar k-mer keys from ballots, probe the cuckoo
+//               table (both buckets, one memory round trip), prefix-sum the posting-block sizes and
+//               issue one cp.async.bulk (TMA) per matched window into a per-warp shared-memory stage,
+//               completion counted on an mbarrier;
+//   drain(i)    wait for stage i, then add the posting blocks into the read's score vector S[n_nodes]
+//               (shared memory) window by window.
+// so the gathers of group i+1 are in flight while group i is being accumulated (two stages per warp).
+// The accumulation uses plain (non-atomic) shared-memory read-modify-writes: node ids are distinct
+// inside a k-mer's posting list, so the 32 lanes of one instruction never collide, and because a node
+// receives at most one posting per window and the windows are visited in order, every S[x] is
+// accumulated in exactly the reference's f32 order (bit-exact scores, no atomics).  Untouched entries
+// hold a NaN sentinel; "first touch" (C[x]==0 in the reference) is `S[x] is the sentinel`.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -31,21 +38,45 @@ namespace rp {
 
 constexpr uint32_t kSentinelBits = 0x7FFFFFFFu;  // a NaN no arithmetic here produces
 constexpr int kMaxWarpsPerCta = 16;
-constexpr int kMaxWarpsPerSm = 32;  // 64 registers per thread stay available
+constexpr int kMaxWarpsPerSm = 32;
+
+// ------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (TMA, SASS UBLKCP); dst/src 16 B aligned, bytes % 16 == 0
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------ helpers
-__device__ __forceinline__ bool table_probe(const DbView& db, uint64_t code, uint64_t& meta) {
-  uint64_t h = mix64(code) & db.mask;
-  for (;;) {
-    const uint4 s = __ldg(db.table + h);
-    const uint64_t key = (uint64_t)s.x | ((uint64_t)s.y << 32);
-    if (key == code) {
-      meta = (uint64_t)s.z | ((uint64_t)s.w << 32);
-      return true;
-    }
-    if (key == kEmptyKey) return false;
-    h = (h + 1) & db.mask;
-  }
+// Cuckoo lookup: both candidate buckets (2 x 2 slots of 16 B) are loaded unconditionally.
+__device__ __forceinline__ bool table_probe(const DbView& db, uint64_t key, uint64_t& meta) {
+  const uint32_t m = mix_key(key);
+  const uint4* p1 = db.table + (size_t)bucket1(m, db.bucket_shift) * kBucketSlots;
+  const uint4* p2 = db.table + (size_t)bucket2(m, db.bucket_shift) * kBucketSlots;
+  const uint4 s0 = __ldg(p1), s1 = __ldg(p1 + 1), s2 = __ldg(p2), s3 = __ldg(p2 + 1);
+  const uint32_t klo = (uint32_t)key, khi = (uint32_t)(key >> 32);
+  const bool h0 = s0.x == klo && s0.y == khi, h1 = s1.x == klo && s1.y == khi;
+  const bool h2 = s2.x == klo && s2.y == khi, h3 = s3.x == klo && s3.y == khi;
+  const uint32_t z = h0 ? s0.z : h1 ? s1.z : h2 ? s2.z : s3.z;
+  const uint32_t w = h0 ? s0.w : h1 ? s1.w : h2 ? s2.w : s3.w;
+  meta = (uint64_t)z | ((uint64_t)w << 32);
+  return h0 | h1 | h2 | h3;
 }
 
 __device__ __forceinline__ bool is_sentinel(float s) { return __float_as_uint(s) == kSentinelBits; }
@@ -55,28 +86,56 @@ __device__ __forceinline__ bool better(float sa, int xa, float sb, int xb) {
   return sa > sb || (sa == sb && xa < xb);
 }
 
+// planar key of the window whose k class bytes start at c (slow path: ambiguity alternatives, diagnostics)
+__device__ __forceinline__ uint64_t planar_from_states(const uint8_t* c, int k, int bits, int o1, unsigned st1, int o2,
+                                                       unsigned st2, uint64_t* abi_code) {
+  uint64_t key = 0, code = 0;
+  for (int i = 0; i < k; i++) {
+    unsigned st = c[i];
+    if (i == o1) st = st1;
+    else if (i == o2) st = st2;
+    code |= (uint64_t)st << (bits * i);
+    for (int p = 0; p < bits; p++) key |= (uint64_t)((st >> p) & 1u) << (p * k + i);
+  }
+  if (abi_code) *abi_code = code;
+  return key;
+}
+
 struct WarpSmem {
-  float* S;        // [n_pad]
-  uint8_t* flag;   // [n_pad/32]  1 = some node of this 32-node block was touched
-  uint8_t* cls;    // [64] character classes of the current 32-window group (+ look-ahead)
+  float* S;          // [n_pad]
+  uint8_t* cls;      // [2][64] character classes of the two groups in flight
+  uint8_t* stage;    // [2][stage_bytes] posting blocks staged by TMA
+  uint32_t bar;      // shared-space address of mbarrier[2]
+  int stage_bytes;
 };
 
-// Adds one posting block into S, in order.  PlacementProcess.java:719-735.
-__device__ __forceinline__ void accumulate_block(const DbView& db, const WarpSmem& w, uint64_t meta, float QT0,
-                                                 int lane) {
-  const int len = (int)(meta & 0xFFFF);
-  const uint8_t* p = db.blocks + (meta >> 16) * kBlockAlign;
+// Adds one posting block that sits in shared memory into S, in order.  PlacementProcess.java:719-735.
+__device__ __forceinline__ void accumulate_staged(float* __restrict__ S, const uint8_t* p, int len, float QT0, float T,
+                                                  int lane) {
+  for (int base = 0; base < len; base += kSubBlock, p += kSubBlockBytes) {
+    const int m = min(kSubBlock, len - base);
+    if (lane < m) {
+      const float v = *reinterpret_cast<const float*>(p + 4 * lane);
+      const unsigned x = *reinterpret_cast<const unsigned short*>(p + 4 * m + 2 * lane);
+      float s = S[x];
+      if (is_sentinel(s)) s = QT0;                 // C[x]==0 : L.add(x); S[x]+=Q*T   (:726-729)
+      S[x] = __fadd_rn(s, __fsub_rn(v, T));       // S[x]+= v - T   (:733)
+    }
+    __syncwarp();
+  }
+}
+
+// Same from global memory: posting lists larger than a stage, and the ambiguity path.
+__device__ __forceinline__ void accumulate_global(float* __restrict__ S, const uint8_t* p, int len, float QT0, float T,
+                                                  int lane) {
   for (int base = 0; base < len; base += kSubBlock, p += kSubBlockBytes) {
     const int m = min(kSubBlock, len - base);
     if (lane < m) {
       const float v = __ldg((const float*)p + lane);
       const unsigned x = __ldg((const unsigned short*)(p + 4 * m) + lane);
-      float s = w.S[x];
-      if (is_sentinel(s)) {  // C[x]==0 : L.add(x); S[x]+=Q*T   (:726-729)
-        s = QT0;
-        w.flag[x >> 5] = 1;
-      }
-      w.S[x] = __fadd_rn(s, __fsub_rn(v, db.T));  // S[x]+= v - T   (:733)
+      float s = S[x];
+      if (is_sentinel(s)) s = QT0;
+      S[x] = __fadd_rn(s, __fsub_rn(v, T));
     }
     __syncwarp();
   }
@@ -84,30 +143,26 @@ __device__ __forceinline__ void accumulate_block(const DbView& db, const WarpSme
 
 // One ambiguous window (<= max_amb ambiguous residues): treatAmbiguitiesWithMean / WithMax,
 // PlacementProcess.java:1129-1174 / 1185-1236.  Rare path; S_amb/C_amb live in a per-warp global
-// scratch that is all-zero between calls.
-__device__ __noinline__ void ambiguous_window(const AlphabetTables& c_alpha, const DbView& db, const CfgView& cfg, const WarpSmem& w, int l,
-                                              uint32_t wbits, int Q, float QT, float* Sa, int* Ca, int lane) {
+// scratch that is all-zero between calls.  `cls` = class bytes of the window's first character on.
+__device__ __noinline__ void ambiguous_window(const AlphabetTables& c_alpha, const DbView& db, const CfgView& cfg,
+                                              float* __restrict__ S, const uint8_t* cls, uint32_t wbits, float QT,
+                                              float* Sa, int* Ca, int lane) {
   // ambiguous offsets inside the window (ascending) and their alternative sets
   const int o1 = __ffs(wbits) - 1;
   const uint32_t rest = wbits & (wbits - 1);
   const int o2 = rest ? __ffs(rest) - 1 : -1;
-  const int id1 = w.cls[l + o1] & 0x3F;
+  const int id1 = cls[o1] & 0x3F;
   const int n1 = c_alpha.alt_n[id1];
-  const int id2 = o2 >= 0 ? (w.cls[l + o2] & 0x3F) : 0;
+  const int id2 = o2 >= 0 ? (cls[o2] & 0x3F) : 0;
   const int n2 = o2 >= 0 ? c_alpha.alt_n[id2] : 1;
   const int n = n1 * n2;  // W_size ; <= 20 (amino) / 16 (nucl, 2 ambiguities)
   // alternative t (lane t): position o_m takes A_m[t mod |A_m|]  (AmbigSequenceKnife.java:249-256)
   uint64_t meta = 0;
   bool found = false;
   if (lane < n) {
-    uint64_t code = 0;
-    for (int i = 0; i < db.k; i++) {
-      unsigned st = w.cls[l + i];
-      if (i == o1) st = c_alpha.alt_states[id1][lane % n1];
-      else if (i == o2) st = c_alpha.alt_states[id2][lane % n2];
-      code |= (uint64_t)st << (db.bits * i);
-    }
-    found = table_probe(db, code, meta);
+    const uint64_t key = planar_from_states(cls, db.k, db.bits, o1, c_alpha.alt_states[id1][lane % n1], o2,
+                                            c_alpha.alt_states[id2][lane % n2], nullptr);
+    found = table_probe(db, key, meta);
   }
   const uint32_t fm = __ballot_sync(0xffffffffu, found);
   if (!fm) return;
@@ -151,11 +206,8 @@ __device__ __noinline__ void ambiguous_window(const AlphabetTables& c_alpha, con
         const int c = __ldcg(Ca + x);
         if (c != 0) {
           const float sa = __ldcg(Sa + x);
-          float s = w.S[x];
-          if (is_sentinel(s)) {  // S[x]=Q*T  (:1163-1166)
-            s = QT;
-            w.flag[x >> 5] = 1;
-          }
+          float s = S[x];
+          if (is_sentinel(s)) s = QT;  // S[x]=Q*T  (:1163-1166)
           if (cfg.amb_with_max) {
             s = __fadd_rn(s, __fsub_rn(sa, db.T));  // :1230
           } else {
@@ -164,7 +216,7 @@ __device__ __noinline__ void ambiguous_window(const AlphabetTables& c_alpha, con
             // S[x]+=Math.log10(avgProba)-PPStarThresholdAsLog10;   f32 += f64   (:1169)
             s = (float)((double)s + (log10((double)avg) - (double)db.T));
           }
-          w.S[x] = s;
+          S[x] = s;
           __stcg(Ca + x, 0);
           __stcg(Sa + x, 0.0f);
         }
@@ -174,45 +226,75 @@ __device__ __noinline__ void ambiguous_window(const AlphabetTables& c_alpha, con
   }
 }
 
-// K4.  Scans the touched 32-node blocks, keeps the K best (score desc, node asc) spread over lanes
-// 0..K-1, resets S to the sentinel, then computes LWRs and writes the rows.
-// fillBestScoreList (:396-451) + row loop (:974-1000).  `emit` = false only resets (bad read).
-__device__ __forceinline__ int select_and_reset(const DbView& db, const CfgView& cfg, const WarpSmem& w, int n_pad,
-                                                bool emit, float* dump_row, uint16_t* out_node, float* out_score,
+// order-preserving float -> uint (for REDUX.MAX); NaN never reaches it
+__device__ __forceinline__ uint32_t ordered_u32(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// K4.  fillBestScoreList (:396-451) + row loop (:974-1000).  Two passes over S:
+//   1. every lane takes the maximum of its own nodes; the K-th largest of the 32 lane maxima is a
+//      lower bound tau of the K-th best score (K distinct nodes reach it);
+//   2. nodes with score >= tau (a handful) go through a warp-shuffle insertion into the top-K list
+//      (lane i holds the i-th best; order: score desc, node id asc), and S is reset to the sentinel.
+// `emit` = false only resets (bad read).  Returns rows written, or -1 if no node was touched.
+__device__ __forceinline__ int select_and_reset(const CfgView& cfg, float* __restrict__ S, int n_pad, bool emit,
+                                                float* dump_row, int n_nodes, uint16_t* out_node, float* out_score,
                                                 double* out_lwr, int lane) {
   const int K = cfg.K;
+  const float4 sent4 = make_float4(__uint_as_float(kSentinelBits), __uint_as_float(kSentinelBits),
+                                   __uint_as_float(kSentinelBits), __uint_as_float(kSentinelBits));
+  if (!emit) {
+    for (int i = lane * 4; i < n_pad; i += 128) *reinterpret_cast<float4*>(S + i) = sent4;
+    __syncwarp();
+    return 0;
+  }
+  float m = -INFINITY;  // fmaxf ignores the NaN sentinel
+  for (int i = lane * 4; i < n_pad; i += 128) {
+    const float4 q = *reinterpret_cast<const float4*>(S + i);
+    m = fmaxf(m, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
+  }
+  float tau = -INFINITY;
+  {
+    uint32_t t = ordered_u32(m);
+    const uint32_t floor_u = ordered_u32(-INFINITY);
+    for (int j = 0; j < K; j++) {
+      const uint32_t mx = __reduce_max_sync(0xffffffffu, t);
+      if (mx == floor_u) { tau = -INFINITY; break; }
+      tau = __uint_as_float((mx & 0x80000000u) ? (mx & 0x7FFFFFFFu) : ~mx);
+      const uint32_t holders = __ballot_sync(0xffffffffu, t == mx);
+      if (lane == __ffs(holders) - 1) t = floor_u;
+    }
+  }
   float top_s = -INFINITY;  // lane i holds the i-th best so far (valid for i < cnt)
   int top_x = 0xFFFF;
   int cnt = 0;
-  const int n_blocks = n_pad >> 5;
-  for (int b0 = 0; b0 < n_blocks; b0 += 32) {
-    const int bi = b0 + lane;
-    const bool f = bi < n_blocks && w.flag[bi] != 0;
-    uint32_t fm = __ballot_sync(0xffffffffu, f);
-    if (f) w.flag[bi] = 0;
-    while (fm) {
-      const int b = b0 + __ffs(fm) - 1;
-      fm &= fm - 1;
-      const int x = (b << 5) + lane;
-      const float s = w.S[x];
-      const bool touched = !is_sentinel(s);
-      if (touched) {
-        w.S[x] = __uint_as_float(kSentinelBits);
-        if (dump_row) dump_row[x] = s;
-      }
-      if (!emit) continue;
-      // candidates that can enter the current top-K
-      float tau_s = __shfl_sync(0xffffffffu, top_s, K - 1);
-      int tau_x = __shfl_sync(0xffffffffu, top_x, K - 1);
-      uint32_t pm = __ballot_sync(0xffffffffu, touched && (cnt < K || better(s, x, tau_s, tau_x)));
+  for (int i0 = 0; i0 < n_pad; i0 += 128) {
+    const int i = i0 + lane * 4;
+    const float4 q = *reinterpret_cast<const float4*>(S + i);
+    *reinterpret_cast<float4*>(S + i) = sent4;
+    if (dump_row) {
+      const float qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int c = 0; c < 4; c++)
+        if (i + c < n_nodes && !is_sentinel(qq[c])) dump_row[i + c] = qq[c];
+    }
+    // NaN >= tau is false: untouched nodes never qualify
+    const bool c0 = q.x >= tau, c1 = q.y >= tau, c2 = q.z >= tau, c3 = q.w >= tau;
+    if (!__any_sync(0xffffffffu, c0 | c1 | c2 | c3)) continue;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const float s = c == 0 ? q.x : c == 1 ? q.y : c == 2 ? q.z : q.w;
+      const bool cand = c == 0 ? c0 : c == 1 ? c1 : c == 2 ? c2 : c3;
+      uint32_t pm = __ballot_sync(0xffffffffu, cand);
       while (pm) {
         const int src = __ffs(pm) - 1;
         pm &= pm - 1;
         const float cs = __shfl_sync(0xffffffffu, s, src);
-        const int cx = __shfl_sync(0xffffffffu, x, src);
-        if (cnt >= K) {  // threshold may have moved since the ballot
-          tau_s = __shfl_sync(0xffffffffu, top_s, K - 1);
-          tau_x = __shfl_sync(0xffffffffu, top_x, K - 1);
+        const int cx = i0 + src * 4 + c;
+        if (cnt >= K) {
+          const float tau_s = __shfl_sync(0xffffffffu, top_s, K - 1);
+          const int tau_x = __shfl_sync(0xffffffffu, top_x, K - 1);
           if (!better(cs, cx, tau_s, tau_x)) continue;
         }
         // insertion position = number of kept entries that beat the candidate
@@ -227,7 +309,6 @@ __device__ __forceinline__ int select_and_reset(const DbView& db, const CfgView&
     }
   }
   __syncwarp();
-  if (!emit) return 0;
   const int nb = cnt;  // numberOfBestScoreToConsiderForOutput = min(keepAtMost, |L|)  (:828-832)
   if (nb == 0) return -1;
   const float best = __shfl_sync(0xffffffffu, top_s, 0);
@@ -235,16 +316,17 @@ __device__ __forceinline__ int select_and_reset(const DbView& db, const CfgView&
   // computeWeightRatioShift(lowest,best): shift = best iff -308f >= lowest  (:384-390).  In
   // fillBestScoreList `lowest` starts at 0.0f (:413): min(0,lowest) <= -308  <=>  lowest <= -308.
   const float shift = (-308.0f >= lowest) ? best : 0.0f;
-  double e = 0.0;
+  // computeWeightRatio: Math.pow(10.0,(double)(s.score-weightRatioShift))/sum with a double shift (:392-393)
+  double num = 0.0, e = 0.0;
   if (lane < nb) {
-    if (shift != 0.0f) e = pow(10.0, (double)__fsub_rn(top_s, shift));  // f32 subtraction, :446
-    else e = pow(10.0, (double)top_s);                                    // :418
+    num = exp10((double)top_s - (double)shift);
+    // the sum's terms subtract in f32 when shifted (:446), else they are the plain powers (:418)
+    e = (shift != 0.0f) ? exp10((double)__fsub_rn(top_s, shift)) : num;
   }
   double sum = 0.0;  // ascending score order, as the rebuilt sum of :445-447
   for (int i = nb - 1; i >= 0; i--) sum += __shfl_sync(0xffffffffu, e, i);
-  // computeWeightRatio: Math.pow(10.0,(double)(s.score-weightRatioShift))/sum with a double shift (:392-393)
   double lwr = 0.0;
-  if (lane < nb) lwr = pow(10.0, (double)top_s - (double)shift) / sum;
+  if (lane < nb) lwr = num / sum;
   const double best_ratio = __shfl_sync(0xffffffffu, lwr, 0);
   // rows are emitted best-first until the first lwr < bestRatio*keepFactor (:998)
   const bool cut = lane < nb && lane > 0 && lwr < best_ratio * (double)cfg.keep_factor;
@@ -260,11 +342,40 @@ __device__ __forceinline__ int select_and_reset(const DbView& db, const CfgView&
   return rows;
 }
 
+// ------------------------------------------------------------------------------ group pipeline
+enum : int { kGrpLast = 1, kGrpBad = 2 };
+
+struct Group {
+  long long r;      // read index, < 0: the stream is exhausted
+  int Q;            // len - k + 1 of the read (may be <= 0)
+  int flags;        // kGrp*
+  int n_match, n_amb, n_skip;       // totals of the read, valid on its last group
+  uint32_t hitm, ambm, stagedm;     // windows (bit l = window g0+l) matched / ambiguous-to-treat / staged
+  uint32_t a_lo, a_hi;              // ambiguity bits of the 64 characters from g0 on
+  int buf;                          // stage / cls buffer
+  float QT;
+  // per lane
+  uint32_t pk;                      // staged: (stage offset << 16) | n_postings
+  uint64_t meta;                    // table meta of the lane's window
+};
+
+// front-end state of a warp: where the next group starts
+struct Front {
+  long long r = -1;
+  unsigned long long rn_raw = 0;    // lane 0: result of the atomicAdd that fetched the NEXT read
+  const uint8_t* s = nullptr;
+  long long len = 0, Ql = 0, g0 = 0;
+  int n_match = 0, n_amb = 0, n_skip = 0;
+  bool active = false;
+  int buf = 0;
+};
+
 // --------------------------------------------------------------------------------- main kernel
 __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1)
-place_kernel(const __grid_constant__ AlphabetTables c_alpha, DbView db, CfgView cfg, BatchView bt, unsigned long long* work_counter, float* amb_S, int* amb_C,
-             int n_pad, int per_warp_bytes) {
-  extern __shared__ __align__(16) uint8_t smem[];
+place_kernel(const __grid_constant__ AlphabetTables c_alpha, DbView db, CfgView cfg, BatchView bt,
+             unsigned long long* work_counter, float* amb_S, int* amb_C, int n_pad, int per_warp_bytes,
+             int stage_bytes) {
+  extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int warps_per_cta = blockDim.x >> 5;
@@ -272,96 +383,189 @@ place_kernel(const __grid_constant__ AlphabetTables c_alpha, DbView db, CfgView 
   uint8_t* cls_tab = smem;
   for (int i = threadIdx.x; i < 256; i += blockDim.x) cls_tab[i] = c_alpha.cls[i];
   WarpSmem w;
-  uint8_t* base = smem + 256 + (size_t)warp * per_warp_bytes;
-  w.S = (float*)base;
-  w.flag = base + 4 * (size_t)n_pad;
-  w.cls = w.flag + (((n_pad >> 5) + 15) & ~15);
+  {
+    uint8_t* base = smem + 256 + (size_t)warp * per_warp_bytes;
+    w.bar = smem_u32(base);           // 2 x u64
+    w.cls = base + 16;                // 2 x 64 B (+48 pad)
+    w.S = (float*)(base + 192);
+    w.stage = base + 192 + 4 * (size_t)n_pad;
+    w.stage_bytes = stage_bytes;
+  }
   for (int i = lane; i < n_pad; i += 32) w.S[i] = __uint_as_float(kSentinelBits);
-  for (int i = lane; i < (n_pad >> 5); i += 32) w.flag[i] = 0;
+  if (lane == 0) {
+    mbar_init(w.bar, 1);
+    mbar_init(w.bar + 8, 1);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   const size_t gw = (size_t)blockIdx.x * warps_per_cta + warp;
   float* Sa = amb_S + gw * n_pad;
   int* Ca = amb_C + gw * n_pad;
   const int k = db.k;
   const uint32_t kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
+  const int K = cfg.K;
+  uint32_t phase = 0;  // bit b = parity to wait for on stage b
 
-  for (;;) {
-    unsigned long long r = 0;
-    if (lane == 0) r = atomicAdd(work_counter, 1ull);
-    r = __shfl_sync(0xffffffffu, r, 0);
-    if (r >= (unsigned long long)bt.n_reads) break;
-    const uint64_t o0 = bt.seq_off[r] - bt.seq_base;
-    const long long len = (long long)(bt.seq_off[r + 1] - bt.seq_off[r]);
-    const uint8_t* s = bt.seq + o0;
-    const long long Ql = len - k + 1;  // sk.getMerCount()
-    const int Q = (int)Ql;
-    const float QT = __fmul_rn((float)Q, db.T);  // Q*PPStarThresholdAsLog10 (int*float)
-    const float QT0 = __fadd_rn(0.0f, QT);       // S[x]+=Q*T on a zeroed S[x]
-    int n_match = 0, n_amb = 0, n_skip = 0;
-    bool bad = false;
-    if (Ql <= 0) {
-      // no window; still an unsupported character aborts the reference before the length matters
-      uint8_t c = (lane < len) ? cls_tab[s[lane]] : kClsPad;
-      bad = __any_sync(0xffffffffu, c == kClsBad);
+  Front fe;
+  if (lane == 0) fe.rn_raw = atomicAdd(work_counter, 1ull);
+
+  // ---- front end: produce the next group of the warp's stream -----------------------------
+  auto front = [&]() -> Group {
+    Group g;
+    g.r = -1; g.Q = 0; g.flags = 0; g.n_match = g.n_amb = g.n_skip = 0;
+    g.hitm = g.ambm = g.stagedm = 0; g.a_lo = g.a_hi = 0; g.buf = 0; g.QT = 0.f; g.pk = 0; g.meta = 0;
+    if (!fe.active) {
+      const unsigned long long r = __shfl_sync(0xffffffffu, fe.rn_raw, 0);
+      if (r >= (unsigned long long)bt.n_reads) return g;
+      if (lane == 0) fe.rn_raw = atomicAdd(work_counter, 1ull);  // consumed when this read is finished
+      const uint64_t o0 = bt.seq_off[r], o1 = bt.seq_off[r + 1];
+      fe.r = (long long)r;
+      fe.s = bt.seq + (o0 - bt.seq_base);
+      fe.len = (long long)(o1 - o0);
+      fe.Ql = fe.len - k + 1;  // sk.getMerCount()
+      fe.g0 = 0;
+      fe.n_match = fe.n_amb = fe.n_skip = 0;
+      fe.active = true;
     }
-    for (long long g0 = 0; g0 < Ql && !bad; g0 += 32) {
-      // classes of characters [g0, g0+64): 32 window starts + up to k-1 <= 30 look-ahead
-      const long long i0 = g0 + lane, i1 = i0 + 32;
-      const uint8_t c0 = (i0 < len) ? cls_tab[s[i0]] : kClsPad;
-      const uint8_t c1 = (i1 < len) ? cls_tab[s[i1]] : kClsPad;
-      if (__any_sync(0xffffffffu, c0 == kClsBad || c1 == kClsBad)) { bad = true; break; }
-      w.cls[lane] = c0;
-      w.cls[lane + 32] = c1;
+    g.r = fe.r;
+    g.Q = (int)fe.Ql;
+    g.QT = __fmul_rn((float)g.Q, db.T);  // Q*PPStarThresholdAsLog10 (int*float)
+    g.buf = fe.buf;
+    fe.buf ^= 1;
+    const uint8_t* s = fe.s;
+    const long long len = fe.len, g0 = fe.g0;
+    if (fe.Ql <= 0) {
+      // no window; still an unsupported character aborts the reference before the length matters
+      const uint8_t c = (lane < len) ? cls_tab[s[lane]] : kClsPad;
+      if (__any_sync(0xffffffffu, c == kClsBad)) g.flags |= kGrpBad;
+      g.flags |= kGrpLast;
+      fe.active = false;
+      return g;
+    }
+    // classes of characters [g0, g0+64): 32 window starts + up to k-1 <= 30 look-ahead
+    const long long i0 = g0 + lane, i1 = i0 + 32;
+    const uint8_t c0 = (i0 < len) ? cls_tab[s[i0]] : kClsPad;
+    const uint8_t c1 = (i1 < len) ? cls_tab[s[i1]] : kClsPad;
+    if (__any_sync(0xffffffffu, c0 == kClsBad || c1 == kClsBad)) {
+      g.flags |= kGrpBad | kGrpLast;
+      fe.active = false;
+      return g;
+    }
+    // ambiguityCountPerMer of window g0+lane = popcount of the ambiguity bits of its k characters
+    const uint32_t a0 = __ballot_sync(0xffffffffu, (c0 & 0xC0) == kClsAmb);
+    const uint32_t a1 = __ballot_sync(0xffffffffu, (c1 & 0xC0) == kClsAmb);
+    g.a_lo = a0; g.a_hi = a1;
+    if (a0 | a1) {  // only the ambiguity path reads the class bytes back
+      uint8_t* cb = w.cls + 64 * g.buf;
+      cb[lane] = c0;
+      cb[lane + 32] = c1;
       __syncwarp();
-      // ambiguityCountPerMer of window g0+lane = popcount of the ambiguity bits of its k characters
-      const uint32_t a0 = __ballot_sync(0xffffffffu, (c0 & 0xC0) == kClsAmb);
-      const uint32_t a1 = __ballot_sync(0xffffffffu, (c1 & 0xC0) == kClsAmb);
-      const uint64_t amask = (uint64_t)a0 | ((uint64_t)a1 << 32);
-      const uint32_t wbits = (uint32_t)(amask >> lane) & kmask;
-      const int na = __popc(wbits);
-      const bool valid = (g0 + lane) < Ql;
-      // getNextByteWord (:224-233) + processQueries (:691-750)
-      const bool plain = valid && na == 0;
-      const bool skip = valid && na > 0 && (na > db.max_amb || !cfg.treat_amb);
-      const bool ambw = valid && na > 0 && !skip;
-      uint64_t meta = 0;
-      bool found = false;
-      if (plain) {
-        uint64_t code = 0;
-        for (int i = 0; i < k; i++) code |= (uint64_t)w.cls[lane + i] << (db.bits * i);
-        found = table_probe(db, code, meta);
-      }
-      const uint32_t hitm = __ballot_sync(0xffffffffu, found);
-      const uint32_t ambm = __ballot_sync(0xffffffffu, ambw);
-      n_match += __popc(hitm);
-      n_amb += __popc(ambm);
-      n_skip += __popc(__ballot_sync(0xffffffffu, skip));
+    }
+    const uint32_t wbits = __funnelshift_r(a0, a1, lane) & kmask;
+    const int na = __popc(wbits);
+    const int nv = (int)min(32LL, fe.Ql - g0);  // windows left in the read
+    const bool valid = lane < nv;
+    // getNextByteWord (:224-233) + processQueries (:691-750)
+    const bool plain = valid && na == 0;
+    const bool skip = valid && na > 0 && (na > db.max_amb || !cfg.treat_amb);
+    const bool ambw = valid && na > 0 && !skip;
+    // planar key: plane p of window `lane` = bits [lane, lane+k) of the p-th state-bit ballots
+    uint64_t key = 0;
+    for (int p = 0; p < db.bits; p++) {
+      const uint32_t b0 = __ballot_sync(0xffffffffu, (c0 >> p) & 1u);
+      const uint32_t b1 = __ballot_sync(0xffffffffu, (c1 >> p) & 1u);
+      key |= (uint64_t)(__funnelshift_r(b0, b1, lane) & kmask) << (p * k);
+    }
+    uint64_t meta = 0;
+    bool found = false;
+    if (plain) found = table_probe(db, key, meta);
+    // stage assignment: windows are taken in order while their posting blocks fit into the stage;
+    // a block larger than a whole stage is read from global memory by the drain instead
+    const uint32_t n_post = (uint32_t)(meta & 0xFFFF);
+    const uint32_t bytes = (n_post * 6 + 31) & ~31u;
+    const bool giant = bytes > (uint32_t)stage_bytes;
+    const uint32_t sb = (found && !giant) ? bytes : 0u;
+    uint32_t incl = sb;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    const uint32_t nofit = __ballot_sync(0xffffffffu, incl > (uint32_t)stage_bytes);
+    int cons = nofit ? __ffs(nofit) - 1 : 32;  // >= 1: lane 0 alone always fits
+    cons = min(cons, nv);
+    const uint32_t lanes = cons >= 32 ? 0xffffffffu : ((1u << cons) - 1u);
+    g.hitm = __ballot_sync(0xffffffffu, found) & lanes;
+    g.ambm = __ballot_sync(0xffffffffu, ambw) & lanes;
+    g.stagedm = __ballot_sync(0xffffffffu, sb != 0u) & lanes;
+    fe.n_match += __popc(g.hitm);
+    fe.n_amb += __popc(g.ambm);
+    fe.n_skip += __popc(__ballot_sync(0xffffffffu, skip) & lanes);
+    g.meta = meta;
+    g.pk = ((incl - sb) << 16) | n_post;
+    if (g.stagedm) {
+      const uint32_t total = __shfl_sync(0xffffffffu, incl, cons - 1);
+      const uint32_t bar = w.bar + 8 * g.buf;
+      fence_proxy_async();  // the drain's generic-proxy reads of this stage precede the async writes
+      if (lane == 0) mbar_expect_tx(bar, total);
+      __syncwarp();
+      if ((g.stagedm >> lane) & 1u)
+        bulk_g2s(smem_u32(w.stage + (size_t)g.buf * stage_bytes + (incl - sb)),
+                 db.blocks + (meta >> 16) * kBlockAlign, bytes, bar);
+    }
+    fe.g0 = g0 + cons;
+    if (fe.g0 >= fe.Ql) {
+      g.flags |= kGrpLast;
+      fe.active = false;
+    }
+    g.n_match = fe.n_match; g.n_amb = fe.n_amb; g.n_skip = fe.n_skip;
+    return g;
+  };
+
+  // ---- drain: accumulate one group; on the last group of a read, select and write the rows -
+  auto drain = [&](const Group& g) {
+    const float QT0 = __fadd_rn(0.0f, g.QT);  // S[x]+=Q*T on a zeroed S[x]
+    if (g.stagedm) {
+      mbar_wait(w.bar + 8 * g.buf, (phase >> g.buf) & 1u);
+      phase ^= 1u << g.buf;
+    }
+    const bool bad = g.flags & kGrpBad;
+    if (!bad) {
+      const uint8_t* stage = w.stage + (size_t)g.buf * stage_bytes;
       // windows in order: a node's S[x] must see its contributions in window order
-      for (uint32_t todo = hitm | ambm; todo;) {
+      for (uint32_t todo = g.hitm | g.ambm; todo;) {
         const int l = __ffs(todo) - 1;
         todo &= todo - 1;
-        if ((hitm >> l) & 1u) {
-          accumulate_block(db, w, __shfl_sync(0xffffffffu, meta, l), QT0, lane);
+        if ((g.hitm >> l) & 1u) {
+          const uint32_t pk = __shfl_sync(0xffffffffu, g.pk, l);
+          if ((g.stagedm >> l) & 1u) {
+            accumulate_staged(w.S, stage + (pk >> 16), (int)(pk & 0xFFFF), QT0, db.T, lane);
+          } else {
+            const uint64_t mt = __shfl_sync(0xffffffffu, g.meta, l);
+            accumulate_global(w.S, db.blocks + (mt >> 16) * kBlockAlign, (int)(pk & 0xFFFF), QT0, db.T, lane);
+          }
         } else {
-          ambiguous_window(c_alpha, db, cfg, w, l, (uint32_t)(amask >> l) & kmask, Q, QT, Sa, Ca, lane);
+          const uint64_t amask = (uint64_t)g.a_lo | ((uint64_t)g.a_hi << 32);
+          ambiguous_window(c_alpha, db, cfg, w.S, w.cls + 64 * g.buf + l, (uint32_t)(amask >> l) & kmask, g.QT, Sa,
+                           Ca, lane);
         }
       }
-      __syncwarp();
     }
+    if (!(g.flags & kGrpLast)) return;
     // ---- selection / outputs
-    const int K = cfg.K;
+    const long long r = g.r;
     uint16_t* o_node = bt.node + r * K;
     float* o_score = bt.score + r * K;
     double* o_lwr = bt.lwr + r * K;
     int status, rows = 0;
     if (bad) {
-      select_and_reset(db, cfg, w, n_pad, false, nullptr, o_node, o_score, o_lwr, lane);
+      select_and_reset(cfg, w.S, n_pad, false, nullptr, db.n_nodes, o_node, o_score, o_lwr, lane);
       status = RP_STATUS_BAD_CHAR;
-    } else if (Ql < 0) {
+    } else if (g.Q < 0) {
       status = RP_STATUS_TOO_SHORT;
     } else {
       float* dump_row = bt.dump_scores ? bt.dump_scores + r * (size_t)db.n_nodes : nullptr;
-      rows = select_and_reset(db, cfg, w, n_pad, true, dump_row, o_node, o_score, o_lwr, lane);
+      rows = select_and_reset(cfg, w.S, n_pad, true, dump_row, db.n_nodes, o_node, o_score, o_lwr, lane);
       status = rows < 0 ? RP_STATUS_UNPLACED : RP_STATUS_PLACED;  // L empty -> not placed (:797-806)
     }
     if (rows <= 0 && status != RP_STATUS_PLACED) {
@@ -373,10 +577,19 @@ place_kernel(const __grid_constant__ AlphabetTables c_alpha, DbView db, CfgView 
       bt.status[r] = status;
       if (bt.counts) {
         const bool ok = status <= RP_STATUS_UNPLACED;
-        int4 c = make_int4(ok ? (Q > 0 ? Q : 0) : 0, ok ? n_match : 0, ok ? n_amb : 0, ok ? n_skip : 0);
+        int4 c = make_int4(ok ? (g.Q > 0 ? g.Q : 0) : 0, ok ? g.n_match : 0, ok ? g.n_amb : 0, ok ? g.n_skip : 0);
         *reinterpret_cast<int4*>(bt.counts + 4 * r) = c;
       }
     }
+  };
+
+  Group cur = front();
+  while (cur.r >= 0) {
+    Group nxt;
+    // after a bad character the read is abandoned: nothing of it may be in flight past its last group
+    nxt = front();
+    drain(cur);
+    cur = nxt;
   }
 }
 
@@ -389,7 +602,7 @@ __global__ void extract_kernel(const __grid_constant__ AlphabetTables c_alpha, D
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint8_t* cls = cls_all[warp];
   const int k = db.k;
-  const uint32_t kmask = (1u << k) - 1u;
+  const uint32_t kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
   for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + warp; r < n_reads;
        r += (long long)gridDim.x * (blockDim.x >> 5)) {
     const uint8_t* s = seq + seq_off[r];
@@ -421,10 +634,10 @@ __global__ void extract_kernel(const __grid_constant__ AlphabetTables c_alpha, D
       uint64_t code0 = ~0ull;
       int kind = RP_WIN_SKIPPED, nalt = 0, hits = -1;
       if (!bad && na == 0) {
-        uint64_t code = 0, meta;
-        for (int i = 0; i < k; i++) code |= (uint64_t)cls[lane + i] << (db.bits * i);
+        uint64_t code, meta;
+        const uint64_t key = planar_from_states(cls + lane, k, db.bits, -1, 0, -1, 0, &code);
         code0 = code; kind = RP_WIN_PLAIN; nalt = 1;
-        if (table_probe(db, code, meta)) hits = (int)(meta & 0xFFFF);
+        if (table_probe(db, key, meta)) hits = (int)(meta & 0xFFFF);
       } else if (!bad && na <= db.max_amb) {
         const int o1 = __ffs(wbits) - 1;
         const uint32_t rest = wbits & (wbits - 1);
@@ -434,15 +647,11 @@ __global__ void extract_kernel(const __grid_constant__ AlphabetTables c_alpha, D
         kind = RP_WIN_AMBIG; nalt = n1 * n2;
         int tot = 0; bool any = false;
         for (int t = 0; t < nalt; t++) {
-          uint64_t code = 0, meta;
-          for (int i = 0; i < k; i++) {
-            unsigned st = cls[lane + i];
-            if (i == o1) st = c_alpha.alt_states[id1][t % n1];
-            else if (i == o2) st = c_alpha.alt_states[id2][t % n2];
-            code |= (uint64_t)st << (db.bits * i);
-          }
+          uint64_t code, meta;
+          const uint64_t key = planar_from_states(cls + lane, k, db.bits, o1, c_alpha.alt_states[id1][t % n1], o2,
+                                                  c_alpha.alt_states[id2][t % n2], &code);
           if (t == 0) code0 = code;
-          if (table_probe(db, code, meta)) { any = true; tot += (int)(meta & 0xFFFF); }
+          if (table_probe(db, key, meta)) { any = true; tot += (int)(meta & 0xFFFF); }
         }
         hits = any ? tot : -1;
       }
@@ -457,15 +666,27 @@ __global__ void fill_f32_kernel(float* p, size_t n, float v) {
 
 // ------------------------------------------------------------------------------ host plumbing
 // warps per CTA x CTAs per SM maximising resident warps under the shared-memory budget
+// Shared memory per warp = S[n_pad] + two posting stages; warps per CTA x CTAs per SM maximise the
+// resident warps under the 227 KB budget.  The stage holds ~32 average posting blocks (a whole group
+// of windows); RP_STAGE_BYTES overrides it for tuning runs.
 int compute_geometry(const rp_db* db, DeviceCtx* dc) {
   LaunchGeom g;
-  g.n_pad = (db->desc.n_nodes + 31) & ~31;
-  const size_t flag_bytes = ((g.n_pad >> 5) + 15) & ~15;
-  g.per_warp_bytes = 4 * (size_t)g.n_pad + flag_bytes + 64;
-  g.per_warp_bytes = (g.per_warp_bytes + 15) & ~(size_t)15;
+  g.n_pad = (db->desc.n_nodes + 127) & ~127;
   const size_t cta_fixed = 256;
   const size_t optin = dc->smem_optin;         // 227 KB on sm_100
   const size_t sm_total = optin + 1024;        // 228 KB per SM, 1 KB reserved per resident CTA
+  const double mean_block = db->desc.n_keys ? (double)db->block_bytes / (double)db->desc.n_keys : 32.0;
+  long stage = (long)(32.0 * mean_block * 0.85);
+  if (const char* e = getenv("RP_STAGE_BYTES")) stage = atol(e);
+  stage = std::max(1024L, std::min(stage, 32768L - 128));
+  stage = (stage + 127) & ~127L;
+  for (;;) {
+    g.stage_bytes = (int)stage;
+    g.per_warp_bytes = (192 + 4 * (size_t)g.n_pad + 2 * (size_t)g.stage_bytes + 127) & ~(size_t)127;
+    // big trees: give the stages up before giving the accumulator up
+    if (cta_fixed + 2 * g.per_warp_bytes <= optin || stage <= 1024) break;
+    stage = std::max(1024L, (stage / 2 + 127) & ~127L);
+  }
   if (cta_fixed + g.per_warp_bytes > optin)
     return set_error(RP_E_UNSUPPORTED,
                      "n_nodes=%d needs %zu B of shared memory per read (> %zu B per CTA); trees beyond ~56k nodes "
@@ -534,7 +755,7 @@ static int launch_place(const rp_db* db, DeviceCtx* dc, StreamCtx* sc, const rp_
   if (time_it) RP_CUDA_TRY(cudaEventRecord(sc->ev_k0, stream));
   place_kernel<<<g.grid, g.warps_per_cta * 32, g.smem_bytes, stream>>>(
       db->alpha, make_db_view(db, dc), make_cfg_view(cfg), bt, sc->d_counter, sc->d_amb_S, sc->d_amb_C, g.n_pad,
-      (int)g.per_warp_bytes);
+      (int)g.per_warp_bytes, g.stage_bytes);
   RP_CUDA_TRY(cudaGetLastError());
   g_kernel_launches.fetch_add(1);
   if (time_it) RP_CUDA_TRY(cudaEventRecord(sc->ev_k1, stream));
