@@ -139,6 +139,7 @@ struct LaunchGeom {
   size_t smem_bytes = 0, per_warp_bytes = 0;
   int n_pad = 0;        // S[] entries per warp, multiple of 128
   int stage_bytes = 0;  // one posting staging buffer (two per warp), multiple of 128
+  int max_chunks = 0;   // chunk descriptors per stage
 };
 
 struct DeviceCtx {

@@ -102,12 +102,44 @@ __device__ __forceinline__ uint64_t planar_from_states(const uint8_t* c, int k, 
 }
 
 struct WarpSmem {
-  float* S;          // [n_pad]
+  float* S;          // [n_pad + 32]: the last 32 entries are per-lane dummies for idle lanes
   uint8_t* cls;      // [2][64] character classes of the two groups in flight
   uint8_t* stage;    // [2][stage_bytes] posting blocks staged by TMA
+  uint2* desc;       // [2][max_chunks] chunk descriptors of the staged groups
   uint32_t bar;      // shared-space address of mbarrier[2]
-  int stage_bytes;
+  int stage_bytes, max_chunks;
 };
+
+// A chunk = up to 32 postings of one window (one posting sub-block).  x = shared-space byte address of
+// its scores, y = number of postings m; its node ids start at x + 4*m.
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+
+// Adds the staged posting blocks of a whole group into S, chunk by chunk, in window order
+// (PlacementProcess.java:719-735).  Branch-free: idle lanes of a short chunk update their private dummy
+// entry.  The loads of chunk j+1 are issued before the read-modify-write of chunk j.
+__device__ __forceinline__ void accumulate_chunks(float* __restrict__ S, const uint2* __restrict__ dl, int n_chunks,
+                                                  int n_pad, float QT0, float T, int lane) {
+  const uint32_t lane4 = lane * 4, lane2 = lane * 2;
+  const uint32_t dummy = n_pad + lane;
+  uint2 d = dl[0];
+  float v = lds_f32(d.x + lane4);
+  uint32_t x = lds_u16(d.x + 4 * d.y + lane2);
+  uint2 dn = dl[1];
+#pragma unroll 1
+  for (int j = 0; j < n_chunks; j++) {
+    const float vn = lds_f32(dn.x + lane4);
+    const uint32_t xn = lds_u16(dn.x + 4 * dn.y + lane2);
+    const uint2 dnn = dl[j + 2];
+    const uint32_t idx = lane < d.y ? x : dummy;
+    float s = S[idx];
+    if (is_sentinel(s)) s = QT0;                   // C[x]==0 : L.add(x); S[x]+=Q*T   (:726-729)
+    S[idx] = __fadd_rn(s, __fsub_rn(v, T));        // S[x]+= v - T   (:733)
+    asm volatile("" ::: "memory");                 // keep the warp's shared-memory accesses in program order
+    d = dn; v = vn; x = xn; dn = dnn;
+  }
+  __syncwarp();
+}
 
 // Adds one posting block that sits in shared memory into S, in order.  PlacementProcess.java:719-735.
 __device__ __forceinline__ void accumulate_staged(float* __restrict__ S, const uint8_t* p, int len, float QT0, float T,
@@ -353,6 +385,7 @@ struct Group {
   uint32_t hitm, ambm, stagedm;     // windows (bit l = window g0+l) matched / ambiguous-to-treat / staged
   uint32_t a_lo, a_hi;              // ambiguity bits of the 64 characters from g0 on
   int buf;                          // stage / cls buffer
+  int n_chunks;                     // chunk descriptors written for the staged windows
   float QT;
   // per lane
   uint32_t pk;                      // staged: (stage offset << 16) | n_postings
@@ -374,7 +407,7 @@ struct Front {
 __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1)
 place_kernel(const __grid_constant__ AlphabetTables c_alpha, DbView db, CfgView cfg, BatchView bt,
              unsigned long long* work_counter, float* amb_S, int* amb_C, int n_pad, int per_warp_bytes,
-             int stage_bytes) {
+             int stage_bytes, int max_chunks) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -388,10 +421,12 @@ place_kernel(const __grid_constant__ AlphabetTables c_alpha, DbView db, CfgView 
     w.bar = smem_u32(base);           // 2 x u64
     w.cls = base + 16;                // 2 x 64 B (+48 pad)
     w.S = (float*)(base + 192);
-    w.stage = base + 192 + 4 * (size_t)n_pad;
+    w.stage = base + 192 + 4 * (size_t)(n_pad + 32);
     w.stage_bytes = stage_bytes;
+    w.max_chunks = max_chunks;
+    w.desc = (uint2*)(w.stage + 2 * (size_t)stage_bytes);
   }
-  for (int i = lane; i < n_pad; i += 32) w.S[i] = __uint_as_float(kSentinelBits);
+  for (int i = lane; i < n_pad + 32; i += 32) w.S[i] = __uint_as_float(kSentinelBits);
   if (lane == 0) {
     mbar_init(w.bar, 1);
     mbar_init(w.bar + 8, 1);
@@ -413,7 +448,7 @@ place_kernel(const __grid_constant__ AlphabetTables c_alpha, DbView db, CfgView 
   auto front = [&]() -> Group {
     Group g;
     g.r = -1; g.Q = 0; g.flags = 0; g.n_match = g.n_amb = g.n_skip = 0;
-    g.hitm = g.ambm = g.stagedm = 0; g.a_lo = g.a_hi = 0; g.buf = 0; g.QT = 0.f; g.pk = 0; g.meta = 0;
+    g.hitm = g.ambm = g.stagedm = 0; g.a_lo = g.a_hi = 0; g.buf = 0; g.n_chunks = 0; g.QT = 0.f; g.pk = 0; g.meta = 0;
     if (!fe.active) {
       const unsigned long long r = __shfl_sync(0xffffffffu, fe.rn_raw, 0);
       if (r >= (unsigned long long)bt.n_reads) return g;
@@ -485,13 +520,16 @@ place_kernel(const __grid_constant__ AlphabetTables c_alpha, DbView db, CfgView 
     const uint32_t bytes = (n_post * 6 + 31) & ~31u;
     const bool giant = bytes > (uint32_t)stage_bytes;
     const uint32_t sb = (found && !giant) ? bytes : 0u;
-    uint32_t incl = sb;
+    // one scan for both prefix sums: bytes in 32 B units (<= 2^15 over the warp) above the chunk count (< 2^13)
+    const uint32_t my_chunks = sb ? (n_post + 31) >> 5 : 0u;
+    uint32_t incl = (sb >> 5 << 13) | my_chunks;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
       if (lane >= d) incl += t;
     }
-    const uint32_t nofit = __ballot_sync(0xffffffffu, incl > (uint32_t)stage_bytes);
+    const uint32_t incl_bytes = incl >> 13 << 5, incl_chunks = incl & 0x1FFFu;
+    const uint32_t nofit = __ballot_sync(0xffffffffu, incl_bytes > (uint32_t)stage_bytes);
     int cons = nofit ? __ffs(nofit) - 1 : 32;  // >= 1: lane 0 alone always fits
     cons = min(cons, nv);
     const uint32_t lanes = cons >= 32 ? 0xffffffffu : ((1u << cons) - 1u);
@@ -502,16 +540,31 @@ place_kernel(const __grid_constant__ AlphabetTables c_alpha, DbView db, CfgView 
     fe.n_amb += __popc(g.ambm);
     fe.n_skip += __popc(__ballot_sync(0xffffffffu, skip) & lanes);
     g.meta = meta;
-    g.pk = ((incl - sb) << 16) | n_post;
+    const uint32_t off = incl_bytes - sb;
+    g.pk = (off << 16) | n_post;
     if (g.stagedm) {
-      const uint32_t total = __shfl_sync(0xffffffffu, incl, cons - 1);
+      const uint32_t last = __shfl_sync(0xffffffffu, incl, cons - 1);
+      const uint32_t total = last >> 13 << 5;
+      g.n_chunks = (int)(last & 0x1FFFu);
       const uint32_t bar = w.bar + 8 * g.buf;
+      const uint32_t dst = smem_u32(w.stage + (size_t)g.buf * stage_bytes) + off;
       fence_proxy_async();  // the drain's generic-proxy reads of this stage precede the async writes
       if (lane == 0) mbar_expect_tx(bar, total);
       __syncwarp();
-      if ((g.stagedm >> lane) & 1u)
-        bulk_g2s(smem_u32(w.stage + (size_t)g.buf * stage_bytes + (incl - sb)),
-                 db.blocks + (meta >> 16) * kBlockAlign, bytes, bar);
+      if ((g.stagedm >> lane) & 1u) {
+        bulk_g2s(dst, db.blocks + (meta >> 16) * kBlockAlign, bytes, bar);
+        // chunk descriptors of this window, in window order
+        uint2* dl = w.desc + (size_t)g.buf * w.max_chunks + (incl_chunks - my_chunks);
+        uint32_t a = dst;
+        for (uint32_t left = n_post; left; a += kSubBlockBytes) {
+          const uint32_t m = min(left, 32u);
+          *dl++ = make_uint2(a, m);
+          left -= m;
+        }
+      }
+      if (lane < 2)  // two idle descriptors behind the list: the drain prefetches that far
+        w.desc[(size_t)g.buf * w.max_chunks + g.n_chunks + lane] = make_uint2(dst - off, 0u);
+      __syncwarp();
     }
     fe.g0 = g0 + cons;
     if (fe.g0 >= fe.Ql) {
@@ -530,7 +583,10 @@ place_kernel(const __grid_constant__ AlphabetTables c_alpha, DbView db, CfgView 
       phase ^= 1u << g.buf;
     }
     const bool bad = g.flags & kGrpBad;
-    if (!bad) {
+    if (!bad && !(g.ambm | (g.hitm & ~g.stagedm))) {
+      // common case: every matched window of the group is staged
+      if (g.n_chunks) accumulate_chunks(w.S, w.desc + (size_t)g.buf * w.max_chunks, g.n_chunks, n_pad, QT0, db.T, lane);
+    } else if (!bad) {
       const uint8_t* stage = w.stage + (size_t)g.buf * stage_bytes;
       // windows in order: a node's S[x] must see its contributions in window order
       for (uint32_t todo = g.hitm | g.ambm; todo;) {
@@ -682,7 +738,8 @@ int compute_geometry(const rp_db* db, DeviceCtx* dc) {
   stage = (stage + 127) & ~127L;
   for (;;) {
     g.stage_bytes = (int)stage;
-    g.per_warp_bytes = (192 + 4 * (size_t)g.n_pad + 2 * (size_t)g.stage_bytes + 127) & ~(size_t)127;
+    g.max_chunks = 32 + g.stage_bytes / kSubBlockBytes + 3;  // one per window + one per extra sub-block + 2 idle
+    g.per_warp_bytes = (192 + 4 * (size_t)(g.n_pad + 32) + 2 * (size_t)g.stage_bytes + 2 * 8 * (size_t)g.max_chunks + 127) & ~(size_t)127;
     // big trees: give the stages up before giving the accumulator up
     if (cta_fixed + 2 * g.per_warp_bytes <= optin || stage <= 1024) break;
     stage = std::max(1024L, (stage / 2 + 127) & ~127L);
@@ -755,7 +812,7 @@ static int launch_place(const rp_db* db, DeviceCtx* dc, StreamCtx* sc, const rp_
   if (time_it) RP_CUDA_TRY(cudaEventRecord(sc->ev_k0, stream));
   place_kernel<<<g.grid, g.warps_per_cta * 32, g.smem_bytes, stream>>>(
       db->alpha, make_db_view(db, dc), make_cfg_view(cfg), bt, sc->d_counter, sc->d_amb_S, sc->d_amb_C, g.n_pad,
-      (int)g.per_warp_bytes, g.stage_bytes);
+      (int)g.per_warp_bytes, g.stage_bytes, g.max_chunks);
   RP_CUDA_TRY(cudaGetLastError());
   g_kernel_launches.fetch_add(1);
   if (time_it) RP_CUDA_TRY(cudaEventRecord(sc->ev_k1, stream));
