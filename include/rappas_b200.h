@@ -51,6 +51,7 @@ extern "C" {
 #define RP_STATUS_UNPLACED  1 /* no k-mer hit: PlacementProcess.java:797-806            */
 #define RP_STATUS_TOO_SHORT 2 /* len < k-1; the reference throws NegativeArraySizeException (AmbigSequenceKnife.java:145) */
 #define RP_STATUS_BAD_CHAR  3 /* unsupported character; the reference exits(1) (AmbigSequenceKnife.java:124-128) */
+#define RP_STATUS_TOO_LONG  4 /* read longer than 2^26-64 characters: not placed (CUDA library limit)    */
 
 /* per-window kind (rp_extract_kmers) */
 #define RP_WIN_PLAIN   0     /* no ambiguity: one k-mer                                */

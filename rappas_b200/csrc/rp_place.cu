@@ -10,15 +10,18 @@
 //   K4  selection + LWR         fillBestScoreList (:396-451), computeWeightRatio[Shift] (:384-394),
 //                               row loop (:974-1000)
 //
-// Execution model: ONE WARP OWNS ONE READ and runs a two-stage software pipeline over
-// GROUPS of up to 32 consecutive windows:
-//   front(i+1)  classify 64 characters, build the 32 planar k-mer keys from ballots, probe the cuckoo
-//               table (both buckets, one memory round trip), prefix-sum the posting-block sizes and
-//               issue one cp.async.bulk (TMA) per matched window into a per-warp shared-memory stage,
-//               completion counted on an mbarrier;
-//   drain(i)    wait for stage i, then add the posting blocks into the read's score vector S[n_nodes]
-//               (shared memory) window by window.
-// so the gathers of group i+1 are in flight while group i is being accumulated (two stages per warp).
+// Execution model: ONE WARP OWNS ONE READ AT A TIME and is split into a front end and a
+// back end that talk through a per-warp ring of 8-byte DESCRIPTORS in shared memory:
+//   front end   classifies 64 characters, builds the 32 planar k-mer keys of a group of windows from
+//               ballots, probes the cuckoo table (both buckets, one memory round trip) and appends, in
+//               window order, one CHUNK descriptor per <=32 postings of every matched window (plus
+//               START / END markers per read and AMB / GIANT markers for the rare slow paths);
+//   back end    walks the descriptor stream with a kPrefetch-deep register pipeline: the two coalesced
+//               loads of chunk j+kPrefetch (scores, node ids) are issued while chunk j is added into the
+//               read's score vector S[n_nodes] in shared memory.
+// The front end runs whenever the ring runs low, so table probes, posting gathers and the accumulation
+// of (possibly different) reads overlap inside one warp, and nothing but S and the small ring lives in
+// shared memory (about 2.5x more resident warps than staging the postings there).
 // The accumulation uses plain (non-atomic) shared-memory read-modify-writes: node ids are distinct
 // inside a k-mer's posting list, so the 32 lanes of one instruction never collide, and because a node
 // receives at most one posting per window and the windows are visited in order, every S[x] is
@@ -39,29 +42,20 @@ namespace rp {
 constexpr uint32_t kSentinelBits = 0x7FFFFFFFu;  // a NaN no arithmetic here produces
 constexpr int kMaxWarpsPerCta = 16;
 constexpr int kMaxWarpsPerSm = 32;
+constexpr int kPrefetch = 8;        // posting chunks in flight per warp (registers)
+constexpr int kRing = 256;          // descriptors per warp (power of two)
+constexpr int kInfoSlots = 8;       // reads in flight between front and back end (power of two)
+constexpr int kGiantChunks = 64;    // a posting list longer than this many chunks is one GIANT descriptor
+constexpr int kMaxReadLen = (1 << 26) - 64;
 
-// ------------------------------------------------------------------------------- PTX wrappers
+// ------------------------------------------------------------------------------- tiny wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n.reg .pred p;\nWAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(bar), "r"(parity)
-      : "memory");
-}
-// global -> shared bulk copy (TMA, SASS UBLKCP); dst/src 16 B aligned, bytes % 16 == 0
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint2 lds_u64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_u64(uint32_t a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory"); }
+// streaming loads of posting data: read once, keep out of L1
+__device__ __forceinline__ float ldg_stream_f32(const void* p) { float v; asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v; }
+__device__ __forceinline__ uint32_t ldg_stream_u16(const void* p) { uint32_t v; asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
 
 // ------------------------------------------------------------------------------------ helpers
 // Cuckoo lookup: both candidate buckets (2 x 2 slots of 16 B) are loaded unconditionally.
@@ -101,73 +95,18 @@ __device__ __forceinline__ uint64_t planar_from_states(const uint8_t* c, int k, 
   return key;
 }
 
-struct WarpSmem {
-  float* S;          // [n_pad + 32]: the last 32 entries are per-lane dummies for idle lanes
-  uint8_t* cls;      // [2][64] character classes of the two groups in flight
-  uint8_t* stage;    // [2][stage_bytes] posting blocks staged by TMA
-  uint2* desc;       // [2][max_chunks] chunk descriptors of the staged groups
-  uint32_t bar;      // shared-space address of mbarrier[2]
-  int stage_bytes, max_chunks;
-};
-
-// A chunk = up to 32 postings of one window (one posting sub-block).  x = shared-space byte address of
-// its scores, y = number of postings m; its node ids start at x + 4*m.
-__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-
-// Adds the staged posting blocks of a whole group into S, chunk by chunk, in window order
-// (PlacementProcess.java:719-735).  Branch-free: idle lanes of a short chunk update their private dummy
-// entry.  The loads of chunk j+1 are issued before the read-modify-write of chunk j.
-__device__ __forceinline__ void accumulate_chunks(float* __restrict__ S, const uint2* __restrict__ dl, int n_chunks,
-                                                  int n_pad, float QT0, float T, int lane) {
-  const uint32_t lane4 = lane * 4, lane2 = lane * 2;
-  const uint32_t dummy = n_pad + lane;
-  uint2 d = dl[0];
-  float v = lds_f32(d.x + lane4);
-  uint32_t x = lds_u16(d.x + 4 * d.y + lane2);
-  uint2 dn = dl[1];
-#pragma unroll 1
-  for (int j = 0; j < n_chunks; j++) {
-    const float vn = lds_f32(dn.x + lane4);
-    const uint32_t xn = lds_u16(dn.x + 4 * dn.y + lane2);
-    const uint2 dnn = dl[j + 2];
-    const uint32_t idx = lane < d.y ? x : dummy;
-    float s = S[idx];
-    if (is_sentinel(s)) s = QT0;                   // C[x]==0 : L.add(x); S[x]+=Q*T   (:726-729)
-    S[idx] = __fadd_rn(s, __fsub_rn(v, T));        // S[x]+= v - T   (:733)
-    asm volatile("" ::: "memory");                 // keep the warp's shared-memory accesses in program order
-    d = dn; v = vn; x = xn; dn = dnn;
-  }
-  __syncwarp();
-}
-
-// Adds one posting block that sits in shared memory into S, in order.  PlacementProcess.java:719-735.
-__device__ __forceinline__ void accumulate_staged(float* __restrict__ S, const uint8_t* p, int len, float QT0, float T,
-                                                  int lane) {
-  for (int base = 0; base < len; base += kSubBlock, p += kSubBlockBytes) {
-    const int m = min(kSubBlock, len - base);
-    if (lane < m) {
-      const float v = *reinterpret_cast<const float*>(p + 4 * lane);
-      const unsigned x = *reinterpret_cast<const unsigned short*>(p + 4 * m + 2 * lane);
-      float s = S[x];
-      if (is_sentinel(s)) s = QT0;                 // C[x]==0 : L.add(x); S[x]+=Q*T   (:726-729)
-      S[x] = __fadd_rn(s, __fsub_rn(v, T));       // S[x]+= v - T   (:733)
-    }
-    __syncwarp();
-  }
-}
-
-// Same from global memory: posting lists larger than a stage, and the ambiguity path.
-__device__ __forceinline__ void accumulate_global(float* __restrict__ S, const uint8_t* p, int len, float QT0, float T,
-                                                  int lane) {
+// Adds one posting block straight from global memory into S, in order (PlacementProcess.java:719-735):
+// posting lists too long for the descriptor ring.
+__device__ __noinline__ void accumulate_global(float* __restrict__ S, const uint8_t* p, int len, float QT0, float T,
+                                               int lane) {
   for (int base = 0; base < len; base += kSubBlock, p += kSubBlockBytes) {
     const int m = min(kSubBlock, len - base);
     if (lane < m) {
       const float v = __ldg((const float*)p + lane);
       const unsigned x = __ldg((const unsigned short*)(p + 4 * m) + lane);
       float s = S[x];
-      if (is_sentinel(s)) s = QT0;
-      S[x] = __fadd_rn(s, __fsub_rn(v, T));
+      if (is_sentinel(s)) s = QT0;            // C[x]==0 : L.add(x); S[x]+=Q*T   (:726-729)
+      S[x] = __fadd_rn(s, __fsub_rn(v, T));   // S[x]+= v - T   (:733)
     }
     __syncwarp();
   }
@@ -175,11 +114,17 @@ __device__ __forceinline__ void accumulate_global(float* __restrict__ S, const u
 
 // One ambiguous window (<= max_amb ambiguous residues): treatAmbiguitiesWithMean / WithMax,
 // PlacementProcess.java:1129-1174 / 1185-1236.  Rare path; S_amb/C_amb live in a per-warp global
-// scratch that is all-zero between calls.  `cls` = class bytes of the window's first character on.
+// scratch that is all-zero between calls.  `seq` = the window's first character.
 __device__ __noinline__ void ambiguous_window(const AlphabetTables& c_alpha, const DbView& db, const CfgView& cfg,
-                                              float* __restrict__ S, const uint8_t* cls, uint32_t wbits, float QT,
-                                              float* Sa, int* Ca, int lane) {
-  // ambiguous offsets inside the window (ascending) and their alternative sets
+                                              float* __restrict__ S, const uint8_t* seq, float QT, float* Sa, int* Ca,
+                                              int lane) {
+  // class bytes of the window (k <= 31), and the ambiguous offsets inside it (ascending)
+  uint8_t cls[32];
+  uint32_t wbits = 0;
+  for (int i = 0; i < db.k; i++) {
+    cls[i] = c_alpha.cls[seq[i]];
+    if ((cls[i] & 0xC0) == kClsAmb) wbits |= 1u << i;
+  }
   const int o1 = __ffs(wbits) - 1;
   const uint32_t rest = wbits & (wbits - 1);
   const int o2 = rest ? __ffs(rest) - 1 : -1;
@@ -270,9 +215,9 @@ __device__ __forceinline__ uint32_t ordered_u32(float f) {
 //   2. nodes with score >= tau (a handful) go through a warp-shuffle insertion into the top-K list
 //      (lane i holds the i-th best; order: score desc, node id asc), and S is reset to the sentinel.
 // `emit` = false only resets (bad read).  Returns rows written, or -1 if no node was touched.
-__device__ __forceinline__ int select_and_reset(const CfgView& cfg, float* __restrict__ S, int n_pad, bool emit,
-                                                float* dump_row, int n_nodes, uint16_t* out_node, float* out_score,
-                                                double* out_lwr, int lane) {
+__device__ __noinline__ int select_and_reset(const CfgView& cfg, float* __restrict__ S, int n_pad, bool emit,
+                                             float* dump_row, int n_nodes, uint16_t* out_node, float* out_score,
+                                             double* out_lwr, int lane) {
   const int K = cfg.K;
   const float4 sent4 = make_float4(__uint_as_float(kSentinelBits), __uint_as_float(kSentinelBits),
                                    __uint_as_float(kSentinelBits), __uint_as_float(kSentinelBits));
@@ -374,64 +319,57 @@ __device__ __forceinline__ int select_and_reset(const CfgView& cfg, float* __res
   return rows;
 }
 
-// ------------------------------------------------------------------------------ group pipeline
-enum : int { kGrpLast = 1, kGrpBad = 2 };
+// --------------------------------------------------------------------------- descriptor stream
+// 8-byte descriptor.  x: CHUNK -> byte offset / 32 of the chunk inside the posting blocks, GIANT -> of
+// the block, others 0 (so that the back end may always prefetch from it).  y: [31:29] type,
+// [28:26] read-info slot, [25:0] payload (CHUNK: m = 1..32 postings; GIANT: postings of the list;
+// AMB: window start).
+enum : uint32_t { kDescChunk = 0u, kDescStart = 1u, kDescEnd = 2u, kDescAmb = 3u, kDescGiant = 4u };
+__device__ __forceinline__ uint32_t desc_y(uint32_t type, uint32_t slot, uint32_t payload) {
+  return (type << 29) | (slot << 26) | payload;
+}
 
-struct Group {
-  long long r;      // read index, < 0: the stream is exhausted
-  int Q;            // len - k + 1 of the read (may be <= 0)
-  int flags;        // kGrp*
-  int n_match, n_amb, n_skip;       // totals of the read, valid on its last group
-  uint32_t hitm, ambm, stagedm;     // windows (bit l = window g0+l) matched / ambiguous-to-treat / staged
-  uint32_t a_lo, a_hi;              // ambiguity bits of the 64 characters from g0 on
-  int buf;                          // stage / cls buffer
-  int n_chunks;                     // chunk descriptors written for the staged windows
-  float QT;
-  // per lane
-  uint32_t pk;                      // staged: (stage offset << 16) | n_postings
-  uint64_t meta;                    // table meta of the lane's window
+// what the back end needs to finish a read; written by the front end (START: r..QT, END: the rest)
+struct __align__(16) ReadInfo {
+  long long r;           // read index in the batch
+  const uint8_t* seq;    // first character
+  int len, Q;            // Q = len - k + 1 (may be <= 0)
+  float QT;              // (float)Q * T
+  int flags;             // kInfoBad
+  int n_match, n_amb, n_skip;
+  int pad[3];
 };
+static_assert(sizeof(ReadInfo) == 64, "ReadInfo is one 64 B slot");
+enum : int { kInfoBad = 1, kInfoTooLong = 2 };
 
-// front-end state of a warp: where the next group starts
+// front-end state of a warp (registers, warp-uniform)
 struct Front {
-  long long r = -1;
   unsigned long long rn_raw = 0;    // lane 0: result of the atomicAdd that fetched the NEXT read
   const uint8_t* s = nullptr;
-  long long len = 0, Ql = 0, g0 = 0;
+  int len = 0, Ql = 0, g0 = 0;
   int n_match = 0, n_amb = 0, n_skip = 0;
-  bool active = false;
-  int buf = 0;
+  int slot = 0;
+  bool active = false, done = false;
 };
 
 // --------------------------------------------------------------------------------- main kernel
 __global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1)
-place_kernel(const __grid_constant__ AlphabetTables c_alpha, DbView db, CfgView cfg, BatchView bt,
-             unsigned long long* work_counter, float* amb_S, int* amb_C, int n_pad, int per_warp_bytes,
-             int stage_bytes, int max_chunks) {
+place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_constant__ DbView db,
+             const __grid_constant__ CfgView cfg, const __grid_constant__ BatchView bt,
+             unsigned long long* work_counter, float* amb_S, int* amb_C, int n_pad, int per_warp_bytes) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int warps_per_cta = blockDim.x >> 5;
   // CTA-wide: character class table
-  uint8_t* cls_tab = smem;
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) cls_tab[i] = c_alpha.cls[i];
-  WarpSmem w;
-  {
-    uint8_t* base = smem + 256 + (size_t)warp * per_warp_bytes;
-    w.bar = smem_u32(base);           // 2 x u64
-    w.cls = base + 16;                // 2 x 64 B (+48 pad)
-    w.S = (float*)(base + 192);
-    w.stage = base + 192 + 4 * (size_t)(n_pad + 32);
-    w.stage_bytes = stage_bytes;
-    w.max_chunks = max_chunks;
-    w.desc = (uint2*)(w.stage + 2 * (size_t)stage_bytes);
-  }
-  for (int i = lane; i < n_pad + 32; i += 32) w.S[i] = __uint_as_float(kSentinelBits);
-  if (lane == 0) {
-    mbar_init(w.bar, 1);
-    mbar_init(w.bar + 8, 1);
-  }
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) smem[i] = c_alpha.cls[i];
+  const uint32_t cls_tab = smem_u32(smem);
+  // per warp: read-info slots | descriptor ring | S[n_pad + 32]
+  uint8_t* base = smem + 256 + (size_t)warp * per_warp_bytes;
+  ReadInfo* info = reinterpret_cast<ReadInfo*>(base);
+  const uint32_t ring = smem_u32(base + kInfoSlots * sizeof(ReadInfo));
+  float* S = reinterpret_cast<float*>(base + kInfoSlots * sizeof(ReadInfo) + kRing * 8);
+  for (int i = lane; i < n_pad + 32; i += 32) S[i] = __uint_as_float(kSentinelBits);
   __syncthreads();
   const size_t gw = (size_t)blockIdx.x * warps_per_cta + warp;
   float* Sa = amb_S + gw * n_pad;
@@ -439,214 +377,255 @@ place_kernel(const __grid_constant__ AlphabetTables c_alpha, DbView db, CfgView 
   const int k = db.k;
   const uint32_t kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
   const int K = cfg.K;
-  uint32_t phase = 0;  // bit b = parity to wait for on stage b
 
+  uint32_t head = 0, tail = 0;        // descriptor ring (free-running counters)
+  uint32_t info_head = 0, info_tail = 0;
   Front fe;
   if (lane == 0) fe.rn_raw = atomicAdd(work_counter, 1ull);
 
-  // ---- front end: produce the next group of the warp's stream -----------------------------
-  auto front = [&]() -> Group {
-    Group g;
-    g.r = -1; g.Q = 0; g.flags = 0; g.n_match = g.n_amb = g.n_skip = 0;
-    g.hitm = g.ambm = g.stagedm = 0; g.a_lo = g.a_hi = 0; g.buf = 0; g.n_chunks = 0; g.QT = 0.f; g.pk = 0; g.meta = 0;
+  auto push = [&](uint32_t x, uint32_t y) {  // one descriptor, by lane 0
+    if (lane == 0) sts_u64(ring + 8 * (head & (kRing - 1)), make_uint2(x, y));
+    head++;
+  };
+
+  // ---- front end: append the descriptors of the next group of windows ------------------------
+  // Called with at least kGiantChunks + 34 free ring entries.
+  auto front = [&]() {
     if (!fe.active) {
       const unsigned long long r = __shfl_sync(0xffffffffu, fe.rn_raw, 0);
-      if (r >= (unsigned long long)bt.n_reads) return g;
+      if (r >= (unsigned long long)bt.n_reads) { fe.done = true; return; }
       if (lane == 0) fe.rn_raw = atomicAdd(work_counter, 1ull);  // consumed when this read is finished
       const uint64_t o0 = bt.seq_off[r], o1 = bt.seq_off[r + 1];
-      fe.r = (long long)r;
       fe.s = bt.seq + (o0 - bt.seq_base);
-      fe.len = (long long)(o1 - o0);
+      const uint64_t len64 = o1 - o0;
+      const bool too_long = len64 > (uint64_t)kMaxReadLen;
+      fe.len = too_long ? 0 : (int)len64;
       fe.Ql = fe.len - k + 1;  // sk.getMerCount()
       fe.g0 = 0;
       fe.n_match = fe.n_amb = fe.n_skip = 0;
+      fe.slot = info_head & (kInfoSlots - 1);
+      info_head++;
       fe.active = true;
+      const float QT = __fmul_rn((float)fe.Ql, db.T);  // Q*PPStarThresholdAsLog10 (int*float)
+      if (lane == 0) {
+        ReadInfo& ri = info[fe.slot];
+        ri.r = (long long)r; ri.seq = fe.s; ri.len = fe.len; ri.Q = fe.Ql; ri.QT = QT;
+        ri.flags = too_long ? kInfoTooLong : 0;
+      }
+      push(0u, desc_y(kDescStart, fe.slot, 0u));
     }
-    g.r = fe.r;
-    g.Q = (int)fe.Ql;
-    g.QT = __fmul_rn((float)g.Q, db.T);  // Q*PPStarThresholdAsLog10 (int*float)
-    g.buf = fe.buf;
-    fe.buf ^= 1;
     const uint8_t* s = fe.s;
-    const long long len = fe.len, g0 = fe.g0;
+    const int len = fe.len, g0 = fe.g0;
+    bool bad = false, last = false;
     if (fe.Ql <= 0) {
       // no window; still an unsupported character aborts the reference before the length matters
-      const uint8_t c = (lane < len) ? cls_tab[s[lane]] : kClsPad;
-      if (__any_sync(0xffffffffu, c == kClsBad)) g.flags |= kGrpBad;
-      g.flags |= kGrpLast;
-      fe.active = false;
-      return g;
-    }
-    // classes of characters [g0, g0+64): 32 window starts + up to k-1 <= 30 look-ahead
-    const long long i0 = g0 + lane, i1 = i0 + 32;
-    const uint8_t c0 = (i0 < len) ? cls_tab[s[i0]] : kClsPad;
-    const uint8_t c1 = (i1 < len) ? cls_tab[s[i1]] : kClsPad;
-    if (__any_sync(0xffffffffu, c0 == kClsBad || c1 == kClsBad)) {
-      g.flags |= kGrpBad | kGrpLast;
-      fe.active = false;
-      return g;
-    }
-    // ambiguityCountPerMer of window g0+lane = popcount of the ambiguity bits of its k characters
-    const uint32_t a0 = __ballot_sync(0xffffffffu, (c0 & 0xC0) == kClsAmb);
-    const uint32_t a1 = __ballot_sync(0xffffffffu, (c1 & 0xC0) == kClsAmb);
-    g.a_lo = a0; g.a_hi = a1;
-    if (a0 | a1) {  // only the ambiguity path reads the class bytes back
-      uint8_t* cb = w.cls + 64 * g.buf;
-      cb[lane] = c0;
-      cb[lane + 32] = c1;
-      __syncwarp();
-    }
-    const uint32_t wbits = __funnelshift_r(a0, a1, lane) & kmask;
-    const int na = __popc(wbits);
-    const int nv = (int)min(32LL, fe.Ql - g0);  // windows left in the read
-    const bool valid = lane < nv;
-    // getNextByteWord (:224-233) + processQueries (:691-750)
-    const bool plain = valid && na == 0;
-    const bool skip = valid && na > 0 && (na > db.max_amb || !cfg.treat_amb);
-    const bool ambw = valid && na > 0 && !skip;
-    // planar key: plane p of window `lane` = bits [lane, lane+k) of the p-th state-bit ballots
-    uint64_t key = 0;
-    for (int p = 0; p < db.bits; p++) {
-      const uint32_t b0 = __ballot_sync(0xffffffffu, (c0 >> p) & 1u);
-      const uint32_t b1 = __ballot_sync(0xffffffffu, (c1 >> p) & 1u);
-      key |= (uint64_t)(__funnelshift_r(b0, b1, lane) & kmask) << (p * k);
-    }
-    uint64_t meta = 0;
-    bool found = false;
-    if (plain) found = table_probe(db, key, meta);
-    // stage assignment: windows are taken in order while their posting blocks fit into the stage;
-    // a block larger than a whole stage is read from global memory by the drain instead
-    const uint32_t n_post = (uint32_t)(meta & 0xFFFF);
-    const uint32_t bytes = (n_post * 6 + 31) & ~31u;
-    const bool giant = bytes > (uint32_t)stage_bytes;
-    const uint32_t sb = (found && !giant) ? bytes : 0u;
-    // one scan for both prefix sums: bytes in 32 B units (<= 2^15 over the warp) above the chunk count (< 2^13)
-    const uint32_t my_chunks = sb ? (n_post + 31) >> 5 : 0u;
-    uint32_t incl = (sb >> 5 << 13) | my_chunks;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += t;
-    }
-    const uint32_t incl_bytes = incl >> 13 << 5, incl_chunks = incl & 0x1FFFu;
-    const uint32_t nofit = __ballot_sync(0xffffffffu, incl_bytes > (uint32_t)stage_bytes);
-    int cons = nofit ? __ffs(nofit) - 1 : 32;  // >= 1: lane 0 alone always fits
-    cons = min(cons, nv);
-    const uint32_t lanes = cons >= 32 ? 0xffffffffu : ((1u << cons) - 1u);
-    g.hitm = __ballot_sync(0xffffffffu, found) & lanes;
-    g.ambm = __ballot_sync(0xffffffffu, ambw) & lanes;
-    g.stagedm = __ballot_sync(0xffffffffu, sb != 0u) & lanes;
-    fe.n_match += __popc(g.hitm);
-    fe.n_amb += __popc(g.ambm);
-    fe.n_skip += __popc(__ballot_sync(0xffffffffu, skip) & lanes);
-    g.meta = meta;
-    const uint32_t off = incl_bytes - sb;
-    g.pk = (off << 16) | n_post;
-    if (g.stagedm) {
-      const uint32_t last = __shfl_sync(0xffffffffu, incl, cons - 1);
-      const uint32_t total = last >> 13 << 5;
-      g.n_chunks = (int)(last & 0x1FFFu);
-      const uint32_t bar = w.bar + 8 * g.buf;
-      const uint32_t dst = smem_u32(w.stage + (size_t)g.buf * stage_bytes) + off;
-      fence_proxy_async();  // the drain's generic-proxy reads of this stage precede the async writes
-      if (lane == 0) mbar_expect_tx(bar, total);
-      __syncwarp();
-      if ((g.stagedm >> lane) & 1u) {
-        bulk_g2s(dst, db.blocks + (meta >> 16) * kBlockAlign, bytes, bar);
-        // chunk descriptors of this window, in window order
-        uint2* dl = w.desc + (size_t)g.buf * w.max_chunks + (incl_chunks - my_chunks);
-        uint32_t a = dst;
-        for (uint32_t left = n_post; left; a += kSubBlockBytes) {
-          const uint32_t m = min(left, 32u);
-          *dl++ = make_uint2(a, m);
-          left -= m;
-        }
-      }
-      if (lane < 2)  // two idle descriptors behind the list: the drain prefetches that far
-        w.desc[(size_t)g.buf * w.max_chunks + g.n_chunks + lane] = make_uint2(dst - off, 0u);
-      __syncwarp();
-    }
-    fe.g0 = g0 + cons;
-    if (fe.g0 >= fe.Ql) {
-      g.flags |= kGrpLast;
-      fe.active = false;
-    }
-    g.n_match = fe.n_match; g.n_amb = fe.n_amb; g.n_skip = fe.n_skip;
-    return g;
-  };
-
-  // ---- drain: accumulate one group; on the last group of a read, select and write the rows -
-  auto drain = [&](const Group& g) {
-    const float QT0 = __fadd_rn(0.0f, g.QT);  // S[x]+=Q*T on a zeroed S[x]
-    if (g.stagedm) {
-      mbar_wait(w.bar + 8 * g.buf, (phase >> g.buf) & 1u);
-      phase ^= 1u << g.buf;
-    }
-    const bool bad = g.flags & kGrpBad;
-    if (!bad && !(g.ambm | (g.hitm & ~g.stagedm))) {
-      // common case: every matched window of the group is staged
-      if (g.n_chunks) accumulate_chunks(w.S, w.desc + (size_t)g.buf * w.max_chunks, g.n_chunks, n_pad, QT0, db.T, lane);
-    } else if (!bad) {
-      const uint8_t* stage = w.stage + (size_t)g.buf * stage_bytes;
-      // windows in order: a node's S[x] must see its contributions in window order
-      for (uint32_t todo = g.hitm | g.ambm; todo;) {
-        const int l = __ffs(todo) - 1;
-        todo &= todo - 1;
-        if ((g.hitm >> l) & 1u) {
-          const uint32_t pk = __shfl_sync(0xffffffffu, g.pk, l);
-          if ((g.stagedm >> l) & 1u) {
-            accumulate_staged(w.S, stage + (pk >> 16), (int)(pk & 0xFFFF), QT0, db.T, lane);
-          } else {
-            const uint64_t mt = __shfl_sync(0xffffffffu, g.meta, l);
-            accumulate_global(w.S, db.blocks + (mt >> 16) * kBlockAlign, (int)(pk & 0xFFFF), QT0, db.T, lane);
-          }
-        } else {
-          const uint64_t amask = (uint64_t)g.a_lo | ((uint64_t)g.a_hi << 32);
-          ambiguous_window(c_alpha, db, cfg, w.S, w.cls + 64 * g.buf + l, (uint32_t)(amask >> l) & kmask, g.QT, Sa,
-                           Ca, lane);
-        }
-      }
-    }
-    if (!(g.flags & kGrpLast)) return;
-    // ---- selection / outputs
-    const long long r = g.r;
-    uint16_t* o_node = bt.node + r * K;
-    float* o_score = bt.score + r * K;
-    double* o_lwr = bt.lwr + r * K;
-    int status, rows = 0;
-    if (bad) {
-      select_and_reset(cfg, w.S, n_pad, false, nullptr, db.n_nodes, o_node, o_score, o_lwr, lane);
-      status = RP_STATUS_BAD_CHAR;
-    } else if (g.Q < 0) {
-      status = RP_STATUS_TOO_SHORT;
+      const uint32_t c = (lane < len) ? lds_u8(cls_tab + s[lane]) : kClsPad;
+      bad = __any_sync(0xffffffffu, c == kClsBad);
+      last = true;
     } else {
-      float* dump_row = bt.dump_scores ? bt.dump_scores + r * (size_t)db.n_nodes : nullptr;
-      rows = select_and_reset(cfg, w.S, n_pad, true, dump_row, db.n_nodes, o_node, o_score, o_lwr, lane);
-      status = rows < 0 ? RP_STATUS_UNPLACED : RP_STATUS_PLACED;  // L empty -> not placed (:797-806)
-    }
-    if (rows <= 0 && status != RP_STATUS_PLACED) {
-      rows = 0;
-      if (lane < K) { o_node[lane] = 0xFFFF; o_score[lane] = -INFINITY; o_lwr[lane] = 0.0; }
-    }
-    if (lane == 0) {
-      bt.n_rows[r] = rows;
-      bt.status[r] = status;
-      if (bt.counts) {
-        const bool ok = status <= RP_STATUS_UNPLACED;
-        int4 c = make_int4(ok ? (g.Q > 0 ? g.Q : 0) : 0, ok ? g.n_match : 0, ok ? g.n_amb : 0, ok ? g.n_skip : 0);
-        *reinterpret_cast<int4*>(bt.counts + 4 * r) = c;
+      // classes of characters [g0, g0+64): 32 window starts + up to k-1 <= 30 look-ahead
+      const int i0 = g0 + lane, i1 = i0 + 32;
+      const uint32_t c0 = (i0 < len) ? lds_u8(cls_tab + s[i0]) : kClsPad;
+      const uint32_t c1 = (i1 < len) ? lds_u8(cls_tab + s[i1]) : kClsPad;
+      bad = __any_sync(0xffffffffu, c0 == kClsBad || c1 == kClsBad);
+      if (!bad) {
+        // ambiguityCountPerMer of window g0+lane = popcount of the ambiguity bits of its k characters
+        const uint32_t a0 = __ballot_sync(0xffffffffu, (c0 & 0xC0) == kClsAmb);
+        const uint32_t a1 = __ballot_sync(0xffffffffu, (c1 & 0xC0) == kClsAmb);
+        const int na = __popc(__funnelshift_r(a0, a1, lane) & kmask);
+        const int nv = min(32, fe.Ql - g0);  // windows left in the read
+        const bool valid = lane < nv;
+        // getNextByteWord (:224-233) + processQueries (:691-750)
+        const bool plain = valid && na == 0;
+        const bool skip = valid && na > 0 && (na > db.max_amb || !cfg.treat_amb);
+        const bool ambw = valid && na > 0 && !skip;
+        // planar key: plane p of window `lane` = bits [lane, lane+k) of the p-th state-bit ballots
+        uint64_t key = 0;
+        for (int p = 0; p < db.bits; p++) {
+          const uint32_t b0 = __ballot_sync(0xffffffffu, (c0 >> p) & 1u);
+          const uint32_t b1 = __ballot_sync(0xffffffffu, (c1 >> p) & 1u);
+          key |= (uint64_t)(__funnelshift_r(b0, b1, lane) & kmask) << (p * k);
+        }
+        uint64_t meta = 0;
+        bool found = false;
+        if (plain) found = table_probe(db, key, meta);
+        // descriptors of this lane's window: one per <=32 postings, or a single GIANT / AMB marker
+        const uint32_t n_post = found ? (uint32_t)(meta & 0xFFFF) : 0u;
+        const uint32_t chunks = (n_post + 31) >> 5;
+        const bool giant = chunks > (uint32_t)kGiantChunks;
+        const uint32_t my = ambw ? 1u : giant ? 1u : chunks;
+        uint32_t incl = my;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += t;
+        }
+        // windows are taken in order while their descriptors fit (one entry stays free for END)
+        const uint32_t space = kRing - (head - tail) - 1u;
+        const uint32_t nofit = __ballot_sync(0xffffffffu, incl > space);
+        int cons = nofit ? __ffs(nofit) - 1 : 32;  // >= 1: one window needs <= kGiantChunks entries
+        cons = min(cons, nv);
+        const uint32_t lanes = cons >= 32 ? 0xffffffffu : ((1u << cons) - 1u);
+        fe.n_match += __popc(__ballot_sync(0xffffffffu, found) & lanes);
+        fe.n_amb += __popc(__ballot_sync(0xffffffffu, ambw) & lanes);
+        fe.n_skip += __popc(__ballot_sync(0xffffffffu, skip) & lanes);
+        if (lane < cons && my) {
+          uint32_t at = head + incl - my;
+          const uint32_t off32 = (uint32_t)(meta >> 16);
+          if (ambw) {
+            sts_u64(ring + 8 * (at & (kRing - 1)), make_uint2(0u, desc_y(kDescAmb, fe.slot, (uint32_t)(g0 + lane))));
+          } else if (giant) {
+            sts_u64(ring + 8 * (at & (kRing - 1)), make_uint2(off32, desc_y(kDescGiant, fe.slot, n_post)));
+          } else {
+            uint32_t o = off32;
+            for (uint32_t left = n_post; left; at++, o += kSubBlockBytes / kBlockAlign) {
+              const uint32_t m = min(left, 32u);
+              sts_u64(ring + 8 * (at & (kRing - 1)), make_uint2(o, desc_y(kDescChunk, 0u, m)));
+              left -= m;
+            }
+          }
+        }
+        head += __shfl_sync(0xffffffffu, incl, cons - 1);
+        fe.g0 = g0 + cons;
+        last = fe.g0 >= fe.Ql;
       }
+    }
+    if (bad || last) {
+      if (lane == 0) {
+        ReadInfo& ri = info[fe.slot];
+        if (bad) ri.flags |= kInfoBad;
+        ri.n_match = fe.n_match; ri.n_amb = fe.n_amb; ri.n_skip = fe.n_skip;
+      }
+      push(0u, desc_y(kDescEnd, fe.slot, 0u));
+      fe.active = false;
+    }
+    __syncwarp();
+  };
+
+  // ---- back end: rare descriptors ---------------------------------------------------------------
+  float QT = 0.f, QT0 = 0.f;  // of the read being accumulated
+  auto special = [&](uint2 d) {
+    const uint32_t type = d.y >> 29, slot = (d.y >> 26) & 7u, payload = d.y & 0x3FFFFFFu;
+    __syncwarp();
+    if (type == kDescStart) {
+      QT = info[slot].QT;
+      QT0 = __fadd_rn(0.0f, QT);  // S[x]+=Q*T on a zeroed S[x]
+    } else if (type == kDescGiant) {
+      accumulate_global(S, db.blocks + (size_t)d.x * kBlockAlign, (int)payload, QT0, db.T, lane);
+    } else if (type == kDescAmb) {
+      if (!(info[slot].flags & kInfoBad))
+        ambiguous_window(c_alpha, db, cfg, S, info[slot].seq + payload, QT, Sa, Ca, lane);
+    } else {  // kDescEnd: selection / outputs
+      const ReadInfo ri = info[slot];
+      const long long r = ri.r;
+      uint16_t* o_node = bt.node + r * K;
+      float* o_score = bt.score + r * K;
+      double* o_lwr = bt.lwr + r * K;
+      int status, rows = 0;
+      if (ri.flags & kInfoBad) {
+        select_and_reset(cfg, S, n_pad, false, nullptr, db.n_nodes, o_node, o_score, o_lwr, lane);
+        status = RP_STATUS_BAD_CHAR;
+      } else if (ri.flags & kInfoTooLong) {
+        status = RP_STATUS_TOO_LONG;
+      } else if (ri.Q < 0) {
+        status = RP_STATUS_TOO_SHORT;
+      } else {
+        float* dump_row = bt.dump_scores ? bt.dump_scores + r * (size_t)db.n_nodes : nullptr;
+        rows = select_and_reset(cfg, S, n_pad, true, dump_row, db.n_nodes, o_node, o_score, o_lwr, lane);
+        status = rows < 0 ? RP_STATUS_UNPLACED : RP_STATUS_PLACED;  // L empty -> not placed (:797-806)
+      }
+      if (rows <= 0 && status != RP_STATUS_PLACED) {
+        rows = 0;
+        if (lane < K) { o_node[lane] = 0xFFFF; o_score[lane] = -INFINITY; o_lwr[lane] = 0.0; }
+      }
+      if (lane == 0) {
+        bt.n_rows[r] = rows;
+        bt.status[r] = status;
+        if (bt.counts) {
+          const bool ok = status <= RP_STATUS_UNPLACED;
+          int4 c = make_int4(ok ? (ri.Q > 0 ? ri.Q : 0) : 0, ok ? ri.n_match : 0, ok ? ri.n_amb : 0, ok ? ri.n_skip : 0);
+          *reinterpret_cast<int4*>(bt.counts + 4 * r) = c;
+        }
+      }
+      info_tail++;
+      __syncwarp();
     }
   };
 
-  Group cur = front();
-  while (cur.r >= 0) {
-    Group nxt;
-    // after a bad character the read is abandoned: nothing of it may be in flight past its last group
-    nxt = front();
-    drain(cur);
-    cur = nxt;
+  // ---- the stream ---------------------------------------------------------------------------------
+  // Slot u of the register pipeline holds the descriptor at a ring position == u (mod kPrefetch), with
+  // its posting data already requested; step u of the unrolled round consumes position `tail`.
+  const uint32_t lane4 = lane * 4, lane2 = lane * 2;
+  const uint32_t dummy = n_pad + lane;
+  float pv[kPrefetch];
+  uint32_t px[kPrefetch], py[kPrefetch];
+#pragma unroll
+  for (int u = 0; u < kPrefetch; u++) { pv[u] = 0.f; px[u] = 0u; py[u] = 0u; }
+  auto fetch = [&](int u, uint32_t pos) {  // descriptor `pos` (an idle one if past the head) -> slot u
+    uint2 d = lds_u64(ring + 8 * (pos & (kRing - 1)));
+    if ((int32_t)(head - pos) <= 0) d = make_uint2(0u, 0u);
+    const uint32_t mm = (d.y >> 29) == kDescChunk ? (d.y & 0x3Fu) : 0u;
+    const uint8_t* p = db.blocks + (size_t)d.x * kBlockAlign;
+    py[u] = d.y;
+    if (lane < mm) {
+      pv[u] = ldg_stream_f32(p + lane4);
+      px[u] = ldg_stream_u16(p + 4 * mm + lane2);
+    }
+  };
+  const uint32_t kNeed = kGiantChunks + 34;  // free entries one front() call may use
+
+// one step of the round: a CHUNK descriptor is consumed here, anything else leaves through `slow`
+#define RP_STEP(u)                                                                                     \
+  case u: {                                                                                            \
+    if (head == tail) break;                                                                           \
+    const uint32_t y = py[u];                                                                          \
+    if (y - 1u >= 0x3Fu) { slow = true; break; } /* not a CHUNK with 1..63 postings */                 \
+    const uint32_t idx = lane < y ? px[u] : dummy;                                                     \
+    float s_ = S[idx];                                                                                 \
+    if (is_sentinel(s_)) s_ = QT0;                    /* C[x]==0 : L.add(x); S[x]+=Q*T   (:726-729) */ \
+    S[idx] = __fadd_rn(s_, __fsub_rn(pv[u], db.T));   /* S[x]+= v - T   (:733) */                      \
+    asm volatile("" ::: "memory");                    /* keep the warp's smem accesses in program order */ \
+    tail++;                                                                                            \
+    fetch(u, tail + kPrefetch - 1);                                                                    \
   }
+
+  for (;;) {
+    // top the ring up (the prefetched chunks stay in flight meanwhile)
+    if (head - tail < 64u) {
+      while (!fe.done && head - tail < 128u && kRing - (head - tail) >= kNeed) {
+        if (!fe.active && info_head - info_tail >= (uint32_t)kInfoSlots) break;  // back end must finish a read first
+        front();
+      }
+      if (head == tail) break;  // nothing queued and nothing left to read
+    }
+    bool slow = false;
+    switch (tail & (kPrefetch - 1)) {
+      RP_STEP(0) RP_STEP(1) RP_STEP(2) RP_STEP(3) RP_STEP(4) RP_STEP(5) RP_STEP(6) RP_STEP(7)
+    }
+    static_assert(kPrefetch == 8, "RP_STEP list");
+    if (!slow) continue;
+    // ---- slow path: the slot of position `tail` holds a marker, or was fetched before the descriptor existed
+    const uint2 d = lds_u64(ring + 8 * (tail & (kRing - 1)));
+    const bool is_chunk = (d.y >> 29) == kDescChunk;
+    if (!is_chunk) {
+      special(d);
+      tail++;
+    }
+    // (re)load the slot: the descriptor at `tail` itself if it is a chunk that was fetched too early,
+    // else the one kPrefetch-1 ahead of the new tail
+    const uint32_t pos = is_chunk ? tail : tail + kPrefetch - 1;
+    switch (pos & (kPrefetch - 1)) {
+      case 0: fetch(0, pos); break;
+      case 1: fetch(1, pos); break;
+      case 2: fetch(2, pos); break;
+      case 3: fetch(3, pos); break;
+      case 4: fetch(4, pos); break;
+      case 5: fetch(5, pos); break;
+      case 6: fetch(6, pos); break;
+      default: fetch(7, pos); break;
+    }
+  }
+#undef RP_STEP
 }
 
 // ------------------------------------------------------------------------- diagnostics kernel
@@ -721,40 +700,33 @@ __global__ void fill_f32_kernel(float* p, size_t n, float v) {
 }
 
 // ------------------------------------------------------------------------------ host plumbing
-// warps per CTA x CTAs per SM maximising resident warps under the shared-memory budget
-// Shared memory per warp = S[n_pad] + two posting stages; warps per CTA x CTAs per SM maximise the
-// resident warps under the 227 KB budget.  The stage holds ~32 average posting blocks (a whole group
-// of windows); RP_STAGE_BYTES overrides it for tuning runs.
+// Shared memory per warp = read-info slots + descriptor ring + S[n_pad + 32]; warps per CTA x CTAs per
+// SM maximise the resident warps under the 227 KB budget and the register file.
 int compute_geometry(const rp_db* db, DeviceCtx* dc) {
   LaunchGeom g;
   g.n_pad = (db->desc.n_nodes + 127) & ~127;
   const size_t cta_fixed = 256;
   const size_t optin = dc->smem_optin;         // 227 KB on sm_100
   const size_t sm_total = optin + 1024;        // 228 KB per SM, 1 KB reserved per resident CTA
-  const double mean_block = db->desc.n_keys ? (double)db->block_bytes / (double)db->desc.n_keys : 32.0;
-  long stage = (long)(32.0 * mean_block * 0.85);
-  if (const char* e = getenv("RP_STAGE_BYTES")) stage = atol(e);
-  stage = std::max(1024L, std::min(stage, 32768L - 128));
-  stage = (stage + 127) & ~127L;
-  for (;;) {
-    g.stage_bytes = (int)stage;
-    g.max_chunks = 32 + g.stage_bytes / kSubBlockBytes + 3;  // one per window + one per extra sub-block + 2 idle
-    g.per_warp_bytes = (192 + 4 * (size_t)(g.n_pad + 32) + 2 * (size_t)g.stage_bytes + 2 * 8 * (size_t)g.max_chunks + 127) & ~(size_t)127;
-    // big trees: give the stages up before giving the accumulator up
-    if (cta_fixed + 2 * g.per_warp_bytes <= optin || stage <= 1024) break;
-    stage = std::max(1024L, (stage / 2 + 127) & ~127L);
-  }
+  g.per_warp_bytes = (kInfoSlots * sizeof(ReadInfo) + kRing * 8 + 4 * (size_t)(g.n_pad + 32) + 127) & ~(size_t)127;
   if (cta_fixed + g.per_warp_bytes > optin)
     return set_error(RP_E_UNSUPPORTED,
                      "n_nodes=%d needs %zu B of shared memory per read (> %zu B per CTA); trees beyond ~56k nodes "
                      "are not supported by the shared-memory accumulator",
                      db->desc.n_nodes, g.per_warp_bytes, optin);
+  RP_CUDA_TRY(cudaSetDevice(dc->device));
+  cudaFuncAttributes fa;
+  RP_CUDA_TRY(cudaFuncGetAttributes(&fa, place_kernel));
+  const int reg_warps = std::max(1, 65536 / (32 * std::max(1, fa.numRegs)));  // warps per SM the registers allow
+  int max_warps_sm = std::min(kMaxWarpsPerSm, reg_warps);
+  if (const char* e = getenv("RP_WARPS_PER_SM")) max_warps_sm = std::max(1, std::min(max_warps_sm, atoi(e)));
   int best_total = 0;
   for (int c = 1; c <= 8; c++) {
     const size_t budget = std::min(optin, sm_total / c - 1024);
     if (budget < cta_fixed + g.per_warp_bytes) break;
     int wpc = (int)std::min<size_t>(kMaxWarpsPerCta, (budget - cta_fixed) / g.per_warp_bytes);
-    if (c * wpc > kMaxWarpsPerSm) wpc = std::max(1, kMaxWarpsPerSm / c);
+    if (c * wpc > max_warps_sm) wpc = max_warps_sm / c;
+    if (wpc < 1) break;
     if (c * wpc > best_total) {
       best_total = c * wpc;
       g.ctas_per_sm = c;
@@ -762,9 +734,8 @@ int compute_geometry(const rp_db* db, DeviceCtx* dc) {
     }
   }
   g.smem_bytes = cta_fixed + g.warps_per_cta * g.per_warp_bytes;
-  RP_CUDA_TRY(cudaSetDevice(dc->device));
   RP_CUDA_TRY(cudaFuncSetAttribute(place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-  // what the hardware really keeps resident (registers may bind before shared memory does)
+  // what the hardware really keeps resident
   int resident = 0;
   RP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, place_kernel, g.warps_per_cta * 32, g.smem_bytes));
   if (resident < 1) return set_error(RP_E_CUDA, "placement kernel does not fit on an SM (smem %zu B)", g.smem_bytes);
@@ -812,7 +783,7 @@ static int launch_place(const rp_db* db, DeviceCtx* dc, StreamCtx* sc, const rp_
   if (time_it) RP_CUDA_TRY(cudaEventRecord(sc->ev_k0, stream));
   place_kernel<<<g.grid, g.warps_per_cta * 32, g.smem_bytes, stream>>>(
       db->alpha, make_db_view(db, dc), make_cfg_view(cfg), bt, sc->d_counter, sc->d_amb_S, sc->d_amb_C, g.n_pad,
-      (int)g.per_warp_bytes, g.stage_bytes, g.max_chunks);
+      (int)g.per_warp_bytes);
   RP_CUDA_TRY(cudaGetLastError());
   g_kernel_launches.fetch_add(1);
   if (time_it) RP_CUDA_TRY(cudaEventRecord(sc->ev_k1, stream));
