@@ -346,9 +346,9 @@ int rp_db_load(const rp_db_desc* desc, const uint64_t* keys, const uint64_t* off
       dc->smem_optin = prop.sharedMemPerBlockOptin;
       e = cudaMalloc((void**)&dc->d_table, img.n_buckets * 32);
     }
-    // +256 B: idle lanes of the last block's last chunk may address (never load) past its end, and an
+    // +512 B: idle lanes of the last block's last chunk may address (never load) past its end, and an
     // idle descriptor prefetches nothing from offset 0
-    if (e == cudaSuccess) e = cudaMalloc((void**)&dc->d_blocks, img.block_bytes + 256);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dc->d_blocks, img.block_bytes + 512);
     if (e == cudaSuccess) e = cudaMemcpy(dc->d_table, img.table.data(), img.n_buckets * 32, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && img.block_bytes)
       e = cudaMemcpy(dc->d_blocks, img.blocks, img.block_bytes, cudaMemcpyHostToDevice);

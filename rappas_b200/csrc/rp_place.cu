@@ -54,8 +54,15 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatil
 __device__ __forceinline__ uint2 lds_u64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
 __device__ __forceinline__ void sts_u64(uint32_t a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory"); }
 // streaming loads of posting data: read once, keep out of L1
-__device__ __forceinline__ float ldg_stream_f32(const void* p) { float v; asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v; }
-__device__ __forceinline__ uint32_t ldg_stream_u16(const void* p) { uint32_t v; asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+// (score, node id) of one posting, only in lanes < m; branch-free
+__device__ __forceinline__ void ldg_posting(float& v, uint32_t& x, const void* pv, const void* px, uint32_t lane, uint32_t m) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.lt.u32 p, %4, %5;\n"
+      "@p ld.global.nc.L1::no_allocate.f32 %0, [%2];\n"
+      "@p ld.global.nc.L1::no_allocate.u16 %1, [%3];\n}"
+      : "+f"(v), "+r"(x)
+      : "l"(pv), "l"(px), "r"(lane), "r"(m));
+}
 
 // ------------------------------------------------------------------------------------ helpers
 // Cuckoo lookup: both candidate buckets (2 x 2 slots of 16 B) are loaded unconditionally.
@@ -324,7 +331,7 @@ __device__ __noinline__ int select_and_reset(const CfgView& cfg, float* __restri
 // the block, others 0 (so that the back end may always prefetch from it).  y: [31:29] type,
 // [28:26] read-info slot, [25:0] payload (CHUNK: m = 1..32 postings; GIANT: postings of the list;
 // AMB: window start).
-enum : uint32_t { kDescChunk = 0u, kDescStart = 1u, kDescEnd = 2u, kDescAmb = 3u, kDescGiant = 4u };
+enum : uint32_t { kDescChunk = 0u, kDescStart = 1u, kDescEnd = 2u, kDescAmb = 3u, kDescGiant = 4u, kDescStop = 5u };
 __device__ __forceinline__ uint32_t desc_y(uint32_t type, uint32_t slot, uint32_t payload) {
   return (type << 29) | (slot << 26) | payload;
 }
@@ -393,7 +400,13 @@ place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_consta
   auto front = [&]() {
     if (!fe.active) {
       const unsigned long long r = __shfl_sync(0xffffffffu, fe.rn_raw, 0);
-      if (r >= (unsigned long long)bt.n_reads) { fe.done = true; return; }
+      if (r >= (unsigned long long)bt.n_reads) {
+        fe.done = true;
+        push(0u, desc_y(kDescStop, 0u, 0u));
+        if (lane < kPrefetch) sts_u64(ring + 8 * ((head + lane) & (kRing - 1)), make_uint2(0u, 0u));
+        __syncwarp();
+        return;
+      }
       if (lane == 0) fe.rn_raw = atomicAdd(work_counter, 1ull);  // consumed when this read is finished
       const uint64_t o0 = bt.seq_off[r], o1 = bt.seq_off[r + 1];
       fe.s = bt.seq + (o0 - bt.seq_base);
@@ -461,7 +474,7 @@ place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_consta
           if (lane >= d) incl += t;
         }
         // windows are taken in order while their descriptors fit (one entry stays free for END)
-        const uint32_t space = kRing - (head - tail) - 1u;
+        const uint32_t space = kRing - (head - tail) - 1u - kPrefetch;
         const uint32_t nofit = __ballot_sync(0xffffffffu, incl > space);
         int cons = nofit ? __ffs(nofit) - 1 : 32;  // >= 1: one window needs <= kGiantChunks entries
         cons = min(cons, nv);
@@ -499,6 +512,8 @@ place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_consta
       push(0u, desc_y(kDescEnd, fe.slot, 0u));
       fe.active = false;
     }
+    // the kPrefetch entries behind the head read as idle descriptors: the back end may look that far
+    if (lane < kPrefetch) sts_u64(ring + 8 * ((head + lane) & (kRing - 1)), make_uint2(0u, 0u));
     __syncwarp();
   };
 
@@ -555,35 +570,34 @@ place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_consta
   // ---- the stream ---------------------------------------------------------------------------------
   // Slot u of the register pipeline holds the descriptor at a ring position == u (mod kPrefetch), with
   // its posting data already requested; step u of the unrolled round consumes position `tail`.
-  const uint32_t lane4 = lane * 4, lane2 = lane * 2;
+  // Entries behind the head are zero (idle), the last descriptor of the stream is STOP.
+  const uint8_t* const base_v = db.blocks + lane * 4;   // per-lane bases: chunk address = base + 32 * desc.x
+  const uint8_t* const base_x = db.blocks + lane * 2;
   const uint32_t dummy = n_pad + lane;
+  const float T = db.T;
   float pv[kPrefetch];
   uint32_t px[kPrefetch], py[kPrefetch];
 #pragma unroll
   for (int u = 0; u < kPrefetch; u++) { pv[u] = 0.f; px[u] = 0u; py[u] = 0u; }
-  auto fetch = [&](int u, uint32_t pos) {  // descriptor `pos` (an idle one if past the head) -> slot u
-    uint2 d = lds_u64(ring + 8 * (pos & (kRing - 1)));
-    if ((int32_t)(head - pos) <= 0) d = make_uint2(0u, 0u);
-    const uint32_t mm = (d.y >> 29) == kDescChunk ? (d.y & 0x3Fu) : 0u;
-    const uint8_t* p = db.blocks + (size_t)d.x * kBlockAlign;
+  auto fetch = [&](int u, uint32_t pos) {  // descriptor `pos` -> slot u, its postings requested
+    const uint2 d = lds_u64(ring + ((pos << 3) & (8 * kRing - 8)));
+    // markers carry x = 0 and are never consumed as chunks: whatever their low bits request is harmless
+    const uint32_t mm = d.y & 0x3Fu;
+    const uint8_t* a = base_v + ((uint64_t)d.x << 5);
     py[u] = d.y;
-    if (lane < mm) {
-      pv[u] = ldg_stream_f32(p + lane4);
-      px[u] = ldg_stream_u16(p + 4 * mm + lane2);
-    }
+    ldg_posting(pv[u], px[u], a, base_x + ((uint64_t)d.x << 5) + 4 * mm, (uint32_t)lane, mm);
   };
-  const uint32_t kNeed = kGiantChunks + 34;  // free entries one front() call may use
+  const uint32_t kNeed = kGiantChunks + 34 + kPrefetch;  // free entries one front() call may use
 
 // one step of the round: a CHUNK descriptor is consumed here, anything else leaves through `slow`
 #define RP_STEP(u)                                                                                     \
   case u: {                                                                                            \
-    if (head == tail) break;                                                                           \
     const uint32_t y = py[u];                                                                          \
-    if (y - 1u >= 0x3Fu) { slow = true; break; } /* not a CHUNK with 1..63 postings */                 \
+    if (y - 1u >= 0x3Fu) break; /* not a CHUNK with 1..63 postings: marker, idle or stale slot */      \
     const uint32_t idx = lane < y ? px[u] : dummy;                                                     \
     float s_ = S[idx];                                                                                 \
     if (is_sentinel(s_)) s_ = QT0;                    /* C[x]==0 : L.add(x); S[x]+=Q*T   (:726-729) */ \
-    S[idx] = __fadd_rn(s_, __fsub_rn(pv[u], db.T));   /* S[x]+= v - T   (:733) */                      \
+    S[idx] = __fadd_rn(s_, __fsub_rn(pv[u], T));      /* S[x]+= v - T   (:733) */                      \
     asm volatile("" ::: "memory");                    /* keep the warp's smem accesses in program order */ \
     tail++;                                                                                            \
     fetch(u, tail + kPrefetch - 1);                                                                    \
@@ -596,17 +610,19 @@ place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_consta
         if (!fe.active && info_head - info_tail >= (uint32_t)kInfoSlots) break;  // back end must finish a read first
         front();
       }
-      if (head == tail) break;  // nothing queued and nothing left to read
     }
-    bool slow = false;
+    const uint32_t tail0 = tail;
     switch (tail & (kPrefetch - 1)) {
       RP_STEP(0) RP_STEP(1) RP_STEP(2) RP_STEP(3) RP_STEP(4) RP_STEP(5) RP_STEP(6) RP_STEP(7)
     }
     static_assert(kPrefetch == 8, "RP_STEP list");
-    if (!slow) continue;
+    if (tail - tail0 == (uint32_t)kPrefetch - (tail0 & (kPrefetch - 1))) continue;  // the round ran to its end
     // ---- slow path: the slot of position `tail` holds a marker, or was fetched before the descriptor existed
-    const uint2 d = lds_u64(ring + 8 * (tail & (kRing - 1)));
-    const bool is_chunk = (d.y >> 29) == kDescChunk;
+    if (head == tail) continue;  // (cannot happen before STOP: the front end always appends when the ring is short)
+    const uint2 d = lds_u64(ring + ((tail << 3) & (8 * kRing - 8)));
+    const uint32_t type = d.y >> 29;
+    if (type == kDescStop) break;
+    const bool is_chunk = type == kDescChunk;
     if (!is_chunk) {
       special(d);
       tail++;
