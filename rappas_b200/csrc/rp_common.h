@@ -137,7 +137,9 @@ struct StreamCtx {
 struct LaunchGeom {
   int warps_per_cta = 0, ctas_per_sm = 0, grid = 0;
   size_t smem_bytes = 0, per_warp_bytes = 0;
-  int n_pad = 0;        // S[] entries per warp, multiple of 128
+  int n_pad = 0;        // S[] entries per pair, multiple of 128
+  int stage_bytes = 0;  // one posting stage (kStages per pair), multiple of 128
+  int max_chunks = 0;   // chunk descriptors per stage
 };
 
 struct DeviceCtx {

@@ -10,18 +10,21 @@
 //   K4  selection + LWR         fillBestScoreList (:396-451), computeWeightRatio[Shift] (:384-394),
 //                               row loop (:974-1000)
 //
-// Execution model: ONE WARP OWNS ONE READ AT A TIME and is split into a front end and a
-// back end that talk through a per-warp ring of 8-byte DESCRIPTORS in shared memory:
-//   front end   classifies 64 characters, builds the 32 planar k-mer keys of a group of windows from
-//               ballots, probes the cuckoo table (both buckets, one memory round trip) and appends, in
-//               window order, one CHUNK descriptor per <=32 postings of every matched window (plus
-//               START / END markers per read and AMB / GIANT markers for the rare slow paths);
-//   back end    walks the descriptor stream with a kPrefetch-deep register pipeline: the two coalesced
-//               loads of chunk j+kPrefetch (scores, node ids) are issued while chunk j is added into the
-//               read's score vector S[n_nodes] in shared memory.
-// The front end runs whenever the ring runs low, so table probes, posting gathers and the accumulation
-// of (possibly different) reads overlap inside one warp, and nothing but S and the small ring lives in
-// shared memory (about 2.5x more resident warps than staging the postings there).
+// Execution model: A PAIR OF WARPS OWNS ONE READ AT A TIME.  The CTA is warp-specialised:
+//   producer warp (K1+K2)  walks the read in GROUPS of up to 32 consecutive windows: classifies 64
+//               characters, builds the 32 planar k-mer keys from ballots, probes the cuckoo table (both
+//               buckets, one memory round trip), prefix-sums the posting-block sizes and issues one
+//               cp.async.bulk (TMA) per matched window into one of the pair's shared-memory STAGES, with
+//               a list of chunk descriptors (<= 32 postings each) beside it; completion is counted on the
+//               stage's `full` mbarrier;
+//   consumer warp (K3+K4)  waits for the stage, adds the posting chunks into the read's score vector
+//               S[n_nodes] (shared memory) in window order, hands the stage back through its `empty`
+//               mbarrier, and on the last group of a read selects the top-K nodes and writes the rows.
+// Producers only need registers, so the pair doubles the resident warps at the shared-memory cost of one:
+// table probes and posting gathers of the next groups (possibly of the next read) are in flight while
+// the current one is being accumulated.  Register prefetching cannot do this: a warp has 6 scoreboard
+// slots, so ptxas drains deep LDG pipelines at every loop back-edge (profiles/r01_v4_*), whereas bulk
+// copies are tracked by mbarriers and any number can be outstanding.
 // The accumulation uses plain (non-atomic) shared-memory read-modify-writes: node ids are distinct
 // inside a k-mer's posting list, so the 32 lanes of one instruction never collide, and because a node
 // receives at most one posting per window and the windows are visited in order, every S[x] is
@@ -40,29 +43,40 @@
 namespace rp {
 
 constexpr uint32_t kSentinelBits = 0x7FFFFFFFu;  // a NaN no arithmetic here produces
-constexpr int kMaxWarpsPerCta = 16;
-constexpr int kMaxWarpsPerSm = 32;
-constexpr int kPrefetch = 8;        // posting chunks in flight per warp (registers)
-constexpr int kRing = 256;          // descriptors per warp (power of two)
-constexpr int kInfoSlots = 8;       // reads in flight between front and back end (power of two)
-constexpr int kGiantChunks = 64;    // a posting list longer than this many chunks is one GIANT descriptor
-constexpr int kMaxReadLen = (1 << 26) - 64;
+constexpr int kMaxPairsPerCta = 12;  // producer warps 0..P-1, consumer warps P..2P-1
+constexpr int kStages = 2;           // posting stages per pair
+constexpr int kMaxReadLen = (1 << 30);
 
-// ------------------------------------------------------------------------------- tiny wrappers
+// ------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint2 lds_u64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
 __device__ __forceinline__ void sts_u64(uint32_t a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory"); }
-// streaming loads of posting data: read once, keep out of L1
-// (score, node id) of one posting, only in lanes < m; branch-free
-__device__ __forceinline__ void ldg_posting(float& v, uint32_t& x, const void* pv, const void* px, uint32_t lane, uint32_t m) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.lt.u32 p, %4, %5;\n"
-      "@p ld.global.nc.L1::no_allocate.f32 %0, [%2];\n"
-      "@p ld.global.nc.L1::no_allocate.u16 %1, [%3];\n}"
-      : "+f"(v), "+r"(x)
-      : "l"(pv), "l"(px), "r"(lane), "r"(m));
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy (TMA, SASS UBLKCP); dst/src 16 B aligned, bytes % 16 == 0
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------ helpers
 // Cuckoo lookup: both candidate buckets (2 x 2 slots of 16 B) are loaded unconditionally.
@@ -326,127 +340,149 @@ __device__ __noinline__ int select_and_reset(const CfgView& cfg, float* __restri
   return rows;
 }
 
-// --------------------------------------------------------------------------- descriptor stream
-// 8-byte descriptor.  x: CHUNK -> byte offset / 32 of the chunk inside the posting blocks, GIANT -> of
-// the block, others 0 (so that the back end may always prefetch from it).  y: [31:29] type,
-// [28:26] read-info slot, [25:0] payload (CHUNK: m = 1..32 postings; GIANT: postings of the list;
-// AMB: window start).
-enum : uint32_t { kDescChunk = 0u, kDescStart = 1u, kDescEnd = 2u, kDescAmb = 3u, kDescGiant = 4u, kDescStop = 5u };
-__device__ __forceinline__ uint32_t desc_y(uint32_t type, uint32_t slot, uint32_t payload) {
-  return (type << 29) | (slot << 26) | payload;
+// ------------------------------------------------------------------------ producer / consumer
+// What the producer hands over with a stage (warp-uniform part; 64 B, written by its lane 0).
+enum : int { kGrpLast = 1, kGrpBad = 2, kGrpTooLong = 4, kGrpStop = 8 };
+struct __align__(16) StageHdr {
+  long long r;           // read index in the batch
+  const uint8_t* seq;    // character g0 of the read: first window of this group
+  int Q;                 // len - k + 1 of the read (may be <= 0)
+  float QT;              // (float)Q * T
+  int flags;             // kGrp*
+  int n_match, n_amb, n_skip;       // totals of the read, valid on its last group
+  int n_chunks;                     // chunk descriptors of the staged windows
+  uint32_t hitm, ambm, stagedm;     // windows (bit l = window g0+l) matched / ambiguous-to-treat / staged
+  int pad[2];
+};
+static_assert(sizeof(StageHdr) == 64, "StageHdr is one 64 B slot");
+
+// shared memory of one pair, in this order (offsets from the pair's base):
+//   [0,32)    full[kStages], empty[kStages] mbarriers
+//   [64, ..)  kStages x { StageHdr (64 B) | pk u32[32] | meta u64[32] }  = 448 B each
+//   stage     kStages x stage_bytes        posting blocks as they lie in HBM
+//   desc      kStages x max_chunks x 8 B   chunk descriptors {shared address of the scores, m}
+//   S         f32[n_pad + 32]              (+32: per-lane dummies for the idle lanes of a short chunk)
+constexpr int kStageMetaBytes = 64 + 128 + 256;
+
+// Adds the staged posting blocks of a whole group into S, chunk by chunk, in window order
+// (PlacementProcess.java:719-735).  Branch-free: idle lanes of a short chunk update their private dummy
+// entry.  The loads of chunk j+1 are issued before the read-modify-write of chunk j.
+__device__ __forceinline__ void accumulate_chunks(float* __restrict__ S, uint32_t dl, int n_chunks, int n_pad, float QT0,
+                                                  float T, int lane) {
+  const uint32_t lane4 = lane * 4, lane2 = lane * 2;
+  const uint32_t dummy = n_pad + lane;
+  uint2 d = lds_u64(dl);
+  float v = lds_f32(d.x + lane4);
+  uint32_t x = lds_u16(d.x + 4 * d.y + lane2);
+  uint2 dn = lds_u64(dl + 8);
+#pragma unroll 1
+  for (int j = 0; j < n_chunks; j++) {
+    const float vn = lds_f32(dn.x + lane4);
+    const uint32_t xn = lds_u16(dn.x + 4 * dn.y + lane2);
+    const uint2 dnn = lds_u64(dl + 8 * (j + 2));
+    const uint32_t idx = lane < d.y ? x : dummy;
+    float s = S[idx];
+    if (is_sentinel(s)) s = QT0;                   // C[x]==0 : L.add(x); S[x]+=Q*T   (:726-729)
+    S[idx] = __fadd_rn(s, __fsub_rn(v, T));        // S[x]+= v - T   (:733)
+    asm volatile("" ::: "memory");                 // keep the warp's shared-memory accesses in program order
+    d = dn; v = vn; x = xn; dn = dnn;
+  }
+  __syncwarp();
 }
 
-// what the back end needs to finish a read; written by the front end (START: r..QT, END: the rest)
-struct __align__(16) ReadInfo {
-  long long r;           // read index in the batch
-  const uint8_t* seq;    // first character
-  int len, Q;            // Q = len - k + 1 (may be <= 0)
-  float QT;              // (float)Q * T
-  int flags;             // kInfoBad
-  int n_match, n_amb, n_skip;
-  int pad[3];
-};
-static_assert(sizeof(ReadInfo) == 64, "ReadInfo is one 64 B slot");
-enum : int { kInfoBad = 1, kInfoTooLong = 2 };
+// Same for one posting block, staged (p = shared address) -- slow path of a group with special windows
+__device__ __forceinline__ void accumulate_staged(float* __restrict__ S, uint32_t p, int len, float QT0, float T, int lane) {
+  for (int base = 0; base < len; base += kSubBlock, p += kSubBlockBytes) {
+    const int m = min(kSubBlock, len - base);
+    if (lane < m) {
+      const float v = lds_f32(p + 4 * lane);
+      const unsigned x = lds_u16(p + 4 * m + 2 * lane);
+      float s = S[x];
+      if (is_sentinel(s)) s = QT0;
+      S[x] = __fadd_rn(s, __fsub_rn(v, T));
+    }
+    __syncwarp();
+  }
+}
 
-// front-end state of a warp (registers, warp-uniform)
-struct Front {
-  unsigned long long rn_raw = 0;    // lane 0: result of the atomicAdd that fetched the NEXT read
-  const uint8_t* s = nullptr;
-  int len = 0, Ql = 0, g0 = 0;
-  int n_match = 0, n_amb = 0, n_skip = 0;
-  int slot = 0;
-  bool active = false, done = false;
+struct PairSmem {
+  uint32_t bar;        // shared address of full[0]; full[i] = bar + 8 i, empty[i] = bar + 8 (kStages + i)
+  uint8_t* meta;       // kStages x kStageMetaBytes
+  uint32_t desc;       // shared address of the descriptor lists
+  float* S;
+  uint32_t stage;      // shared address of stage 0
+  int stage_bytes, max_chunks;
 };
 
-// --------------------------------------------------------------------------------- main kernel
-__global__ void __launch_bounds__(kMaxWarpsPerCta * 32, 1)
-place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_constant__ DbView db,
-             const __grid_constant__ CfgView cfg, const __grid_constant__ BatchView bt,
-             unsigned long long* work_counter, float* amb_S, int* amb_C, int n_pad, int per_warp_bytes) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int warps_per_cta = blockDim.x >> 5;
-  // CTA-wide: character class table
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) smem[i] = c_alpha.cls[i];
-  const uint32_t cls_tab = smem_u32(smem);
-  // per warp: read-info slots | descriptor ring | S[n_pad + 32]
-  uint8_t* base = smem + 256 + (size_t)warp * per_warp_bytes;
-  ReadInfo* info = reinterpret_cast<ReadInfo*>(base);
-  const uint32_t ring = smem_u32(base + kInfoSlots * sizeof(ReadInfo));
-  float* S = reinterpret_cast<float*>(base + kInfoSlots * sizeof(ReadInfo) + kRing * 8);
-  for (int i = lane; i < n_pad + 32; i += 32) S[i] = __uint_as_float(kSentinelBits);
-  __syncthreads();
-  const size_t gw = (size_t)blockIdx.x * warps_per_cta + warp;
-  float* Sa = amb_S + gw * n_pad;
-  int* Ca = amb_C + gw * n_pad;
+// ---- K1 + K2: the producer warp ----------------------------------------------------------------
+__device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const DbView& db, const CfgView& cfg,
+                                         const BatchView& bt, unsigned long long* work_counter, const PairSmem& w,
+                                         uint32_t cls_tab, int lane) {
   const int k = db.k;
   const uint32_t kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
-  const int K = cfg.K;
-
-  uint32_t head = 0, tail = 0;        // descriptor ring (free-running counters)
-  uint32_t info_head = 0, info_tail = 0;
-  Front fe;
-  if (lane == 0) fe.rn_raw = atomicAdd(work_counter, 1ull);
-
-  auto push = [&](uint32_t x, uint32_t y) {  // one descriptor, by lane 0
-    if (lane == 0) sts_u64(ring + 8 * (head & (kRing - 1)), make_uint2(x, y));
-    head++;
-  };
-
-  // ---- front end: append the descriptors of the next group of windows ------------------------
-  // Called with at least kGiantChunks + 34 free ring entries.
-  auto front = [&]() {
-    if (!fe.active) {
-      const unsigned long long r = __shfl_sync(0xffffffffu, fe.rn_raw, 0);
-      if (r >= (unsigned long long)bt.n_reads) {
-        fe.done = true;
-        push(0u, desc_y(kDescStop, 0u, 0u));
-        if (lane < kPrefetch) sts_u64(ring + 8 * ((head + lane) & (kRing - 1)), make_uint2(0u, 0u));
-        __syncwarp();
+  const int stage_bytes = w.stage_bytes;
+  unsigned long long rn_raw = 0;  // lane 0: result of the atomicAdd that fetched the NEXT read
+  if (lane == 0) rn_raw = atomicAdd(work_counter, 1ull);
+  // read being cut into groups
+  long long r = -1;
+  const uint8_t* s = nullptr;
+  int len = 0, Ql = 0, g0 = 0, n_match = 0, n_amb = 0, n_skip = 0;
+  bool active = false, too_long = false;
+  float QT = 0.f;
+  for (uint32_t batch = 0;; batch++) {
+    const int slot = batch % kStages;
+    const uint32_t use = batch / kStages;
+    if (use) mbar_wait(w.bar + 8 * (kStages + slot), (use - 1) & 1u);  // the consumer has released the stage
+    StageHdr* hdr = reinterpret_cast<StageHdr*>(w.meta + slot * kStageMetaBytes);
+    uint32_t* pk_arr = reinterpret_cast<uint32_t*>(w.meta + slot * kStageMetaBytes + 64);
+    uint64_t* meta_arr = reinterpret_cast<uint64_t*>(w.meta + slot * kStageMetaBytes + 192);
+    const uint32_t full = w.bar + 8 * slot;
+    if (!active) {
+      const unsigned long long rr = __shfl_sync(0xffffffffu, rn_raw, 0);
+      if (rr >= (unsigned long long)bt.n_reads) {
+        if (lane == 0) {
+          hdr->flags = kGrpStop;
+          hdr->n_chunks = 0; hdr->hitm = hdr->ambm = hdr->stagedm = 0;
+          mbar_arrive(full);
+        }
         return;
       }
-      if (lane == 0) fe.rn_raw = atomicAdd(work_counter, 1ull);  // consumed when this read is finished
-      const uint64_t o0 = bt.seq_off[r], o1 = bt.seq_off[r + 1];
-      fe.s = bt.seq + (o0 - bt.seq_base);
-      const uint64_t len64 = o1 - o0;
-      const bool too_long = len64 > (uint64_t)kMaxReadLen;
-      fe.len = too_long ? 0 : (int)len64;
-      fe.Ql = fe.len - k + 1;  // sk.getMerCount()
-      fe.g0 = 0;
-      fe.n_match = fe.n_amb = fe.n_skip = 0;
-      fe.slot = info_head & (kInfoSlots - 1);
-      info_head++;
-      fe.active = true;
-      const float QT = __fmul_rn((float)fe.Ql, db.T);  // Q*PPStarThresholdAsLog10 (int*float)
-      if (lane == 0) {
-        ReadInfo& ri = info[fe.slot];
-        ri.r = (long long)r; ri.seq = fe.s; ri.len = fe.len; ri.Q = fe.Ql; ri.QT = QT;
-        ri.flags = too_long ? kInfoTooLong : 0;
-      }
-      push(0u, desc_y(kDescStart, fe.slot, 0u));
+      if (lane == 0) rn_raw = atomicAdd(work_counter, 1ull);  // consumed when this read is finished
+      const uint64_t o0 = bt.seq_off[rr], o1 = bt.seq_off[rr + 1];
+      r = (long long)rr;
+      s = bt.seq + (o0 - bt.seq_base);
+      too_long = (o1 - o0) > (uint64_t)kMaxReadLen;
+      len = too_long ? 0 : (int)(o1 - o0);
+      Ql = len - k + 1;  // sk.getMerCount()
+      QT = __fmul_rn((float)Ql, db.T);  // Q*PPStarThresholdAsLog10 (int*float)
+      g0 = 0;
+      n_match = n_amb = n_skip = 0;
+      active = true;
     }
-    const uint8_t* s = fe.s;
-    const int len = fe.len, g0 = fe.g0;
-    bool bad = false, last = false;
-    if (fe.Ql <= 0) {
+    int flags = too_long ? kGrpTooLong : 0;
+    int n_chunks = 0;
+    uint32_t hitm = 0, ambm = 0, stagedm = 0, total = 0;
+    uint32_t copy_dst = 0, copy_bytes = 0;  // this lane's bulk copy, issued once the stage is published
+    const uint8_t* copy_src = nullptr;
+    const uint8_t* seq_g0 = s + g0;
+    if (Ql <= 0) {
       // no window; still an unsupported character aborts the reference before the length matters
       const uint32_t c = (lane < len) ? lds_u8(cls_tab + s[lane]) : kClsPad;
-      bad = __any_sync(0xffffffffu, c == kClsBad);
-      last = true;
+      if (__any_sync(0xffffffffu, c == kClsBad)) flags |= kGrpBad;
+      flags |= kGrpLast;
     } else {
       // classes of characters [g0, g0+64): 32 window starts + up to k-1 <= 30 look-ahead
       const int i0 = g0 + lane, i1 = i0 + 32;
       const uint32_t c0 = (i0 < len) ? lds_u8(cls_tab + s[i0]) : kClsPad;
       const uint32_t c1 = (i1 < len) ? lds_u8(cls_tab + s[i1]) : kClsPad;
-      bad = __any_sync(0xffffffffu, c0 == kClsBad || c1 == kClsBad);
-      if (!bad) {
+      if (__any_sync(0xffffffffu, c0 == kClsBad || c1 == kClsBad)) {
+        flags |= kGrpBad | kGrpLast;
+      } else {
         // ambiguityCountPerMer of window g0+lane = popcount of the ambiguity bits of its k characters
         const uint32_t a0 = __ballot_sync(0xffffffffu, (c0 & 0xC0) == kClsAmb);
         const uint32_t a1 = __ballot_sync(0xffffffffu, (c1 & 0xC0) == kClsAmb);
         const int na = __popc(__funnelshift_r(a0, a1, lane) & kmask);
-        const int nv = min(32, fe.Ql - g0);  // windows left in the read
+        const int nv = min(32, Ql - g0);  // windows left in the read
         const bool valid = lane < nv;
         // getNextByteWord (:224-233) + processQueries (:691-750)
         const bool plain = valid && na == 0;
@@ -462,186 +498,195 @@ place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_consta
         uint64_t meta = 0;
         bool found = false;
         if (plain) found = table_probe(db, key, meta);
-        // descriptors of this lane's window: one per <=32 postings, or a single GIANT / AMB marker
-        const uint32_t n_post = found ? (uint32_t)(meta & 0xFFFF) : 0u;
-        const uint32_t chunks = (n_post + 31) >> 5;
-        const bool giant = chunks > (uint32_t)kGiantChunks;
-        const uint32_t my = ambw ? 1u : giant ? 1u : chunks;
-        uint32_t incl = my;
+        // stage assignment: windows are taken in order while their posting blocks fit into the stage;
+        // a block larger than a whole stage is read from global memory by the consumer instead
+        const uint32_t n_post = (uint32_t)(meta & 0xFFFF);
+        const uint32_t bytes = (n_post * 6 + 31) & ~31u;
+        const bool giant = bytes > (uint32_t)stage_bytes;
+        const uint32_t sb = (found && !giant) ? bytes : 0u;
+        // one scan for both prefix sums: bytes in 32 B units (<= 2^15 over the warp) above the chunk count (< 2^13)
+        const uint32_t my_chunks = sb ? (n_post + 31) >> 5 : 0u;
+        uint32_t incl = (sb >> 5 << 13) | my_chunks;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
           const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
           if (lane >= d) incl += t;
         }
-        // windows are taken in order while their descriptors fit (one entry stays free for END)
-        const uint32_t space = kRing - (head - tail) - 1u - kPrefetch;
-        const uint32_t nofit = __ballot_sync(0xffffffffu, incl > space);
-        int cons = nofit ? __ffs(nofit) - 1 : 32;  // >= 1: one window needs <= kGiantChunks entries
+        const uint32_t incl_bytes = incl >> 13 << 5, incl_chunks = incl & 0x1FFFu;
+        const uint32_t nofit = __ballot_sync(0xffffffffu, incl_bytes > (uint32_t)stage_bytes);
+        int cons = nofit ? __ffs(nofit) - 1 : 32;  // >= 1: lane 0 alone always fits
         cons = min(cons, nv);
         const uint32_t lanes = cons >= 32 ? 0xffffffffu : ((1u << cons) - 1u);
-        fe.n_match += __popc(__ballot_sync(0xffffffffu, found) & lanes);
-        fe.n_amb += __popc(__ballot_sync(0xffffffffu, ambw) & lanes);
-        fe.n_skip += __popc(__ballot_sync(0xffffffffu, skip) & lanes);
-        if (lane < cons && my) {
-          uint32_t at = head + incl - my;
-          const uint32_t off32 = (uint32_t)(meta >> 16);
-          if (ambw) {
-            sts_u64(ring + 8 * (at & (kRing - 1)), make_uint2(0u, desc_y(kDescAmb, fe.slot, (uint32_t)(g0 + lane))));
-          } else if (giant) {
-            sts_u64(ring + 8 * (at & (kRing - 1)), make_uint2(off32, desc_y(kDescGiant, fe.slot, n_post)));
-          } else {
-            uint32_t o = off32;
-            for (uint32_t left = n_post; left; at++, o += kSubBlockBytes / kBlockAlign) {
+        hitm = __ballot_sync(0xffffffffu, found) & lanes;
+        ambm = __ballot_sync(0xffffffffu, ambw) & lanes;
+        stagedm = __ballot_sync(0xffffffffu, sb != 0u) & lanes;
+        n_match += __popc(hitm);
+        n_amb += __popc(ambm);
+        n_skip += __popc(__ballot_sync(0xffffffffu, skip) & lanes);
+        const uint32_t off = incl_bytes - sb;
+        if (ambm | (hitm & ~stagedm)) {  // the consumer's per-window path needs these
+          pk_arr[lane] = (off << 16) | n_post;
+          meta_arr[lane] = meta;
+        }
+        if (stagedm) {
+          const uint32_t last = __shfl_sync(0xffffffffu, incl, cons - 1);
+          total = last >> 13 << 5;
+          n_chunks = (int)(last & 0x1FFFu);
+          const uint32_t stage0 = w.stage + slot * stage_bytes;
+          const uint32_t dl0 = w.desc + slot * w.max_chunks * 8;
+          if ((stagedm >> lane) & 1u) {
+            copy_dst = stage0 + off;
+            copy_src = db.blocks + (meta >> 16) * kBlockAlign;
+            copy_bytes = bytes;
+            // chunk descriptors of this window, in window order
+            uint32_t dl = dl0 + 8 * (incl_chunks - my_chunks);
+            uint32_t a = copy_dst;
+            for (uint32_t left = n_post; left; a += kSubBlockBytes, dl += 8) {
               const uint32_t m = min(left, 32u);
-              sts_u64(ring + 8 * (at & (kRing - 1)), make_uint2(o, desc_y(kDescChunk, 0u, m)));
+              sts_u64(dl, make_uint2(a, m));
               left -= m;
             }
           }
+          if (lane < 2)  // two idle descriptors behind the list: the consumer prefetches that far
+            sts_u64(dl0 + 8 * (n_chunks + lane), make_uint2(stage0, 0u));
         }
-        head += __shfl_sync(0xffffffffu, incl, cons - 1);
-        fe.g0 = g0 + cons;
-        last = fe.g0 >= fe.Ql;
+        g0 += cons;
+        if (g0 >= Ql) flags |= kGrpLast;
       }
     }
-    if (bad || last) {
-      if (lane == 0) {
-        ReadInfo& ri = info[fe.slot];
-        if (bad) ri.flags |= kInfoBad;
-        ri.n_match = fe.n_match; ri.n_amb = fe.n_amb; ri.n_skip = fe.n_skip;
-      }
-      push(0u, desc_y(kDescEnd, fe.slot, 0u));
-      fe.active = false;
+    if (lane == 0) {
+      hdr->r = r; hdr->seq = seq_g0; hdr->Q = Ql; hdr->QT = QT; hdr->flags = flags;
+      hdr->n_match = n_match; hdr->n_amb = n_amb; hdr->n_skip = n_skip;
+      hdr->n_chunks = n_chunks; hdr->hitm = hitm; hdr->ambm = ambm; hdr->stagedm = stagedm;
     }
-    // the kPrefetch entries behind the head read as idle descriptors: the back end may look that far
-    if (lane < kPrefetch) sts_u64(ring + 8 * ((head + lane) & (kRing - 1)), make_uint2(0u, 0u));
-    __syncwarp();
-  };
+    __syncwarp();  // every lane's descriptors / arrays are written before the stage is published
+    if (lane == 0) {
+      // the arrival releases header + descriptors; the phase completes when the staged bytes have landed too
+      if (stagedm) mbar_expect_tx(full, total);
+      else mbar_arrive(full);
+    }
+    if (copy_bytes) {
+      fence_proxy_async();  // the consumer's generic-proxy reads of this stage precede the async writes
+      bulk_g2s(copy_dst, copy_src, copy_bytes, full);
+    }
+    if (flags & kGrpLast) active = false;
+  }
+}
 
-  // ---- back end: rare descriptors ---------------------------------------------------------------
-  float QT = 0.f, QT0 = 0.f;  // of the read being accumulated
-  auto special = [&](uint2 d) {
-    const uint32_t type = d.y >> 29, slot = (d.y >> 26) & 7u, payload = d.y & 0x3FFFFFFu;
-    __syncwarp();
-    if (type == kDescStart) {
-      QT = info[slot].QT;
-      QT0 = __fadd_rn(0.0f, QT);  // S[x]+=Q*T on a zeroed S[x]
-    } else if (type == kDescGiant) {
-      accumulate_global(S, db.blocks + (size_t)d.x * kBlockAlign, (int)payload, QT0, db.T, lane);
-    } else if (type == kDescAmb) {
-      if (!(info[slot].flags & kInfoBad))
-        ambiguous_window(c_alpha, db, cfg, S, info[slot].seq + payload, QT, Sa, Ca, lane);
-    } else {  // kDescEnd: selection / outputs
-      const ReadInfo ri = info[slot];
-      const long long r = ri.r;
-      uint16_t* o_node = bt.node + r * K;
-      float* o_score = bt.score + r * K;
-      double* o_lwr = bt.lwr + r * K;
-      int status, rows = 0;
-      if (ri.flags & kInfoBad) {
-        select_and_reset(cfg, S, n_pad, false, nullptr, db.n_nodes, o_node, o_score, o_lwr, lane);
-        status = RP_STATUS_BAD_CHAR;
-      } else if (ri.flags & kInfoTooLong) {
-        status = RP_STATUS_TOO_LONG;
-      } else if (ri.Q < 0) {
-        status = RP_STATUS_TOO_SHORT;
-      } else {
-        float* dump_row = bt.dump_scores ? bt.dump_scores + r * (size_t)db.n_nodes : nullptr;
-        rows = select_and_reset(cfg, S, n_pad, true, dump_row, db.n_nodes, o_node, o_score, o_lwr, lane);
-        status = rows < 0 ? RP_STATUS_UNPLACED : RP_STATUS_PLACED;  // L empty -> not placed (:797-806)
-      }
-      if (rows <= 0 && status != RP_STATUS_PLACED) {
-        rows = 0;
-        if (lane < K) { o_node[lane] = 0xFFFF; o_score[lane] = -INFINITY; o_lwr[lane] = 0.0; }
-      }
-      if (lane == 0) {
-        bt.n_rows[r] = rows;
-        bt.status[r] = status;
-        if (bt.counts) {
-          const bool ok = status <= RP_STATUS_UNPLACED;
-          int4 c = make_int4(ok ? (ri.Q > 0 ? ri.Q : 0) : 0, ok ? ri.n_match : 0, ok ? ri.n_amb : 0, ok ? ri.n_skip : 0);
-          *reinterpret_cast<int4*>(bt.counts + 4 * r) = c;
+// ---- K3 + K4: the consumer warp ------------------------------------------------------------------
+__device__ __forceinline__ void consumer(const AlphabetTables& c_alpha, const DbView& db, const CfgView& cfg,
+                                         const BatchView& bt, const PairSmem& w, float* Sa, int* Ca, int n_pad, int lane) {
+  const int K = cfg.K;
+  float* S = w.S;
+  for (uint32_t batch = 0;; batch++) {
+    const int slot = batch % kStages;
+    const uint32_t use = batch / kStages;
+    mbar_wait(w.bar + 8 * slot, use & 1u);
+    const StageHdr g = *reinterpret_cast<const StageHdr*>(w.meta + slot * kStageMetaBytes);
+    if (g.flags & kGrpStop) return;
+    const float QT0 = __fadd_rn(0.0f, g.QT);  // S[x]+=Q*T on a zeroed S[x]
+    const bool bad = g.flags & kGrpBad;
+    if (!bad && !(g.ambm | (g.hitm & ~g.stagedm))) {
+      // common case: every matched window of the group is staged
+      if (g.n_chunks) accumulate_chunks(S, w.desc + slot * w.max_chunks * 8, g.n_chunks, n_pad, QT0, db.T, lane);
+    } else if (!bad) {
+      const uint32_t* pk_arr = reinterpret_cast<const uint32_t*>(w.meta + slot * kStageMetaBytes + 64);
+      const uint64_t* meta_arr = reinterpret_cast<const uint64_t*>(w.meta + slot * kStageMetaBytes + 192);
+      const uint32_t stage = w.stage + slot * w.stage_bytes;
+      // windows in order: a node's S[x] must see its contributions in window order
+      for (uint32_t todo = g.hitm | g.ambm; todo;) {
+        const int l = __ffs(todo) - 1;
+        todo &= todo - 1;
+        if ((g.hitm >> l) & 1u) {
+          const uint32_t pk = pk_arr[l];
+          if ((g.stagedm >> l) & 1u) {
+            accumulate_staged(S, stage + (pk >> 16), (int)(pk & 0xFFFF), QT0, db.T, lane);
+          } else {
+            accumulate_global(S, db.blocks + (meta_arr[l] >> 16) * kBlockAlign, (int)(pk & 0xFFFF), QT0, db.T, lane);
+          }
+        } else {
+          ambiguous_window(c_alpha, db, cfg, S, g.seq + l, g.QT, Sa, Ca, lane);
         }
       }
-      info_tail++;
-      __syncwarp();
     }
-  };
-
-  // ---- the stream ---------------------------------------------------------------------------------
-  // Slot u of the register pipeline holds the descriptor at a ring position == u (mod kPrefetch), with
-  // its posting data already requested; step u of the unrolled round consumes position `tail`.
-  // Entries behind the head are zero (idle), the last descriptor of the stream is STOP.
-  const uint8_t* const base_v = db.blocks + lane * 4;   // per-lane bases: chunk address = base + 32 * desc.x
-  const uint8_t* const base_x = db.blocks + lane * 2;
-  const uint32_t dummy = n_pad + lane;
-  const float T = db.T;
-  float pv[kPrefetch];
-  uint32_t px[kPrefetch], py[kPrefetch];
-#pragma unroll
-  for (int u = 0; u < kPrefetch; u++) { pv[u] = 0.f; px[u] = 0u; py[u] = 0u; }
-  auto fetch = [&](int u, uint32_t pos) {  // descriptor `pos` -> slot u, its postings requested
-    const uint2 d = lds_u64(ring + ((pos << 3) & (8 * kRing - 8)));
-    // markers carry x = 0 and are never consumed as chunks: whatever their low bits request is harmless
-    const uint32_t mm = d.y & 0x3Fu;
-    const uint8_t* a = base_v + ((uint64_t)d.x << 5);
-    py[u] = d.y;
-    ldg_posting(pv[u], px[u], a, base_x + ((uint64_t)d.x << 5) + 4 * mm, (uint32_t)lane, mm);
-  };
-  const uint32_t kNeed = kGiantChunks + 34 + kPrefetch;  // free entries one front() call may use
-
-// one step of the round: a CHUNK descriptor is consumed here, anything else leaves through `slow`
-#define RP_STEP(u)                                                                                     \
-  case u: {                                                                                            \
-    const uint32_t y = py[u];                                                                          \
-    if (y - 1u >= 0x3Fu) break; /* not a CHUNK with 1..63 postings: marker, idle or stale slot */      \
-    const uint32_t idx = lane < y ? px[u] : dummy;                                                     \
-    float s_ = S[idx];                                                                                 \
-    if (is_sentinel(s_)) s_ = QT0;                    /* C[x]==0 : L.add(x); S[x]+=Q*T   (:726-729) */ \
-    S[idx] = __fadd_rn(s_, __fsub_rn(pv[u], T));      /* S[x]+= v - T   (:733) */                      \
-    asm volatile("" ::: "memory");                    /* keep the warp's smem accesses in program order */ \
-    tail++;                                                                                            \
-    fetch(u, tail + kPrefetch - 1);                                                                    \
-  }
-
-  for (;;) {
-    // top the ring up (the prefetched chunks stay in flight meanwhile)
-    if (head - tail < 64u) {
-      while (!fe.done && head - tail < 128u && kRing - (head - tail) >= kNeed) {
-        if (!fe.active && info_head - info_tail >= (uint32_t)kInfoSlots) break;  // back end must finish a read first
-        front();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(w.bar + 8 * (kStages + slot));  // the stage may be refilled
+    if (!(g.flags & kGrpLast)) continue;
+    // ---- selection / outputs
+    const long long r = g.r;
+    uint16_t* o_node = bt.node + r * K;
+    float* o_score = bt.score + r * K;
+    double* o_lwr = bt.lwr + r * K;
+    int status, rows = 0;
+    if (bad) {
+      select_and_reset(cfg, S, n_pad, false, nullptr, db.n_nodes, o_node, o_score, o_lwr, lane);
+      status = RP_STATUS_BAD_CHAR;
+    } else if (g.flags & kGrpTooLong) {
+      status = RP_STATUS_TOO_LONG;
+    } else if (g.Q < 0) {
+      status = RP_STATUS_TOO_SHORT;
+    } else {
+      float* dump_row = bt.dump_scores ? bt.dump_scores + r * (size_t)db.n_nodes : nullptr;
+      rows = select_and_reset(cfg, S, n_pad, true, dump_row, db.n_nodes, o_node, o_score, o_lwr, lane);
+      status = rows < 0 ? RP_STATUS_UNPLACED : RP_STATUS_PLACED;  // L empty -> not placed (:797-806)
+    }
+    if (rows <= 0 && status != RP_STATUS_PLACED) {
+      rows = 0;
+      if (lane < K) { o_node[lane] = 0xFFFF; o_score[lane] = -INFINITY; o_lwr[lane] = 0.0; }
+    }
+    if (lane == 0) {
+      bt.n_rows[r] = rows;
+      bt.status[r] = status;
+      if (bt.counts) {
+        const bool ok = status <= RP_STATUS_UNPLACED;
+        int4 c = make_int4(ok ? (g.Q > 0 ? g.Q : 0) : 0, ok ? g.n_match : 0, ok ? g.n_amb : 0, ok ? g.n_skip : 0);
+        *reinterpret_cast<int4*>(bt.counts + 4 * r) = c;
       }
     }
-    const uint32_t tail0 = tail;
-    switch (tail & (kPrefetch - 1)) {
-      RP_STEP(0) RP_STEP(1) RP_STEP(2) RP_STEP(3) RP_STEP(4) RP_STEP(5) RP_STEP(6) RP_STEP(7)
-    }
-    static_assert(kPrefetch == 8, "RP_STEP list");
-    if (tail - tail0 == (uint32_t)kPrefetch - (tail0 & (kPrefetch - 1))) continue;  // the round ran to its end
-    // ---- slow path: the slot of position `tail` holds a marker, or was fetched before the descriptor existed
-    if (head == tail) continue;  // (cannot happen before STOP: the front end always appends when the ring is short)
-    const uint2 d = lds_u64(ring + ((tail << 3) & (8 * kRing - 8)));
-    const uint32_t type = d.y >> 29;
-    if (type == kDescStop) break;
-    const bool is_chunk = type == kDescChunk;
-    if (!is_chunk) {
-      special(d);
-      tail++;
-    }
-    // (re)load the slot: the descriptor at `tail` itself if it is a chunk that was fetched too early,
-    // else the one kPrefetch-1 ahead of the new tail
-    const uint32_t pos = is_chunk ? tail : tail + kPrefetch - 1;
-    switch (pos & (kPrefetch - 1)) {
-      case 0: fetch(0, pos); break;
-      case 1: fetch(1, pos); break;
-      case 2: fetch(2, pos); break;
-      case 3: fetch(3, pos); break;
-      case 4: fetch(4, pos); break;
-      case 5: fetch(5, pos); break;
-      case 6: fetch(6, pos); break;
-      default: fetch(7, pos); break;
-    }
   }
-#undef RP_STEP
+}
+
+// --------------------------------------------------------------------------------- main kernel
+__global__ void __launch_bounds__(kMaxPairsPerCta * 64, 1)
+place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_constant__ DbView db,
+             const __grid_constant__ CfgView cfg, const __grid_constant__ BatchView bt,
+             unsigned long long* work_counter, float* amb_S, int* amb_C, int n_pad, int per_pair_bytes,
+             int stage_bytes, int max_chunks) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int pairs = blockDim.x >> 6;
+  const bool is_producer = warp < pairs;
+  const int pair = is_producer ? warp : warp - pairs;
+  // CTA-wide: character class table
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) smem[i] = c_alpha.cls[i];
+  PairSmem w;
+  {
+    uint8_t* base = smem + 256 + (size_t)pair * per_pair_bytes;
+    w.bar = smem_u32(base);
+    w.meta = base + 64;
+    uint8_t* p = base + 64 + kStages * kStageMetaBytes;
+    w.stage = smem_u32(p);  // idle lanes of a short chunk read (and ignore) up to 160 B past it: keep the stages inside
+    p += (size_t)kStages * stage_bytes;
+    w.desc = smem_u32(p);
+    p += (size_t)kStages * max_chunks * 8;
+    w.S = reinterpret_cast<float*>(p);
+    w.stage_bytes = stage_bytes;
+    w.max_chunks = max_chunks;
+  }
+  if (!is_producer) {
+    for (int i = lane; i < n_pad + 32; i += 32) w.S[i] = __uint_as_float(kSentinelBits);
+    if (lane == 0)
+      for (int i = 0; i < 2 * kStages; i++) mbar_init(w.bar + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (is_producer) {
+    producer(c_alpha, db, cfg, bt, work_counter, w, smem_u32(smem), lane);
+  } else {
+    const size_t gp = (size_t)blockIdx.x * pairs + pair;
+    consumer(c_alpha, db, cfg, bt, w, amb_S + gp * n_pad, amb_C + gp * n_pad, n_pad, lane);
+  }
 }
 
 // ------------------------------------------------------------------------- diagnostics kernel
@@ -716,42 +761,54 @@ __global__ void fill_f32_kernel(float* p, size_t n, float v) {
 }
 
 // ------------------------------------------------------------------------------ host plumbing
-// Shared memory per warp = read-info slots + descriptor ring + S[n_pad + 32]; warps per CTA x CTAs per
-// SM maximise the resident warps under the 227 KB budget and the register file.
+// Shared memory per producer/consumer pair = S[n_pad + 32] + kStages posting stages (+ descriptor lists,
+// stage headers, mbarriers); pairs per CTA x CTAs per SM maximise the resident pairs under the 227 KB
+// budget.  A stage holds about a group's worth of posting blocks; RP_STAGE_BYTES overrides it for tuning.
 int compute_geometry(const rp_db* db, DeviceCtx* dc) {
   LaunchGeom g;
   g.n_pad = (db->desc.n_nodes + 127) & ~127;
   const size_t cta_fixed = 256;
   const size_t optin = dc->smem_optin;         // 227 KB on sm_100
   const size_t sm_total = optin + 1024;        // 228 KB per SM, 1 KB reserved per resident CTA
-  g.per_warp_bytes = (kInfoSlots * sizeof(ReadInfo) + kRing * 8 + 4 * (size_t)(g.n_pad + 32) + 127) & ~(size_t)127;
+  const double mean_block = db->desc.n_keys ? (double)db->block_bytes / (double)db->desc.n_keys : 32.0;
+  long stage = (long)(32.0 * mean_block * 0.65);
+  if (const char* e = getenv("RP_STAGE_BYTES")) stage = atol(e);
+  stage = std::max(1024L, std::min(stage, 32768L - 128));
+  stage = (stage + 127) & ~127L;
+  auto pair_bytes = [&](long st) {
+    const size_t chunks = 32 + st / kSubBlockBytes + 3;  // one per window + one per extra sub-block + 2 idle
+    return (64 + kStages * (size_t)kStageMetaBytes + kStages * 8 * chunks + 4 * (size_t)(g.n_pad + 32) +
+            kStages * (size_t)st + 127) & ~(size_t)127;
+  };
+  // big trees: give the stages up before giving the accumulator up
+  while (stage > 1024 && cta_fixed + 2 * pair_bytes(stage) > optin) stage = std::max(1024L, (stage / 2 + 127) & ~127L);
+  g.stage_bytes = (int)stage;
+  g.max_chunks = 32 + g.stage_bytes / kSubBlockBytes + 3;
+  g.per_warp_bytes = pair_bytes(stage);
   if (cta_fixed + g.per_warp_bytes > optin)
     return set_error(RP_E_UNSUPPORTED,
-                     "n_nodes=%d needs %zu B of shared memory per read (> %zu B per CTA); trees beyond ~56k nodes "
+                     "n_nodes=%d needs %zu B of shared memory per read (> %zu B per CTA); trees beyond ~54k nodes "
                      "are not supported by the shared-memory accumulator",
                      db->desc.n_nodes, g.per_warp_bytes, optin);
-  RP_CUDA_TRY(cudaSetDevice(dc->device));
-  cudaFuncAttributes fa;
-  RP_CUDA_TRY(cudaFuncGetAttributes(&fa, place_kernel));
-  const int reg_warps = std::max(1, 65536 / (32 * std::max(1, fa.numRegs)));  // warps per SM the registers allow
-  int max_warps_sm = std::min(kMaxWarpsPerSm, reg_warps);
-  if (const char* e = getenv("RP_WARPS_PER_SM")) max_warps_sm = std::max(1, std::min(max_warps_sm, atoi(e)));
+  int max_pairs_sm = 16;
+  if (const char* e = getenv("RP_PAIRS_PER_SM")) max_pairs_sm = std::max(1, std::min(16, atoi(e)));
   int best_total = 0;
   for (int c = 1; c <= 8; c++) {
     const size_t budget = std::min(optin, sm_total / c - 1024);
     if (budget < cta_fixed + g.per_warp_bytes) break;
-    int wpc = (int)std::min<size_t>(kMaxWarpsPerCta, (budget - cta_fixed) / g.per_warp_bytes);
-    if (c * wpc > max_warps_sm) wpc = max_warps_sm / c;
-    if (wpc < 1) break;
-    if (c * wpc > best_total) {
-      best_total = c * wpc;
+    int ppc = (int)std::min<size_t>(kMaxPairsPerCta, (budget - cta_fixed) / g.per_warp_bytes);
+    if (c * ppc > max_pairs_sm) ppc = max_pairs_sm / c;
+    if (ppc < 1) break;
+    if (c * ppc > best_total) {
+      best_total = c * ppc;
       g.ctas_per_sm = c;
-      g.warps_per_cta = wpc;
+      g.warps_per_cta = 2 * ppc;
     }
   }
-  g.smem_bytes = cta_fixed + g.warps_per_cta * g.per_warp_bytes;
+  g.smem_bytes = cta_fixed + (g.warps_per_cta / 2) * g.per_warp_bytes;
+  RP_CUDA_TRY(cudaSetDevice(dc->device));
   RP_CUDA_TRY(cudaFuncSetAttribute(place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-  // what the hardware really keeps resident
+  // what the hardware really keeps resident (registers may bind before shared memory does)
   int resident = 0;
   RP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, place_kernel, g.warps_per_cta * 32, g.smem_bytes));
   if (resident < 1) return set_error(RP_E_CUDA, "placement kernel does not fit on an SM (smem %zu B)", g.smem_bytes);
@@ -768,7 +825,7 @@ int ensure_stream_ctx(const rp_db* db, DeviceCtx* dc, StreamCtx* sc) {
   if (!sc->stream) RP_CUDA_TRY(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
   RP_CUDA_TRY(cudaEventCreate(&sc->ev_k0));
   RP_CUDA_TRY(cudaEventCreate(&sc->ev_k1));
-  const size_t n = (size_t)dc->geom.grid * dc->geom.warps_per_cta * dc->geom.n_pad;
+  const size_t n = (size_t)dc->geom.grid * (dc->geom.warps_per_cta / 2) * dc->geom.n_pad;
   RP_CUDA_TRY(cudaMalloc((void**)&sc->d_amb_S, n * sizeof(float)));
   RP_CUDA_TRY(cudaMalloc((void**)&sc->d_amb_C, n * sizeof(int)));
   RP_CUDA_TRY(cudaMemset(sc->d_amb_S, 0, n * sizeof(float)));
@@ -799,7 +856,7 @@ static int launch_place(const rp_db* db, DeviceCtx* dc, StreamCtx* sc, const rp_
   if (time_it) RP_CUDA_TRY(cudaEventRecord(sc->ev_k0, stream));
   place_kernel<<<g.grid, g.warps_per_cta * 32, g.smem_bytes, stream>>>(
       db->alpha, make_db_view(db, dc), make_cfg_view(cfg), bt, sc->d_counter, sc->d_amb_S, sc->d_amb_C, g.n_pad,
-      (int)g.per_warp_bytes);
+      (int)g.per_warp_bytes, g.stage_bytes, g.max_chunks);
   RP_CUDA_TRY(cudaGetLastError());
   g_kernel_launches.fetch_add(1);
   if (time_it) RP_CUDA_TRY(cudaEventRecord(sc->ev_k1, stream));
