@@ -44,7 +44,10 @@ namespace rp {
 
 constexpr uint32_t kSentinelBits = 0x7FFFFFFFu;  // a NaN no arithmetic here produces
 constexpr int kMaxPairsPerCta = 12;  // producer warps 0..P-1, consumer warps P..2P-1
-constexpr int kStages = 2;           // posting stages per pair
+#ifndef RP_STAGES
+#define RP_STAGES 2  /* 3 measured slower at equal shared memory (tools/try_stages.sh) */
+#endif
+constexpr int kStages = RP_STAGES;   // posting stages per pair
 constexpr int kMaxReadLen = (1 << 30);
 
 // ------------------------------------------------------------------------------- PTX wrappers
@@ -63,12 +66,30 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// Consumer side: spin on try_wait (the stage is usually already full).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n.reg .pred p;\nWAIT_%=:\n"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
       "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(bar), "r"(parity)
       : "memory");
+}
+// Producer side: the consumer is the slower role, so a producer usually finds its stage still in use.
+// try_wait returns after a short hardware time-out; sleeping between polls keeps the idle role out of
+// the issue slots (v5 profile: 25 % of all issued instructions were this poll loop).
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  for (;;) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(400);
+  }
 }
 // global -> shared bulk copy (TMA, SASS UBLKCP); dst/src 16 B aligned, bytes % 16 == 0
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -363,32 +384,45 @@ static_assert(sizeof(StageHdr) == 64, "StageHdr is one 64 B slot");
 //   desc      kStages x max_chunks x 8 B   chunk descriptors {shared address of the scores, m}
 //   S         f32[n_pad + 32]              (+32: per-lane dummies for the idle lanes of a short chunk)
 constexpr int kStageMetaBytes = 64 + 128 + 256;
+static_assert((kStages * kStageMetaBytes) % 64 == 0, "stages start 16 B aligned");
 
 // Adds the staged posting blocks of a whole group into S, chunk by chunk, in window order
 // (PlacementProcess.java:719-735).  Branch-free: idle lanes of a short chunk update their private dummy
-// entry.  The loads of chunk j+1 are issued before the read-modify-write of chunk j.
+// entry.  Four register slots rotate through the descriptor list: the descriptor and the two loads of
+// chunk j+4 are issued right after chunk j has been added, three chunks before they are needed.  The
+// list is padded with idle descriptors (m = 0) up to a multiple of four plus the look-ahead.
+#define RP_CHUNK_STEP(D_, V_, X_, OFF_)                                                                \
+  {                                                                                                    \
+    const uint32_t idx = lane < D_.y ? X_ : dummy;                                                     \
+    float s_ = S[idx];                                                                                 \
+    if (is_sentinel(s_)) s_ = QT0;               /* C[x]==0 : L.add(x); S[x]+=Q*T   (:726-729) */     \
+    S[idx] = __fadd_rn(s_, __fsub_rn(V_, T));    /* S[x]+= v - T   (:733) */                          \
+    asm volatile("" ::: "memory");               /* keep the warp's smem accesses in program order */   \
+    D_ = lds_u64(dp + OFF_);                                                                           \
+    V_ = lds_f32(D_.x + lane4);                                                                        \
+    X_ = lds_u16(D_.x + 4 * D_.y + lane2);                                                             \
+  }
 __device__ __forceinline__ void accumulate_chunks(float* __restrict__ S, uint32_t dl, int n_chunks, int n_pad, float QT0,
                                                   float T, int lane) {
   const uint32_t lane4 = lane * 4, lane2 = lane * 2;
-  const uint32_t dummy = n_pad + lane;
-  uint2 d = lds_u64(dl);
-  float v = lds_f32(d.x + lane4);
-  uint32_t x = lds_u16(d.x + 4 * d.y + lane2);
-  uint2 dn = lds_u64(dl + 8);
+  uint32_t dummy;
+  asm volatile("add.u32 %0, %1, %2;" : "=r"(dummy) : "r"(n_pad), "r"(lane));  // pinned in a register
+  uint2 d0 = lds_u64(dl), d1 = lds_u64(dl + 8), d2 = lds_u64(dl + 16), d3 = lds_u64(dl + 24);
+  float v0 = lds_f32(d0.x + lane4), v1 = lds_f32(d1.x + lane4), v2 = lds_f32(d2.x + lane4), v3 = lds_f32(d3.x + lane4);
+  uint32_t x0 = lds_u16(d0.x + 4 * d0.y + lane2), x1 = lds_u16(d1.x + 4 * d1.y + lane2);
+  uint32_t x2 = lds_u16(d2.x + 4 * d2.y + lane2), x3 = lds_u16(d3.x + 4 * d3.y + lane2);
+  uint32_t dp = dl + 32;  // descriptor j+4 of the round's first chunk
+  const uint32_t dend = dl + 8 * n_chunks;
 #pragma unroll 1
-  for (int j = 0; j < n_chunks; j++) {
-    const float vn = lds_f32(dn.x + lane4);
-    const uint32_t xn = lds_u16(dn.x + 4 * dn.y + lane2);
-    const uint2 dnn = lds_u64(dl + 8 * (j + 2));
-    const uint32_t idx = lane < d.y ? x : dummy;
-    float s = S[idx];
-    if (is_sentinel(s)) s = QT0;                   // C[x]==0 : L.add(x); S[x]+=Q*T   (:726-729)
-    S[idx] = __fadd_rn(s, __fsub_rn(v, T));        // S[x]+= v - T   (:733)
-    asm volatile("" ::: "memory");                 // keep the warp's shared-memory accesses in program order
-    d = dn; v = vn; x = xn; dn = dnn;
+  for (; dp - 32 < dend; dp += 32) {
+    RP_CHUNK_STEP(d0, v0, x0, 0)
+    RP_CHUNK_STEP(d1, v1, x1, 8)
+    RP_CHUNK_STEP(d2, v2, x2, 16)
+    RP_CHUNK_STEP(d3, v3, x3, 24)
   }
   __syncwarp();
 }
+#undef RP_CHUNK_STEP
 
 // Same for one posting block, staged (p = shared address) -- slow path of a group with special windows
 __device__ __forceinline__ void accumulate_staged(float* __restrict__ S, uint32_t p, int len, float QT0, float T, int lane) {
@@ -432,7 +466,7 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
   for (uint32_t batch = 0;; batch++) {
     const int slot = batch % kStages;
     const uint32_t use = batch / kStages;
-    if (use) mbar_wait(w.bar + 8 * (kStages + slot), (use - 1) & 1u);  // the consumer has released the stage
+    if (use) mbar_wait_sleep(w.bar + 8 * (kStages + slot), (use - 1) & 1u);  // the consumer has released the stage
     StageHdr* hdr = reinterpret_cast<StageHdr*>(w.meta + slot * kStageMetaBytes);
     uint32_t* pk_arr = reinterpret_cast<uint32_t*>(w.meta + slot * kStageMetaBytes + 64);
     uint64_t* meta_arr = reinterpret_cast<uint64_t*>(w.meta + slot * kStageMetaBytes + 192);
@@ -547,7 +581,7 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
               left -= m;
             }
           }
-          if (lane < 2)  // two idle descriptors behind the list: the consumer prefetches that far
+          if (lane < 8)  // idle descriptors behind the list: the consumer works in rounds of 4 and looks 4 ahead
             sts_u64(dl0 + 8 * (n_chunks + lane), make_uint2(stage0, 0u));
         }
         g0 += cons;
@@ -776,14 +810,14 @@ int compute_geometry(const rp_db* db, DeviceCtx* dc) {
   stage = std::max(1024L, std::min(stage, 32768L - 128));
   stage = (stage + 127) & ~127L;
   auto pair_bytes = [&](long st) {
-    const size_t chunks = 32 + st / kSubBlockBytes + 3;  // one per window + one per extra sub-block + 2 idle
+    const size_t chunks = (32 + st / kSubBlockBytes + 9 + 1) & ~(size_t)1;  // per window + per extra sub-block + 8 idle
     return (64 + kStages * (size_t)kStageMetaBytes + kStages * 8 * chunks + 4 * (size_t)(g.n_pad + 32) +
             kStages * (size_t)st + 127) & ~(size_t)127;
   };
   // big trees: give the stages up before giving the accumulator up
   while (stage > 1024 && cta_fixed + 2 * pair_bytes(stage) > optin) stage = std::max(1024L, (stage / 2 + 127) & ~127L);
   g.stage_bytes = (int)stage;
-  g.max_chunks = 32 + g.stage_bytes / kSubBlockBytes + 3;
+  g.max_chunks = (32 + g.stage_bytes / kSubBlockBytes + 9 + 1) & ~1;  // even: S stays 16 B aligned behind the lists
   g.per_warp_bytes = pair_bytes(stage);
   if (cta_fixed + g.per_warp_bytes > optin)
     return set_error(RP_E_UNSUPPORTED,
@@ -903,7 +937,7 @@ static int place_on_device(rp_db* db, DeviceCtx* dc, const rp_place_cfg* cfg, co
   const int K = cfg->keep_at_most;
   const int64_t kChunk = out_dump ? 4096 : (1 << 18);
   double ms_total = 0.0;
-  int64_t pending_lo[2] = {-1, -1}, pending_hi[2] = {0, 0};
+  int64_t pending_lo[2] = {-1, -1};
   float* d_dump[2] = {nullptr, nullptr};
   auto finish = [&](int b) -> int {
     if (pending_lo[b] < 0) return RP_OK;
@@ -950,7 +984,6 @@ static int place_on_device(rp_db* db, DeviceCtx* dc, const rp_place_cfg* cfg, co
       RP_CUDA_TRY(cudaMemcpyAsync(out_dump + (size_t)c0 * db->desc.n_nodes, d_dump[b],
                                   (size_t)n * db->desc.n_nodes * sizeof(float), cudaMemcpyDeviceToHost, st));
     pending_lo[b] = c0;
-    pending_hi[b] = c1;
   }
   for (int i = 0; i < 2; i++) {
     int rc2 = finish(i);
