@@ -1,0 +1,60 @@
+"""world_size-2 gloo test (CPU) of the one-process-per-GPU read sharding: each rank places its slice with
+its own DB replica, rank 0 gathers, and the merged rows equal a single-process run of the whole batch.
+The per-rank engine here is the CPU oracle (test infrastructure); on a GPU box bench.py runs the same
+split with rappas_b200.Database per rank."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle_lib as O
+from rappas_b200 import _abi, shard, synth
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        db = synth.make_db(0, 8, 299, n_keys=20000, mean_postings=12, seed=43)       # replica on every rank
+        rb = synth.make_reads(db, 1001, (20, 220), seed=1043, n_rate=0.003)          # odd count: ragged split
+        cfg = _abi.place_cfg()
+        odb = O.OracleDB(db)
+        local, (lo, hi) = shard.place_local_shard(lambda r, c: odb.place(r, c), rb, cfg, rank, world)
+        assert local["n_rows"].shape[0] == hi - lo
+        merged = shard.gather_results(local, dst=0)
+        dist.barrier()
+        if rank == 0:
+            whole = odb.place(rb, cfg)
+            for k in shard.RESULT_KEYS:
+                assert np.array_equal(merged[k], whole[k], equal_nan=True), k
+            open(os.path.join(tmp, "ok"), "w").write("%d" % merged["n_rows"].shape[0])
+        else:
+            assert merged is None
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_bounds_cover_and_match_c_split():
+    for n in (0, 1, 7, 1000, 1001):
+        for w in (1, 2, 3, 8):
+            b = shard.shard_bounds(n, w)
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_sharded_placement_equals_single_process(tmp_path):
+    O.build()
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok").read_text() == "1001"
