@@ -204,3 +204,19 @@ def test_batch_split_and_order_invariance():
     again = g.place(rb)  # idempotent: no state survives a read / a batch
     for key in whole:
         assert np.array_equal(whole[key], again[key], equal_nan=True)
+
+
+def test_multi_device_in_process_matches_single_device():
+    """DB replicated on every visible GPU, reads split in contiguous slices inside rp_place_batch
+    (no collective): identical rows whatever the device count."""
+    import rappas_b200 as R
+    nd = R.device_count()
+    if nd < 2:
+        pytest.skip("needs >= 2 GPUs")
+    db = synth.make_db(0, 8, 299, n_keys=49152, mean_postings=16, seed=43)
+    rb = synth.make_reads(db, 20001, (20, 300), seed=5, n_rate=0.003)
+    one = R.Database.from_synth(db, devices=(0,))
+    many = R.Database.from_synth(db, devices=tuple(range(nd)))
+    a, b = one.place(rb), many.place(rb)
+    for key in a:
+        assert np.array_equal(a[key], b[key], equal_nan=True), key
