@@ -386,6 +386,23 @@ static_assert(sizeof(StageHdr) == 64, "StageHdr is one 64 B slot");
 constexpr int kStageMetaBytes = 64 + 128 + 256;
 static_assert((kStages * kStageMetaBytes) % 64 == 0, "stages start 16 B aligned");
 
+// S[x] += v - T for the lanes below m, with the first-touch rule; predicated (no branch, idle lanes do not
+// touch shared memory).  `a` = shared address of S[x].  PlacementProcess.java:726-733.
+__device__ __forceinline__ void rmw_posting(uint32_t a, float v, float T, float QT0, uint32_t lane, uint32_t m) {
+  asm volatile(
+      "{\n.reg .pred p, q;\n.reg .f32 s, d;\n.reg .b32 sb;\n"
+      "setp.lt.u32 p, %4, %5;\n"
+      "@p ld.shared.f32 s, [%0];\n"
+      "sub.rn.f32 d, %1, %2;\n"          // v - T
+      "mov.b32 sb, s;\n"
+      "setp.eq.u32 q, sb, 0x7FFFFFFF;\n"  // C[x]==0 : L.add(x); S[x]+=Q*T
+      "selp.f32 s, %3, s, q;\n"
+      "add.rn.f32 s, s, d;\n"            // S[x]+= v - T
+      "@p st.shared.f32 [%0], s;\n}"
+      ::"r"(a), "f"(v), "f"(T), "f"(QT0), "r"(lane), "r"(m)
+      : "memory");
+}
+
 // Adds the staged posting blocks of a whole group into S, chunk by chunk, in window order
 // (PlacementProcess.java:719-735).  Branch-free: idle lanes of a short chunk update their private dummy
 // entry.  Four register slots rotate through the descriptor list: the descriptor and the two loads of
@@ -393,11 +410,7 @@ static_assert((kStages * kStageMetaBytes) % 64 == 0, "stages start 16 B aligned"
 // list is padded with idle descriptors (m = 0) up to a multiple of four plus the look-ahead.
 #define RP_CHUNK_STEP(D_, V_, X_, OFF_)                                                                \
   {                                                                                                    \
-    const uint32_t idx = lane < D_.y ? X_ : dummy;                                                     \
-    float s_ = S[idx];                                                                                 \
-    if (is_sentinel(s_)) s_ = QT0;               /* C[x]==0 : L.add(x); S[x]+=Q*T   (:726-729) */     \
-    S[idx] = __fadd_rn(s_, __fsub_rn(V_, T));    /* S[x]+= v - T   (:733) */                          \
-    asm volatile("" ::: "memory");               /* keep the warp's smem accesses in program order */   \
+    rmw_posting(s_base + 4 * X_, V_, T, QT0, lane, D_.y);                                              \
     D_ = lds_u64(dp + OFF_);                                                                           \
     V_ = lds_f32(D_.x + lane4);                                                                        \
     X_ = lds_u16(D_.x + 4 * D_.y + lane2);                                                             \
@@ -405,8 +418,7 @@ static_assert((kStages * kStageMetaBytes) % 64 == 0, "stages start 16 B aligned"
 __device__ __forceinline__ void accumulate_chunks(float* __restrict__ S, uint32_t dl, int n_chunks, int n_pad, float QT0,
                                                   float T, int lane) {
   const uint32_t lane4 = lane * 4, lane2 = lane * 2;
-  uint32_t dummy;
-  asm volatile("add.u32 %0, %1, %2;" : "=r"(dummy) : "r"(n_pad), "r"(lane));  // pinned in a register
+  const uint32_t s_base = smem_u32(S);
   uint2 d0 = lds_u64(dl), d1 = lds_u64(dl + 8), d2 = lds_u64(dl + 16), d3 = lds_u64(dl + 24);
   float v0 = lds_f32(d0.x + lane4), v1 = lds_f32(d1.x + lane4), v2 = lds_f32(d2.x + lane4), v3 = lds_f32(d3.x + lane4);
   uint32_t x0 = lds_u16(d0.x + 4 * d0.y + lane2), x1 = lds_u16(d1.x + 4 * d1.y + lane2);
@@ -599,10 +611,8 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       if (stagedm) mbar_expect_tx(full, total);
       else mbar_arrive(full);
     }
-    if (copy_bytes) {
-      fence_proxy_async();  // the consumer's generic-proxy reads of this stage precede the async writes
-      bulk_g2s(copy_dst, copy_src, copy_bytes, full);
-    }
+    // (the consumer's reads of this stage are ordered before these async writes by its `empty` arrival)
+    if (copy_bytes) bulk_g2s(copy_dst, copy_src, copy_bytes, full);
     if (flags & kGrpLast) active = false;
   }
 }
