@@ -386,51 +386,62 @@ static_assert(sizeof(StageHdr) == 64, "StageHdr is one 64 B slot");
 constexpr int kStageMetaBytes = 64 + 128 + 256;
 static_assert((kStages * kStageMetaBytes) % 64 == 0, "stages start 16 B aligned");
 
-// S[x] += v - T for the lanes below m, with the first-touch rule; predicated (no branch, idle lanes do not
-// touch shared memory).  `a` = shared address of S[x].  PlacementProcess.java:726-733.
-__device__ __forceinline__ void rmw_posting(uint32_t a, float v, float T, float QT0, uint32_t lane, uint32_t m) {
+// S[x] += v - T for the lanes below m, with the first-touch rule (PlacementProcess.java:726-733), split into
+// the shared-memory load and the dependent tail so that independent work can be scheduled in between.
+// Predicated, no branch; idle lanes do not touch shared memory.  `a` = shared address of S[x].
+__device__ __forceinline__ float rmw_load(uint32_t a, uint32_t lane, uint32_t m) {
+  float s;
+  asm volatile("{\n.reg .pred p;\nsetp.lt.u32 p, %2, %3;\n@p ld.shared.f32 %0, [%1];\n}" : "=f"(s) : "r"(a), "r"(lane), "r"(m) : "memory");
+  return s;
+}
+__device__ __forceinline__ void rmw_store(uint32_t a, float s, float d, float QT0, uint32_t lane, uint32_t m) {
   asm volatile(
-      "{\n.reg .pred p, q;\n.reg .f32 s, d;\n.reg .b32 sb;\n"
-      "setp.lt.u32 p, %4, %5;\n"
-      "@p ld.shared.f32 s, [%0];\n"
-      "sub.rn.f32 d, %1, %2;\n"          // v - T
-      "mov.b32 sb, s;\n"
+      "{\n.reg .pred p, q;\n.reg .f32 t;\n.reg .b32 sb;\n"
+      "mov.b32 sb, %1;\n"
       "setp.eq.u32 q, sb, 0x7FFFFFFF;\n"  // C[x]==0 : L.add(x); S[x]+=Q*T
-      "selp.f32 s, %3, s, q;\n"
-      "add.rn.f32 s, s, d;\n"            // S[x]+= v - T
-      "@p st.shared.f32 [%0], s;\n}"
-      ::"r"(a), "f"(v), "f"(T), "f"(QT0), "r"(lane), "r"(m)
+      "selp.f32 t, %3, %1, q;\n"
+      "add.rn.f32 t, t, %2;\n"           // S[x]+= v - T
+      "setp.lt.u32 p, %4, %5;\n"
+      "@p st.shared.f32 [%0], t;\n}"
+      ::"r"(a), "f"(s), "f"(d), "f"(QT0), "r"(lane), "r"(m)
       : "memory");
 }
 
-// Adds the staged posting blocks of a whole group into S, chunk by chunk, in window order
-// (PlacementProcess.java:719-735).  Branch-free: idle lanes of a short chunk update their private dummy
-// entry.  Four register slots rotate through the descriptor list: the descriptor and the two loads of
-// chunk j+4 are issued right after chunk j has been added, three chunks before they are needed.  The
-// list is padded with idle descriptors (m = 0) up to a multiple of four plus the look-ahead.
-#define RP_CHUNK_STEP(D_, V_, X_, OFF_)                                                                \
+// Adds the staged posting blocks of a whole group into S, chunk by chunk, in window order.  Four register
+// slots (m, score, node) rotate through the descriptor list and the descriptor itself is fetched one
+// step earlier still, so no instruction of a step waits on a load issued in the same step: the loads of
+// chunk j+4 and the descriptor of chunk j+5 are issued between the S[x] load of chunk j and its
+// dependent tail.  The list is padded with idle descriptors (m = 0) for the rounds of four + look-ahead.
+#define RP_CHUNK_STEP(M_, V_, X_, OFF_)                                                                \
   {                                                                                                    \
-    rmw_posting(s_base + 4 * X_, V_, T, QT0, lane, D_.y);                                              \
-    D_ = lds_u64(dp + OFF_);                                                                           \
-    V_ = lds_f32(D_.x + lane4);                                                                        \
-    X_ = lds_u16(D_.x + 4 * D_.y + lane2);                                                             \
+    const uint32_t a_ = s_base + 4 * X_, m_ = M_;                                                      \
+    const float s_ = rmw_load(a_, lane, m_);                                                           \
+    const float d_ = __fsub_rn(V_, T);                                                                 \
+    M_ = dn.y;                                                                                         \
+    V_ = lds_f32(dn.x + lane4);                                                                        \
+    X_ = lds_u16(dn.x + 4 * dn.y + lane2);                                                             \
+    dn = lds_u64(dp + OFF_);                                                                           \
+    rmw_store(a_, s_, d_, QT0, lane, m_);                                                              \
   }
 __device__ __forceinline__ void accumulate_chunks(float* __restrict__ S, uint32_t dl, int n_chunks, int n_pad, float QT0,
                                                   float T, int lane) {
   const uint32_t lane4 = lane * 4, lane2 = lane * 2;
   const uint32_t s_base = smem_u32(S);
-  uint2 d0 = lds_u64(dl), d1 = lds_u64(dl + 8), d2 = lds_u64(dl + 16), d3 = lds_u64(dl + 24);
+  (void)n_pad;
+  const uint2 d0 = lds_u64(dl), d1 = lds_u64(dl + 8), d2 = lds_u64(dl + 16), d3 = lds_u64(dl + 24);
+  uint2 dn = lds_u64(dl + 32);
   float v0 = lds_f32(d0.x + lane4), v1 = lds_f32(d1.x + lane4), v2 = lds_f32(d2.x + lane4), v3 = lds_f32(d3.x + lane4);
   uint32_t x0 = lds_u16(d0.x + 4 * d0.y + lane2), x1 = lds_u16(d1.x + 4 * d1.y + lane2);
   uint32_t x2 = lds_u16(d2.x + 4 * d2.y + lane2), x3 = lds_u16(d3.x + 4 * d3.y + lane2);
-  uint32_t dp = dl + 32;  // descriptor j+4 of the round's first chunk
-  const uint32_t dend = dl + 8 * n_chunks;
+  uint32_t m0 = d0.y, m1 = d1.y, m2 = d2.y, m3 = d3.y;
+  uint32_t dp = dl + 40;  // descriptor j+5 of the round's first chunk
+  const uint32_t dend = dl + 40 + 8 * n_chunks;
 #pragma unroll 1
-  for (; dp - 32 < dend; dp += 32) {
-    RP_CHUNK_STEP(d0, v0, x0, 0)
-    RP_CHUNK_STEP(d1, v1, x1, 8)
-    RP_CHUNK_STEP(d2, v2, x2, 16)
-    RP_CHUNK_STEP(d3, v3, x3, 24)
+  for (; dp < dend; dp += 32) {
+    RP_CHUNK_STEP(m0, v0, x0, 0)
+    RP_CHUNK_STEP(m1, v1, x1, 8)
+    RP_CHUNK_STEP(m2, v2, x2, 16)
+    RP_CHUNK_STEP(m3, v3, x3, 24)
   }
   __syncwarp();
 }
@@ -478,7 +489,13 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
   for (uint32_t batch = 0;; batch++) {
     const int slot = batch % kStages;
     const uint32_t use = batch / kStages;
-    if (use) mbar_wait_sleep(w.bar + 8 * (kStages + slot), (use - 1) & 1u);  // the consumer has released the stage
+    // The stage is needed only once the group's table probes are back: everything up to there overlaps
+    // with the consumer still draining this stage's previous contents.
+    bool acquired = use == 0;
+    auto acquire = [&]() {
+      if (!acquired) mbar_wait_sleep(w.bar + 8 * (kStages + slot), (use - 1) & 1u);  // the consumer has released the stage
+      acquired = true;
+    };
     StageHdr* hdr = reinterpret_cast<StageHdr*>(w.meta + slot * kStageMetaBytes);
     uint32_t* pk_arr = reinterpret_cast<uint32_t*>(w.meta + slot * kStageMetaBytes + 64);
     uint64_t* meta_arr = reinterpret_cast<uint64_t*>(w.meta + slot * kStageMetaBytes + 192);
@@ -486,6 +503,7 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
     if (!active) {
       const unsigned long long rr = __shfl_sync(0xffffffffu, rn_raw, 0);
       if (rr >= (unsigned long long)bt.n_reads) {
+        acquire();
         if (lane == 0) {
           hdr->flags = kGrpStop;
           hdr->n_chunks = 0; hdr->hitm = hdr->ambm = hdr->stagedm = 0;
@@ -570,6 +588,7 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
         n_amb += __popc(ambm);
         n_skip += __popc(__ballot_sync(0xffffffffu, skip) & lanes);
         const uint32_t off = incl_bytes - sb;
+        acquire();
         if (ambm | (hitm & ~stagedm)) {  // the consumer's per-window path needs these
           pk_arr[lane] = (off << 16) | n_post;
           meta_arr[lane] = meta;
@@ -600,6 +619,7 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
         if (g0 >= Ql) flags |= kGrpLast;
       }
     }
+    acquire();
     if (lane == 0) {
       hdr->r = r; hdr->seq = seq_g0; hdr->Q = Ql; hdr->QT = QT; hdr->flags = flags;
       hdr->n_match = n_match; hdr->n_amb = n_amb; hdr->n_skip = n_skip;
@@ -815,7 +835,7 @@ int compute_geometry(const rp_db* db, DeviceCtx* dc) {
   const size_t optin = dc->smem_optin;         // 227 KB on sm_100
   const size_t sm_total = optin + 1024;        // 228 KB per SM, 1 KB reserved per resident CTA
   const double mean_block = db->desc.n_keys ? (double)db->block_bytes / (double)db->desc.n_keys : 32.0;
-  long stage = (long)(32.0 * mean_block * 0.65);
+  long stage = (long)(32.0 * mean_block * 0.8);  // tools/sweep_stage.sh: flat optimum around 0.65-0.8
   if (const char* e = getenv("RP_STAGE_BYTES")) stage = atol(e);
   stage = std::max(1024L, std::min(stage, 32768L - 128));
   stage = (stage + 127) & ~127L;
