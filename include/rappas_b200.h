@@ -172,6 +172,43 @@ int  rp_extract_kmers(rp_db* db, const uint8_t* seq, const uint64_t* seq_off, in
 int  rp_node_scores(rp_db* db, const rp_place_cfg* cfg, const uint8_t* seq, const uint64_t* seq_off,
                     int64_t n_reads, float* out_scores, int32_t* out_hitcount);
 
+/* ---- host side either end of the hot path (plain C++, no GPU work) -----------
+ * rp_reads = a parsed query file:
+ *   records   every FASTA record in file order: header = first line without '>', sequence = the other
+ *             lines joined and trimmed, gaps kept; empty and '#' lines skipped
+ *             (FASTAPointer.nextSequenceAsFastaObject, inputs/FASTAPointer.java:67-149)
+ *   unique    the distinct exact sequences in order of first appearance: what is sent to
+ *             rp_place_batch (a sequence is placed once however often it occurs)
+ *   group_of  id of the record's sequence with '-' removed = the reference's duplicate key
+ *             (MD5 of getSequence(true), core/algos/PlacementProcess.java:591-595)
+ */
+typedef struct rp_reads rp_reads;
+int  rp_reads_load_fasta(const char* path, rp_reads** out);
+int  rp_reads_from_memory(const uint8_t* text, uint64_t n_bytes, rp_reads** out);
+void rp_reads_free(rp_reads* r);
+int  rp_reads_describe(const rp_reads* r, uint64_t* n_records, uint64_t* n_unique, uint64_t* n_groups);
+/* pointers stay valid until rp_reads_free; seq_off has n_unique+1 entries, hdr_off n_records+1 */
+int  rp_reads_unique(const rp_reads* r, const uint8_t** seq, const uint64_t** seq_off);
+int  rp_reads_records(const rp_reads* r, const uint8_t** hdr, const uint64_t** hdr_off,
+                      const uint32_t** unique_of, const uint32_t** group_of);
+
+/* .jplace writer: the row assembly of PlacementProcess.java:974-1047 (column order :1005-1024, "nm" of
+ * duplicates :596-624, registration of a placement only once it has rows :1047) and the file shell of
+ * Main_PLACEMENT_v07.java:270-315, without json-simple and the seven whole-document regex passes.
+ * Results are those of rp_place_batch over rp_reads_unique (row-major [n_unique][keep_at_most]).
+ *   edge_id / branch_len [n_nodes]   PhyloNode.getJplaceEdgeId() / getBranchLengthToAncestor() per node id
+ *   not_placed_path                  optional: headers of reads without any k-mer hit (:797-806)
+ * Numbers are printed as Java's Float.toString / Double.toString would (what json-simple emits);
+ * the document equals the reference's as JSON (key order and whitespace are not reproduced).
+ * Fails if a record has status BAD_CHAR / TOO_SHORT / TOO_LONG: the reference aborts on those. */
+int  rp_jplace_write(const char* path, const rp_reads* r, int32_t keep_at_most, const int32_t* n_rows,
+                     const uint16_t* node, const float* score, const double* lwr, const int32_t* status,
+                     const int32_t* edge_id, const float* branch_len, int32_t n_nodes, const char* tree_newick,
+                     const char* invocation, int32_t guppy_compat, const char* not_placed_path,
+                     uint64_t* n_placements);
+/* Float.toString (as_float != 0) / Double.toString of v, as the writer prints numbers (test hook) */
+int  rp_java_number(double v, int32_t as_float, char* out, int32_t cap);
+
 /* ---- introspection used by bench.py / tests */
 int  rp_device_count(void);
 /* number of kernels this library launched since load (all threads); bench.py's gpu_launches */

@@ -55,6 +55,15 @@ PROTOTYPES = {
                                      _P, _P, _P, _P, _P, _P, _P]),
     "extract_kmers": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P]),
     "node_scores": (C.c_int, [_P, C.POINTER(RpPlaceCfg), _P, _P, C.c_int64, _P, _P]),
+    "reads_load_fasta": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
+    "reads_from_memory": (C.c_int, [_P, C.c_uint64, C.POINTER(_P)]),
+    "reads_free": (None, [_P]),
+    "reads_describe": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "reads_unique": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P)]),
+    "reads_records": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    "jplace_write": (C.c_int, [C.c_char_p, _P, C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_char_p,
+                               C.c_char_p, C.c_int32, C.c_char_p, C.POINTER(C.c_uint64)]),
+    "java_number": (C.c_int, [C.c_double, C.c_int32, C.c_char_p, C.c_int32]),
     "device_count": (C.c_int, []),
     "kernel_launch_count": (C.c_uint64, []),
     "last_kernel_ms": (C.c_double, [_P]),

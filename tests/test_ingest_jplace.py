@@ -1,0 +1,117 @@
+"""FASTA ingest + duplicate structure + .jplace writer (C++ in librappas_b200.so, no GPU work) against
+the literal Python restatement in tests/ref_host.py; placement rows come from the CPU oracle."""
+import json
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import ref_host
+from rappas_b200 import _abi, ingest, synth
+
+TRICKY = (
+    "# a comment line\n\n>r1 first read\nACGT\nACGTAC\r\n\n>r2\n  ACGTTT  \n>r3 dup of r1 with gaps\nAC-GT\nACG-TAC\n"
+    ">r4 exact dup of r1\nACGTACGTAC\n>r5\n#not a sequence line\nNNNN\rACGT\n>r6 empty\n>r7 last, no newline\nacgtRYK")
+
+
+def test_fasta_records_match_the_restatement():
+    q = ingest.QueryFile.from_text(TRICKY)
+    exp = ref_host.read_fasta(TRICKY)
+    assert q.n_records == len(exp) == 7
+    assert q.headers == [h for h, _ in exp]
+    seqs = [q.unique.read(int(u)) for u in q.unique_of]
+    assert seqs == [s for _, s in exp]
+    assert seqs[0] == "ACGTACGTAC" and seqs[1] == "ACGTTT" and seqs[5] == "" and seqs[6] == "acgtRYK"
+    # exact duplicates share a unique sequence; gapped variants share only the duplicate group
+    assert q.unique_of[0] == q.unique_of[3] != q.unique_of[2]
+    assert q.group_of[0] == q.group_of[2] == q.group_of[3]
+    assert q.n_unique == 6 and q.n_groups == 5
+
+
+def test_fasta_errors():
+    from rappas_b200._lib import RappasError
+    with pytest.raises(RappasError):
+        ingest.QueryFile.from_text("ACGT\n>late header\nACGT\n")
+    with pytest.raises(RappasError):
+        ingest.QueryFile.from_text("\n# nothing\n")
+    with pytest.raises(RappasError):
+        ingest.QueryFile.from_file("/nonexistent/q.fa")
+
+
+def test_java_number_layout():
+    known = {(1e-5, False): "1.0E-5", (100.0, False): "100.0", (1e7, False): "1.0E7", (0.001, False): "0.001",
+             (9999999.0, False): "9999999.0", (0.5, True): "0.5", (-487.12344, True): "-487.12344",
+             (1.0, False): "1.0", (123456.789, False): "123456.789", (1.0 / 3, False): "0.3333333333333333",
+             (0.0, False): "0.0", (float("inf"), False): "null", (3.4e38, True): "3.4E38", (1.17549435e-38, True): "1.1754944E-38"}
+    for (v, f), s in known.items():
+        assert ingest.java_number(v, f) == s == ref_host.java_number(v, f), (v, f)
+    rng = np.random.default_rng(0)
+    vals = np.concatenate([rng.normal(0, 1, 300), 10.0 ** rng.uniform(-12, 12, 300) * rng.choice([-1, 1], 300),
+                           -rng.uniform(0, 900, 300)])
+    for v in vals:
+        assert ingest.java_number(v) == ref_host.java_number(v)
+        assert ingest.java_number(v, True) == ref_host.java_number(v, True)
+        assert float(ingest.java_number(v)) == v and np.float32(ingest.java_number(v, True)) == np.float32(v)
+
+
+@pytest.mark.parametrize("guppy", [False, True])
+def test_jplace_equals_restatement(tmp_path, guppy):
+    db = synth.make_db(0, 6, 41, n_keys=2500, mean_postings=5, seed=0)
+    rb = synth.make_reads(db, 60, (5, 90), seed=100, n_rate=0.01)
+    rng = np.random.default_rng(1)
+    reads = [rb.read(i) for i in range(rb.n_reads)]
+    reads += ["TTTTTTTT" * 2, "T" * 5]  # probably unplaced; too short would abort the reference, so len >= k-1
+    lines = []
+    for i, s in enumerate(reads):
+        lines.append(">q%d some description %d" % (i, i))
+        lines.append(s)
+    for j in range(25):  # exact duplicates, gapped duplicates (gap = extra A for the placement, same checksum)
+        i = int(rng.integers(0, len(reads)))
+        s = reads[i]
+        if j % 3 == 0 and len(s) > 8:
+            cut = int(rng.integers(1, len(s) - 1))
+            s = s[:cut] + "-" + s[cut:]
+        lines.append(">dup%d of q%d" % (j, i))
+        lines.append(s)
+    text = "\n".join(lines) + "\n"
+    q = ingest.QueryFile.from_text(text)
+    odb = O.OracleDB(db)
+    cfg = _abi.place_cfg()
+    res = odb.place(q.unique, cfg)
+    edge_id = rng.permutation(db.n_nodes).astype(np.int32)
+    branch = rng.uniform(1e-4, 2.0, db.n_nodes).astype(np.float32)
+    out, npl = tmp_path / "out.jplace", tmp_path / "not_placed.txt"
+    n = q.write_jplace(out, res, cfg.keep_at_most, edge_id, branch, tree_newick="(A:1{0},B:2{1}){2};",
+                       invocation="test", guppy_compat=guppy, not_placed_path=npl)
+    raw = out.read_text()
+    doc = json.loads(raw)
+
+    def place_one(seq):
+        one = odb.place(synth.reads_from_strings([seq]), cfg)
+        k = int(one["n_rows"][0])
+        return int(one["status"][0]), [(int(one["node"][0, i]), one["score"][0, i], one["lwr"][0, i]) for i in range(k)]
+
+    exp, exp_np = ref_host.build_jplace(ref_host.read_fasta(text), place_one, edge_id, branch, guppy)
+    assert n == len(exp) == len(doc["placements"]) > 30
+    assert doc["version"] == 3 and doc["metadata"] == {"invocation": "test"} and doc["tree"] == "(A:1{0},B:2{1}){2};"
+    assert doc["fields"] == (["distal_length", "edge_num", "like_weight_ratio", "likelihood", "pendant_length"] if guppy
+                             else ["edge_num", "likelihood", "like_weight_ratio", "distal_length", "pendant_length"])
+    # numbers: compare the printed tokens (Java formatting) and the parsed values
+    got_rows = re.findall(r"\[([^\[\]\"]+)\]", raw.split('"placements"')[1].split('"version"')[0])
+    exp_rows = [",".join(str(c) for c in row) for pl in exp for row in pl["p"]]
+    assert got_rows == exp_rows
+    for g, e in zip(doc["placements"], exp):
+        assert g["nm"] == e["nm"]
+        assert len(g["p"]) == len(e["p"])
+    assert any(len(pl["nm"]) > 1 for pl in doc["placements"])
+    assert npl.read_text().splitlines() == exp_np
+
+
+def test_writer_refuses_reads_the_reference_aborts_on(tmp_path):
+    from rappas_b200._lib import RappasError
+    db = synth.make_db(0, 6, 41, n_keys=2500, mean_postings=5, seed=0)
+    q = ingest.QueryFile.from_text(">ok\nACGTACGTACGT\n>bad\nACGTZZACGTAA\n")
+    res = O.OracleDB(db).place(q.unique, _abi.place_cfg())
+    with pytest.raises(RappasError):
+        q.write_jplace(tmp_path / "x.jplace", res, 7, np.arange(41), np.ones(41))
