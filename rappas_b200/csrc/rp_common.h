@@ -90,13 +90,26 @@ int  max_ambig_per_mer(int alphabet, int k);  // AmbigSequenceKnife.java:95
 // ---------------------------------------------------------------------------------------------
 // device-side views passed to kernels by value
 // ---------------------------------------------------------------------------------------------
+// The DB seen by a kernel: one partition (replicated mode: this device's own copy) or all of them
+// (hash-partitioned mode: partition p lives in the HBM of one GPU, the others reach it over NVLink
+// through peer-mapped pointers -- probes are plain loads, posting gathers are the same bulk copies).
+constexpr int kMaxParts = 8;
 struct DbView {
-  const uint4* table;       // [n_buckets][2] slots
-  int bucket_shift;         // 32 - log2(n_buckets)
-  const uint8_t* blocks;
+  const uint4* table[kMaxParts];      // [n_buckets][2] slots of partition p
+  const uint8_t* blocks[kMaxParts];   // posting blocks of partition p
+  int bucket_shift[kMaxParts];        // 32 - log2(n_buckets)
+  int n_parts;
   int alphabet, k, bits, n_nodes, max_amb;
   float T, Tlin;
 };
+// owner partition of a key: a third multiplicative hash of the mix, so that the keys of one partition
+// still spread over all buckets of that partition's table under bucket1 / bucket2
+__host__ __device__ inline uint32_t owner_of(uint32_t mix, int n_parts) {
+  return (((mix * 0x85EBCA6Bu) >> 16) * (uint32_t)n_parts) >> 16;
+}
+// meta = (partition << 61) | (block_offset_in_32B_units << 16) | n_postings
+constexpr int kMetaPartShift = 61;
+constexpr uint64_t kMetaOffMask = (1ull << 45) - 1;
 
 struct CfgView {
   int K;
@@ -146,8 +159,7 @@ struct DeviceCtx {
   int device = -1;
   int sm_count = 0;
   size_t smem_optin = 0;
-  uint4* d_table = nullptr;
-  uint8_t* d_blocks = nullptr;
+  std::vector<int> parts;  // indices into rp_db::parts this device's kernels use (1 if replicated, all if partitioned)
   LaunchGeom geom;
   StreamCtx sc[2];  // double buffering for host-buffer calls (rp_place_batch)
   StreamCtx sc_dev; // scheduler counter + scratch of device-buffer calls (rp_place_batch_device)
@@ -156,8 +168,18 @@ struct DeviceCtx {
 
 }  // namespace rp
 
+namespace rp {
+struct Partition {   // one table + posting-block image resident on one device
+  int device = -1;
+  uint4* d_table = nullptr;
+  uint8_t* d_blocks = nullptr;
+  uint64_t n_buckets = 0, block_bytes = 0;
+};
+}  // namespace rp
+
 struct rp_db {
   rp_db_desc desc{};
+  std::vector<rp::Partition> parts;
   uint64_t n_buckets = 0;
   uint64_t block_bytes = 0;
   uint64_t max_block_bytes = 0;

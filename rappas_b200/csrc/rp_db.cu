@@ -89,9 +89,14 @@ static int log2_u64(uint64_t x) { int l = 0; while ((1ull << l) < x) l++; return
 
 DbView make_db_view(const rp_db* db, const DeviceCtx* dc) {
   DbView v;
-  v.table = dc->d_table;
-  v.bucket_shift = 32 - log2_u64(db->n_buckets);
-  v.blocks = dc->d_blocks;
+  memset(&v, 0, sizeof v);
+  v.n_parts = (int)dc->parts.size();
+  for (int i = 0; i < v.n_parts; i++) {
+    const Partition& pt = db->parts[dc->parts[i]];
+    v.table[i] = pt.d_table;
+    v.blocks[i] = pt.d_blocks;
+    v.bucket_shift[i] = 32 - log2_u64(pt.n_buckets);
+  }
   v.alphabet = db->desc.alphabet;
   v.k = db->desc.k;
   v.bits = alphabet_bits(db->desc.alphabet);
@@ -140,11 +145,13 @@ static bool cuckoo_insert(std::vector<uint64_t>& tab, int shift, uint64_t key, u
   return false;
 }
 
+// Builds the image of the keys sel[0..n_sel) (all keys if sel == nullptr) as partition `part`.
 static int build_image(const rp_db_desc* d, const uint64_t* keys, const uint64_t* offsets, const uint16_t* post_node,
-                       const float* post_score, HostImage* img) {
-  const uint64_t nk = d->n_keys;
-  if (offsets && nk && offsets[nk] != d->n_postings)
-    return set_error(RP_E_INVALID, "offsets[n_keys]=%llu != n_postings=%llu", (unsigned long long)offsets[nk],
+                       const float* post_score, const uint64_t* sel, uint64_t n_sel, int part, HostImage* img) {
+  const uint64_t nk = sel ? n_sel : d->n_keys;
+  auto key_at = [&](uint64_t j) { return sel ? sel[j] : j; };
+  if (offsets && d->n_keys && offsets[d->n_keys] != d->n_postings)
+    return set_error(RP_E_INVALID, "offsets[n_keys]=%llu != n_postings=%llu", (unsigned long long)offsets[d->n_keys],
                      (unsigned long long)d->n_postings);
   uint64_t nb = kMinBuckets;
   while (nb < nk) nb <<= 1;  // 2 slots per bucket -> load factor in (0.25, 0.5]
@@ -157,14 +164,15 @@ static int build_image(const rp_db_desc* d, const uint64_t* keys, const uint64_t
   // block offsets (32 B units)
   std::vector<uint64_t> boff(nk + 1, 0);
   uint64_t max_bb = 0;
-  for (uint64_t i = 0; i < nk; i++) {
+  for (uint64_t j = 0; j < nk; j++) {
+    const uint64_t i = key_at(j);
     if (offsets[i + 1] < offsets[i]) return set_error(RP_E_INVALID, "offsets not monotone at key %llu", (unsigned long long)i);
     uint64_t P = offsets[i + 1] - offsets[i];
     if (P > 65535) return set_error(RP_E_INVALID, "key %llu has %llu postings (> 65535)", (unsigned long long)i, (unsigned long long)P);
-    boff[i + 1] = boff[i] + block_bytes_for(P) / kBlockAlign;
+    boff[j + 1] = boff[j] + block_bytes_for(P) / kBlockAlign;
     max_bb = std::max(max_bb, block_bytes_for(P));
   }
-  if (boff[nk] >= (1ull << 48)) return set_error(RP_E_INVALID, "posting blocks exceed 2^48 * 32 B");
+  if (boff[nk] > kMetaOffMask) return set_error(RP_E_INVALID, "posting blocks exceed 2^45 * 32 B");
   img->block_bytes = boff[nk] * kBlockAlign;
   img->max_block_bytes = max_bb;
   img->blocks = (uint8_t*)calloc(img->block_bytes ? img->block_bytes : 32, 1);
@@ -179,7 +187,8 @@ static int build_image(const rp_db_desc* d, const uint64_t* keys, const uint64_t
   std::vector<std::vector<std::pair<uint64_t, uint64_t>>> leftover(nt);
   auto pack_range = [&](unsigned tid, uint64_t k0, uint64_t k1) {
     std::vector<std::pair<uint16_t, float>> tmp;
-    for (uint64_t i = k0; i < k1 && !err.load(std::memory_order_relaxed); i++) {
+    for (uint64_t j = k0; j < k1 && !err.load(std::memory_order_relaxed); j++) {
+      const uint64_t i = key_at(j);
       const uint64_t lo = offsets[i], P = offsets[i + 1] - offsets[i];
       if (keys[i] == kEmptyKey || keys[i] >= code_limit) { err = 4; return; }
       tmp.resize(P);
@@ -196,7 +205,7 @@ static int build_image(const rp_db_desc* d, const uint64_t* keys, const uint64_t
         for (uint64_t p = 1; p < P; p++)
           if (tmp[p].first == tmp[p - 1].first) { err = 2; return; }  // one value per (k-mer,node): CustomHash_v4:76-89
       }
-      uint8_t* blk = img->blocks + boff[i] * kBlockAlign;
+      uint8_t* blk = img->blocks + boff[j] * kBlockAlign;
       for (uint64_t base = 0; base < P; base += kSubBlock) {
         uint64_t m = std::min<uint64_t>(kSubBlock, P - base);
         float* sc = (float*)(blk + (base / kSubBlock) * kSubBlockBytes);
@@ -205,7 +214,7 @@ static int build_image(const rp_db_desc* d, const uint64_t* keys, const uint64_t
       }
       // greedy 2-choice placement (lock-free: CAS on the key word, then publish meta)
       const uint64_t key = planar_from_code(keys[i], bits, k);
-      const uint64_t meta = (boff[i] << 16) | P;
+      const uint64_t meta = ((uint64_t)part << kMetaPartShift) | (boff[j] << 16) | P;
       const uint32_t m32 = mix_key(key);
       const uint32_t bk[2] = {bucket1(m32, shift), bucket2(m32, shift)};
       bool placed = false;
@@ -267,8 +276,6 @@ static void free_device_ctx(DeviceCtx* dc) {
       if (s.ev_k1) cudaEventDestroy(s.ev_k1);
       if (s.stream) cudaStreamDestroy(s.stream);
     }
-    cudaFree(dc->d_table);
-    cudaFree(dc->d_blocks);
   }
   delete dc;
 }
@@ -312,7 +319,6 @@ int rp_db_load(const rp_db_desc* desc, const uint64_t* keys, const uint64_t* off
   if (rc) return rc;
   if (!out) return set_error(RP_E_INVALID, "out is NULL");
   *out = nullptr;
-  if (partitioned) return set_error(RP_E_UNSUPPORTED, "hash-partitioned DB mode is not built in this round (see DESIGN.md)");
   if (n_devices < 1 || !devices) return set_error(RP_E_INVALID, "need at least one device");
   if (desc->n_keys && (!keys || !offsets)) return set_error(RP_E_INVALID, "keys/offsets are NULL");
   if (desc->n_postings && (!post_node || !post_score)) return set_error(RP_E_INVALID, "posting arrays are NULL");
@@ -322,46 +328,96 @@ int rp_db_load(const rp_db_desc* desc, const uint64_t* keys, const uint64_t* off
   for (int i = 0; i < n_devices; i++)
     if (devices[i] < 0 || devices[i] >= ndev_avail) return set_error(RP_E_INVALID, "device %d not present", devices[i]);
 
-  HostImage img;
   static const uint64_t zero_off[1] = {0};
-  rc = build_image(desc, keys, desc->n_keys ? offsets : zero_off, post_node, post_score, &img);
-  if (rc) return rc;
+  if (!desc->n_keys) offsets = zero_off;
+  // distinct execution devices; with partitioned != 0 every entry of devices[] is one partition (an
+  // entry may repeat a device: several partitions in one HBM, which is how a 1-GPU box tests the mode)
+  std::vector<int> exec;
+  for (int i = 0; i < n_devices; i++)
+    if (std::find(exec.begin(), exec.end(), devices[i]) == exec.end()) exec.push_back(devices[i]);
+  const int n_parts = partitioned ? n_devices : 1;
+  if (n_parts > kMaxParts) return set_error(RP_E_UNSUPPORTED, "at most %d partitions", kMaxParts);
 
   rp_db* db = new rp_db();
   db->desc = *desc;
-  db->n_buckets = img.n_buckets;
-  db->block_bytes = img.block_bytes;
-  db->max_block_bytes = img.max_block_bytes;
-  db->partitioned = 0;
+  db->partitioned = partitioned ? 1 : 0;
   build_alphabet_tables(desc->alphabet, &db->alpha);
-  for (int i = 0; i < n_devices; i++) {
-    DeviceCtx* dc = new DeviceCtx();
-    db->dev.push_back(dc);
-    dc->device = devices[i];
-    cudaError_t e = cudaSetDevice(dc->device);
-    cudaDeviceProp prop;
-    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, dc->device);
-    if (e == cudaSuccess) {
-      dc->sm_count = prop.multiProcessorCount;
-      dc->smem_optin = prop.sharedMemPerBlockOptin;
-      e = cudaMalloc((void**)&dc->d_table, img.n_buckets * 32);
-    }
-    // +512 B: idle lanes of the last block's last chunk may address (never load) past its end, and an
-    // idle descriptor prefetches nothing from offset 0
-    if (e == cudaSuccess) e = cudaMalloc((void**)&dc->d_blocks, img.block_bytes + 512);
-    if (e == cudaSuccess) e = cudaMemcpy(dc->d_table, img.table.data(), img.n_buckets * 32, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && img.block_bytes)
-      e = cudaMemcpy(dc->d_blocks, img.blocks, img.block_bytes, cudaMemcpyHostToDevice);
+  auto fail = [&](int code) { rp_db_free(db); return code; };
+  auto upload = [&](const HostImage& img, int device) -> int {
+    Partition pt;
+    pt.device = device;
+    pt.n_buckets = img.n_buckets;
+    pt.block_bytes = img.block_bytes;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&pt.d_table, img.n_buckets * 32);
+    // +512 B: idle lanes of the last block's last chunk may address (never load) past its end
+    if (e == cudaSuccess) e = cudaMalloc((void**)&pt.d_blocks, img.block_bytes + 512);
+    if (e == cudaSuccess) e = cudaMemcpy(pt.d_table, img.table.data(), img.n_buckets * 32, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && img.block_bytes) e = cudaMemcpy(pt.d_blocks, img.blocks, img.block_bytes, cudaMemcpyHostToDevice);
+    db->parts.push_back(pt);  // owned (and freed) by the db even on failure
     if (e != cudaSuccess) {
-      int code = (e == cudaErrorMemoryAllocation) ? RP_E_NOMEM : RP_E_CUDA;
-      set_error(code, "device %d: %s while uploading the DB (%llu B table + %llu B blocks)", dc->device,
+      const int code = (e == cudaErrorMemoryAllocation) ? RP_E_NOMEM : RP_E_CUDA;
+      set_error(code, "device %d: %s while uploading the DB (%llu B table + %llu B blocks)", device,
                 cudaGetErrorString(e), (unsigned long long)(img.n_buckets * 32), (unsigned long long)img.block_bytes);
       cudaGetLastError();
-      rp_db_free(db);
       return code;
     }
-    rc = compute_geometry(db, dc);
-    if (rc) { rp_db_free(db); return rc; }
+    return RP_OK;
+  };
+
+  if (!partitioned) {
+    HostImage img;
+    rc = build_image(desc, keys, offsets, post_node, post_score, nullptr, 0, 0, &img);
+    if (rc) return fail(rc);
+    db->n_buckets = img.n_buckets;
+    db->block_bytes = img.block_bytes;
+    db->max_block_bytes = img.max_block_bytes;
+    for (int d : exec)
+      if ((rc = upload(img, d))) return fail(rc);
+  } else {
+    // keys go to partition owner_of(mix(planar key)): the kernel recomputes the same owner from the key
+    const int bits = alphabet_bits(desc->alphabet);
+    std::vector<std::vector<uint64_t>> sel(n_parts);
+    for (uint64_t i = 0; i < desc->n_keys; i++)
+      sel[owner_of(mix_key(planar_from_code(keys[i], bits, desc->k)), n_parts)].push_back(i);
+    for (int p = 0; p < n_parts; p++) {
+      HostImage img;
+      rc = build_image(desc, keys, offsets, post_node, post_score, sel[p].data(), sel[p].size(), p, &img);
+      if (rc) return fail(rc);
+      db->n_buckets = std::max(db->n_buckets, img.n_buckets);
+      db->block_bytes += img.block_bytes;
+      db->max_block_bytes = std::max(db->max_block_bytes, img.max_block_bytes);
+      if ((rc = upload(img, devices[p]))) return fail(rc);
+    }
+    // every executing device must reach every partition: peer-map the HBM of the others (NVLink)
+    for (int a : exec)
+      for (int b : exec) {
+        if (a == b) continue;
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, a, b);
+        if (!can) { set_error(RP_E_UNSUPPORTED, "device %d cannot map the memory of device %d (no peer access)", a, b); return fail(RP_E_UNSUPPORTED); }
+        cudaSetDevice(a);
+        cudaError_t e = cudaDeviceEnablePeerAccess(b, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+          set_error(RP_E_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", a, b, cudaGetErrorString(e));
+          return fail(RP_E_CUDA);
+        }
+        cudaGetLastError();
+      }
+  }
+  for (size_t i = 0; i < exec.size(); i++) {
+    DeviceCtx* dc = new DeviceCtx();
+    db->dev.push_back(dc);
+    dc->device = exec[i];
+    if (partitioned) for (int p = 0; p < n_parts; p++) dc->parts.push_back(p);
+    else dc->parts.push_back((int)i);
+    cudaDeviceProp prop;
+    cudaError_t e = cudaSetDevice(dc->device);
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, dc->device);
+    if (e != cudaSuccess) { set_error(RP_E_CUDA, "device %d: %s", dc->device, cudaGetErrorString(e)); return fail(RP_E_CUDA); }
+    dc->sm_count = prop.multiProcessorCount;
+    dc->smem_optin = prop.sharedMemPerBlockOptin;
+    if ((rc = compute_geometry(db, dc))) return fail(rc);
   }
   *out = db;
   return RP_OK;
@@ -370,6 +426,8 @@ int rp_db_load(const rp_db_desc* desc, const uint64_t* keys, const uint64_t* off
 void rp_db_free(rp_db* db) {
   if (!db) return;
   for (auto* dc : db->dev) free_device_ctx(dc);
+  for (auto& pt : db->parts)
+    if (pt.device >= 0 && cudaSetDevice(pt.device) == cudaSuccess) { cudaFree(pt.d_table); cudaFree(pt.d_blocks); }
   delete db;
 }
 
@@ -381,7 +439,11 @@ int rp_db_describe(const rp_db* db, rp_db_desc* out) {
 
 int rp_db_device_bytes(const rp_db* db, uint64_t* table_bytes, uint64_t* block_bytes) {
   if (!db) return set_error(RP_E_INVALID, "db is NULL");
-  if (table_bytes) *table_bytes = db->n_buckets * 32;
+  // replicated: one replica; partitioned: the sum over the partitions
+  uint64_t tb = 0;
+  for (auto& pt : db->parts) tb += pt.n_buckets * 32;
+  if (!db->partitioned && !db->parts.empty()) tb = db->parts[0].n_buckets * 32;
+  if (table_bytes) *table_bytes = tb;
   if (block_bytes) *block_bytes = db->block_bytes;
   return RP_OK;
 }

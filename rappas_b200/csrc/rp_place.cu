@@ -101,10 +101,14 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 // ------------------------------------------------------------------------------------ helpers
 // Cuckoo lookup: both candidate buckets (2 x 2 slots of 16 B) are loaded unconditionally.
+// In partitioned mode the owner partition's table is probed (peer memory over NVLink if it is remote).
 __device__ __forceinline__ bool table_probe(const DbView& db, uint64_t key, uint64_t& meta) {
   const uint32_t m = mix_key(key);
-  const uint4* p1 = db.table + (size_t)bucket1(m, db.bucket_shift) * kBucketSlots;
-  const uint4* p2 = db.table + (size_t)bucket2(m, db.bucket_shift) * kBucketSlots;
+  const int part = db.n_parts > 1 ? (int)owner_of(m, db.n_parts) : 0;
+  const uint4* table = db.table[part];
+  const int shift = db.bucket_shift[part];
+  const uint4* p1 = table + (size_t)bucket1(m, shift) * kBucketSlots;
+  const uint4* p2 = table + (size_t)bucket2(m, shift) * kBucketSlots;
   const uint4 s0 = __ldg(p1), s1 = __ldg(p1 + 1), s2 = __ldg(p2), s3 = __ldg(p2 + 1);
   const uint32_t klo = (uint32_t)key, khi = (uint32_t)(key >> 32);
   const bool h0 = s0.x == klo && s0.y == khi, h1 = s1.x == klo && s1.y == khi;
@@ -113,6 +117,11 @@ __device__ __forceinline__ bool table_probe(const DbView& db, uint64_t key, uint
   const uint32_t w = h0 ? s0.w : h1 ? s1.w : h2 ? s2.w : s3.w;
   meta = (uint64_t)z | ((uint64_t)w << 32);
   return h0 | h1 | h2 | h3;
+}
+
+// posting block a table meta points to (its partition is in the top bits)
+__device__ __forceinline__ const uint8_t* block_ptr(const DbView& db, uint64_t meta) {
+  return db.blocks[meta >> kMetaPartShift] + ((meta >> 16) & kMetaOffMask) * kBlockAlign;
 }
 
 __device__ __forceinline__ bool is_sentinel(float s) { return __float_as_uint(s) == kSentinelBits; }
@@ -191,7 +200,7 @@ __device__ __noinline__ void ambiguous_window(const AlphabetTables& c_alpha, con
     rem &= rem - 1;
     const uint64_t mt = __shfl_sync(0xffffffffu, meta, t);
     const int len = (int)(mt & 0xFFFF);
-    const uint8_t* p = db.blocks + (mt >> 16) * kBlockAlign;
+    const uint8_t* p = block_ptr(db, mt);
     for (int base = 0; base < len; base += kSubBlock, p += kSubBlockBytes) {
       const int m = min(kSubBlock, len - base);
       if (lane < m) {
@@ -217,7 +226,7 @@ __device__ __noinline__ void ambiguous_window(const AlphabetTables& c_alpha, con
     rem &= rem - 1;
     const uint64_t mt = __shfl_sync(0xffffffffu, meta, t);
     const int len = (int)(mt & 0xFFFF);
-    const uint8_t* p = db.blocks + (mt >> 16) * kBlockAlign;
+    const uint8_t* p = block_ptr(db, mt);
     for (int base = 0; base < len; base += kSubBlock, p += kSubBlockBytes) {
       const int m = min(kSubBlock, len - base);
       if (lane < m) {
@@ -601,7 +610,7 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
           const uint32_t dl0 = w.desc + slot * w.max_chunks * 8;
           if ((stagedm >> lane) & 1u) {
             copy_dst = stage0 + off;
-            copy_src = db.blocks + (meta >> 16) * kBlockAlign;
+            copy_src = block_ptr(db, meta);
             copy_bytes = bytes;
             // chunk descriptors of this window, in window order
             uint32_t dl = dl0 + 8 * (incl_chunks - my_chunks);
@@ -666,7 +675,7 @@ __device__ __forceinline__ void consumer(const AlphabetTables& c_alpha, const Db
           if ((g.stagedm >> l) & 1u) {
             accumulate_staged(S, stage + (pk >> 16), (int)(pk & 0xFFFF), QT0, db.T, lane);
           } else {
-            accumulate_global(S, db.blocks + (meta_arr[l] >> 16) * kBlockAlign, (int)(pk & 0xFFFF), QT0, db.T, lane);
+            accumulate_global(S, block_ptr(db, meta_arr[l]), (int)(pk & 0xFFFF), QT0, db.T, lane);
           }
         } else {
           ambiguous_window(c_alpha, db, cfg, S, g.seq + l, g.QT, Sa, Ca, lane);

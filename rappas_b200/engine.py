@@ -38,9 +38,11 @@ class Database:
         return cls(h, desc)
 
     @classmethod
-    def from_synth(cls, db, devices=(0,)):
+    def from_synth(cls, db, devices=(0,), partitioned=False):
+        """partitioned=True: every entry of `devices` holds one hash partition of the DB (an entry may repeat a
+        device); the kernels of every distinct device reach all partitions through peer-mapped memory."""
         return cls.from_arrays(db.alphabet, db.k, db.n_nodes, db.thr_lin, db.thr_log10, db.keys, db.offsets,
-                               db.post_node, db.post_score, devices=devices)
+                               db.post_node, db.post_score, devices=devices, partitioned=partitioned)
 
     @classmethod
     def from_file(cls, path, devices=(0,), partitioned=False):

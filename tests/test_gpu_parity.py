@@ -220,3 +220,65 @@ def test_multi_device_in_process_matches_single_device():
     a, b = one.place(rb), many.place(rb)
     for key in a:
         assert np.array_equal(a[key], b[key], equal_nan=True), key
+
+
+@pytest.mark.parametrize("n_parts", [2, 3, 8])
+def test_hash_partitioned_db_on_one_device(n_parts):
+    """Partitioned mode with every partition in the same HBM (how a 1-GPU box exercises it): same rows,
+    same k-mer hits and same per-node scores as the replicated DB and the oracle."""
+    import rappas_b200 as R
+    db = synth.make_db(0, 10, 1999, n_keys=100000, mean_postings=24, seed=7)
+    rb = synth.make_reads(db, 1500, (50, 400), seed=8, iupac_rate=0.005, n_rate=0.002)
+    part = R.Database.from_synth(db, devices=(0,) * n_parts, partitioned=True)
+    o = O.OracleDB(db)
+    parity.assert_extract_equal(part.extract(rb), o.extract(rb))
+    oo = o.place(rb)
+    parity.assert_placements_equal(part.place(rb), oo, 7, amb_reads(oo))
+    So, _ = o.node_scores(rb, hitcount=False)
+    parity.assert_scores_equal(part.node_scores(rb), So, amb_reads(oo))
+    tb, bb = part.device_bytes()
+    assert bb > 0 and tb >= n_parts * 32 * 32
+
+
+def test_hash_partitioned_db_over_peer_memory():
+    """One partition per GPU; every GPU places its slice of the reads, probing and gathering from the
+    owner's HBM over NVLink (peer-mapped pointers, no collective)."""
+    import rappas_b200 as R
+    nd = R.device_count()
+    if nd < 2:
+        pytest.skip("needs >= 2 GPUs")
+    db = synth.make_db(0, 10, 1999, n_keys=200000, mean_postings=32, seed=7)
+    rb = synth.make_reads(db, 30001, 150, seed=8, n_rate=0.002)
+    part = R.Database.from_synth(db, devices=tuple(range(nd)), partitioned=True)
+    one = R.Database.from_synth(db, devices=(0,))
+    a, b = one.place(rb), part.place(rb)
+    for key in a:
+        assert np.array_equal(a[key], b[key], equal_nan=True), key
+
+
+def test_fasta_to_jplace_through_the_gpu(tmp_path):
+    """FASTA text -> native ingest (unique sequences) -> CUDA placement -> .jplace, against the same
+    pipeline fed by the oracle (rows identical except among exactly tied scores)."""
+    import json
+    import rappas_b200 as R
+    from rappas_b200 import ingest
+    db = synth.make_db(0, 8, 299, n_keys=49152, mean_postings=16, seed=43)
+    rb = synth.make_reads(db, 400, (20, 300), seed=5, n_rate=0.003)
+    lines = []
+    for i in range(rb.n_reads):
+        lines += [">read%d len=%d" % (i, len(rb.read(i))), rb.read(i)]
+    for i in range(0, 100, 7):
+        lines += [">again%d" % i, rb.read(i)]
+    q = ingest.QueryFile.from_text("\n".join(lines) + "\n")
+    assert q.n_records == 415 and q.n_unique <= 400
+    cfg = _abi.place_cfg()
+    g, o = both(db)
+    rg, ro = g.place(q.unique, cfg), o.place(q.unique, cfg)
+    edge, bl = np.arange(db.n_nodes, dtype=np.int32), np.linspace(0.01, 1.0, db.n_nodes).astype(np.float32)
+    ng = q.write_jplace(tmp_path / "g.jplace", rg, 7, edge, bl, invocation="t")
+    no = q.write_jplace(tmp_path / "o.jplace", ro, 7, edge, bl, invocation="t")
+    dg, do = json.loads((tmp_path / "g.jplace").read_text()), json.loads((tmp_path / "o.jplace").read_text())
+    assert ng == no == len(dg["placements"]) and ng > 300
+    for pg, po in zip(dg["placements"], do["placements"]):
+        assert pg["nm"] == po["nm"] and len(pg["p"]) == len(po["p"])
+        assert [r[1] for r in pg["p"]] == [r[1] for r in po["p"]]  # likelihood column, bit-identical floats
