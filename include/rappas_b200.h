@@ -106,7 +106,10 @@ uint64_t rp_pack_kmer(int32_t alphabet, const uint8_t* states, int32_t k);
  *   post_node/score     postings of key i at [offsets[i], offsets[i+1]), in
  *                       char2FloatEntrySet() iteration order; node ids distinct within a key
  * devices[n_devices]    CUDA ordinals; the DB is replicated on each (partitioned = 0).
- * partitioned = 1       keys are hash-partitioned over the devices (DBs > one GPU's HBM).
+ * partitioned = 1       every entry of devices[] (<= 8, an ordinal may repeat) holds ONE hash partition
+ *                       of the keys and their postings (DBs > one GPU's HBM); the distinct devices
+ *                       peer-map each other's memory and each places its slice of the reads, probing
+ *                       and gathering from the owner's HBM over NVLink.  Same rows as replicated.
  */
 int  rp_db_load(const rp_db_desc* desc, const uint64_t* keys, const uint64_t* offsets,
                 const uint16_t* post_node, const float* post_score,
