@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--partitioned", action="store_true",
+                    help="hash-partition the DB over the ranks (peer memory over NVLink) instead of replicating it")
     return ap.parse_args()
 
 
@@ -204,7 +206,10 @@ def main():
     db = synth.make_db(w.alphabet, w.k, w.n_nodes, w.n_keys, w.mean_postings, seed=42 + w.index)
     rb = synth.make_reads(db, n_reads, w.read_len, seed=1042 + w.index + 7919 * rank, iupac_rate=w.iupac_rate,
                           n_rate=w.n_rate)
-    gdb = R.Database.from_synth(db, devices=(local_rank,))
+    if args.partitioned and world > 1:
+        gdb = R.Database.from_synth_partitioned_dist(db, device=local_rank)
+    else:
+        gdb = R.Database.from_synth(db, devices=(local_rank,))
     cfg = _abi.place_cfg()
     K = cfg.keep_at_most
     n = rb.n_reads
@@ -326,7 +331,8 @@ def main():
         "config": {"workload": w.name, "alphabet": "nucl" if w.alphabet == 0 else "amino", "k": w.k,
                    "n_nodes": w.n_nodes, "n_keys": db.n_keys, "n_postings": db.n_postings,
                    "reads_per_gpu": n, "read_len": w.read_len, "keep_at_most": K, "keep_factor": 0.01,
-                   "db_layout": "replicated per GPU, reads sharded, no collective",
+                   "db_layout": ("hash-partitioned over the GPUs (peer memory over NVLink), reads sharded, no collective"
+                                 if args.partitioned and world > 1 else "replicated per GPU, reads sharded, no collective"),
                    "l2_policy": "inputs larger than L2 (reads+DB+outputs %d MB per step vs 126 MB)"
                                 % ((rb.seq.nbytes + tbytes + bbytes + n * (K * 14 + 24)) >> 20)},
         "kmer_lookups_per_sec": world * lookups / (ms_step / 1e3),

@@ -119,6 +119,19 @@ int  rp_db_load_file(const char* path, const int32_t* devices, int32_t n_devices
                      int32_t partitioned, rp_db** out);
 int  rp_db_save_file(const char* path, const rp_db_desc* desc, const uint64_t* keys,
                      const uint64_t* offsets, const uint16_t* post_node, const float* post_score);
+/* Hash-partitioned DB with ONE PROCESS PER GPU (the torchrun deployment): rank `part` builds and uploads
+ * only its partition on `device` and gets a RP_PART_BLOB_BYTES blob (CUDA IPC handles + sizes); the ranks
+ * exchange the blobs (e.g. torch.distributed all_gather) and each calls rp_db_attach_partitions with all
+ * n_parts blobs in partition order, which maps the other GPUs' partitions into this process.  After
+ * that the handle behaves like rp_db_load(partitioned = 1) restricted to this rank's device. */
+#define RP_PART_BLOB_BYTES 152
+int  rp_db_load_partition(const rp_db_desc* desc, const uint64_t* keys, const uint64_t* offsets,
+                          const uint16_t* post_node, const float* post_score, int32_t device, int32_t part,
+                          int32_t n_parts, uint8_t* blob_out, rp_db** out);
+int  rp_db_attach_partitions(rp_db* db, const uint8_t* blobs, int32_t n_parts);
+/* owner partition (0..n_parts-1) of each k-mer code, as rp_db_load / the kernels compute it */
+int  rp_partition_of_keys(int32_t alphabet, int32_t k, const uint64_t* keys, uint64_t n_keys, int32_t n_parts,
+                          int32_t* out);
 void rp_db_free(rp_db* db);
 int  rp_db_describe(const rp_db* db, rp_db_desc* out);
 /* bytes of HBM the DB occupies on one device (table + posting blocks) */

@@ -7,4 +7,4 @@ Layout:
   synth         seeded synthetic DBs / reads of the BASELINE.json shapes
 """
 from ._abi import place_cfg  # noqa: F401
-from .engine import Database, device_count, kernel_launch_count  # noqa: F401
+from .engine import Database, device_count, kernel_launch_count, partition_of_keys  # noqa: F401

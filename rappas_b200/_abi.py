@@ -12,6 +12,7 @@ import numpy as np
 
 RP_OK = 0
 RP_MAX_KEEP = 32
+RP_PART_BLOB_BYTES = 152
 STATUS_PLACED, STATUS_UNPLACED, STATUS_TOO_SHORT, STATUS_BAD_CHAR = 0, 1, 2, 3
 WIN_PLAIN, WIN_AMBIG, WIN_SKIPPED = 0, 1, 2
 CNT_WINDOWS, CNT_MATCHED, CNT_AMBIG, CNT_SKIPPED = 0, 1, 2, 3
@@ -47,6 +48,9 @@ PROTOTYPES = {
     "db_load": (C.c_int, [C.POINTER(RpDbDesc), _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.POINTER(_P)]),
     "db_load_file": (C.c_int, [C.c_char_p, _P, C.c_int32, C.c_int32, C.POINTER(_P)]),
     "db_save_file": (C.c_int, [C.c_char_p, C.POINTER(RpDbDesc), _P, _P, _P, _P]),
+    "db_load_partition": (C.c_int, [C.POINTER(RpDbDesc), _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.POINTER(_P)]),
+    "db_attach_partitions": (C.c_int, [_P, _P, C.c_int32]),
+    "partition_of_keys": (C.c_int, [C.c_int32, C.c_int32, _P, C.c_uint64, C.c_int32, _P]),
     "db_free": (None, [_P]),
     "db_describe": (C.c_int, [_P, C.POINTER(RpDbDesc)]),
     "db_device_bytes": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),

@@ -174,6 +174,7 @@ struct Partition {   // one table + posting-block image resident on one device
   uint4* d_table = nullptr;
   uint8_t* d_blocks = nullptr;
   uint64_t n_buckets = 0, block_bytes = 0;
+  bool ipc = false;  // opened from another process' handle (cudaIpcCloseMemHandle instead of cudaFree)
 };
 }  // namespace rp
 

@@ -423,11 +423,120 @@ int rp_db_load(const rp_db_desc* desc, const uint64_t* keys, const uint64_t* off
   return RP_OK;
 }
 
+// ---- hash-partitioned DB across PROCESSES (one process per GPU, the bench / torchrun deployment) ------
+// Rank p builds and uploads partition p only, exports a 152-byte blob (two cudaIpcMemHandle_t + sizes),
+// the ranks exchange the blobs through whatever they have (torch.distributed all_gather), and every rank
+// attaches the others' partitions: the kernels then reach them exactly like the in-process peer pointers.
+struct PartBlob {
+  cudaIpcMemHandle_t table, blocks;
+  uint64_t n_buckets, block_bytes, n_keys;
+};
+static_assert(sizeof(PartBlob) == RP_PART_BLOB_BYTES, "blob layout");
+
+int rp_db_load_partition(const rp_db_desc* desc, const uint64_t* keys, const uint64_t* offsets,
+                         const uint16_t* post_node, const float* post_score, int32_t device, int32_t part,
+                         int32_t n_parts, uint8_t* blob_out, rp_db** out) {
+  int rc = check_desc(desc);
+  if (rc) return rc;
+  if (!out || !blob_out) return set_error(RP_E_INVALID, "NULL argument");
+  *out = nullptr;
+  if (n_parts < 1 || n_parts > kMaxParts || part < 0 || part >= n_parts) return set_error(RP_E_INVALID, "bad partition index");
+  if (rp_device_count() == 0) return set_error(RP_E_CUDA, "no CUDA device visible: librappas_b200 has no CPU fallback");
+  static const uint64_t zero_off[1] = {0};
+  if (!desc->n_keys) offsets = zero_off;
+  const int bits = alphabet_bits(desc->alphabet);
+  std::vector<uint64_t> sel;
+  for (uint64_t i = 0; i < desc->n_keys; i++)
+    if ((int)owner_of(mix_key(planar_from_code(keys[i], bits, desc->k)), n_parts) == part) sel.push_back(i);
+  HostImage img;
+  rc = build_image(desc, keys, offsets, post_node, post_score, sel.data(), sel.size(), part, &img);
+  if (rc) return rc;
+  rp_db* db = new rp_db();
+  db->desc = *desc;
+  db->partitioned = 2;  // 2 = waiting for rp_db_attach_partitions
+  build_alphabet_tables(desc->alphabet, &db->alpha);
+  db->parts.resize(n_parts);
+  Partition& pt = db->parts[part];
+  pt.device = device;
+  pt.n_buckets = img.n_buckets;
+  pt.block_bytes = img.block_bytes;
+  db->max_block_bytes = img.max_block_bytes;
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&pt.d_table, img.n_buckets * 32);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&pt.d_blocks, img.block_bytes + 512);
+  if (e == cudaSuccess) e = cudaMemcpy(pt.d_table, img.table.data(), img.n_buckets * 32, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && img.block_bytes) e = cudaMemcpy(pt.d_blocks, img.blocks, img.block_bytes, cudaMemcpyHostToDevice);
+  PartBlob blob;
+  memset(&blob, 0, sizeof blob);
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&blob.table, pt.d_table);
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&blob.blocks, pt.d_blocks);
+  if (e != cudaSuccess) {
+    set_error(e == cudaErrorMemoryAllocation ? RP_E_NOMEM : RP_E_CUDA, "device %d: %s while uploading partition %d", device,
+              cudaGetErrorString(e), part);
+    cudaGetLastError();
+    rp_db_free(db);
+    return e == cudaErrorMemoryAllocation ? RP_E_NOMEM : RP_E_CUDA;
+  }
+  blob.n_buckets = img.n_buckets;
+  blob.block_bytes = img.block_bytes;
+  blob.n_keys = sel.size();
+  memcpy(blob_out, &blob, sizeof blob);
+  DeviceCtx* dc = new DeviceCtx();
+  dc->device = device;
+  db->dev.push_back(dc);
+  *out = db;
+  return RP_OK;
+}
+
+int rp_db_attach_partitions(rp_db* db, const uint8_t* blobs, int32_t n_parts) {
+  if (!db || !blobs) return set_error(RP_E_INVALID, "NULL argument");
+  if (db->partitioned != 2 || (int)db->parts.size() != n_parts || db->dev.size() != 1)
+    return set_error(RP_E_INVALID, "db was not created by rp_db_load_partition with %d partitions", n_parts);
+  DeviceCtx* dc = db->dev[0];
+  RP_CUDA_TRY(cudaSetDevice(dc->device));
+  db->block_bytes = 0;
+  db->n_buckets = 0;
+  for (int p = 0; p < n_parts; p++) {
+    PartBlob blob;
+    memcpy(&blob, blobs + (size_t)p * sizeof blob, sizeof blob);
+    Partition& pt = db->parts[p];
+    if (pt.d_table == nullptr) {  // not mine: map the owner's allocations into this process
+      pt.device = dc->device;
+      pt.ipc = true;
+      pt.n_buckets = blob.n_buckets;
+      pt.block_bytes = blob.block_bytes;
+      RP_CUDA_TRY(cudaIpcOpenMemHandle((void**)&pt.d_table, blob.table, cudaIpcMemLazyEnablePeerAccess));
+      RP_CUDA_TRY(cudaIpcOpenMemHandle((void**)&pt.d_blocks, blob.blocks, cudaIpcMemLazyEnablePeerAccess));
+    }
+    db->block_bytes += pt.block_bytes;
+    db->n_buckets = std::max(db->n_buckets, pt.n_buckets);
+    dc->parts.push_back(p);
+  }
+  cudaDeviceProp prop;
+  RP_CUDA_TRY(cudaGetDeviceProperties(&prop, dc->device));
+  dc->sm_count = prop.multiProcessorCount;
+  dc->smem_optin = prop.sharedMemPerBlockOptin;
+  db->partitioned = 1;
+  return compute_geometry(db, dc);
+}
+
+// owner partition of each ABI k-mer code (host helper; the sharding tests check it against a restatement)
+int rp_partition_of_keys(int32_t alphabet, int32_t k, const uint64_t* keys, uint64_t n_keys, int32_t n_parts, int32_t* out) {
+  if ((!keys || !out) && n_keys) return set_error(RP_E_INVALID, "NULL argument");
+  if (n_parts < 1 || n_parts > kMaxParts) return set_error(RP_E_INVALID, "n_parts out of range");
+  const int bits = alphabet_bits(alphabet);
+  for (uint64_t i = 0; i < n_keys; i++) out[i] = (int32_t)owner_of(mix_key(planar_from_code(keys[i], bits, k)), n_parts);
+  return RP_OK;
+}
+
 void rp_db_free(rp_db* db) {
   if (!db) return;
   for (auto* dc : db->dev) free_device_ctx(dc);
-  for (auto& pt : db->parts)
-    if (pt.device >= 0 && cudaSetDevice(pt.device) == cudaSuccess) { cudaFree(pt.d_table); cudaFree(pt.d_blocks); }
+  for (auto& pt : db->parts) {
+    if (pt.device < 0 || cudaSetDevice(pt.device) != cudaSuccess) continue;
+    if (pt.ipc) { cudaIpcCloseMemHandle(pt.d_table); cudaIpcCloseMemHandle(pt.d_blocks); }
+    else { cudaFree(pt.d_table); cudaFree(pt.d_blocks); }
+  }
   delete db;
 }
 

@@ -45,6 +45,35 @@ class Database:
                                db.post_node, db.post_score, devices=devices, partitioned=partitioned)
 
     @classmethod
+    def from_synth_partitioned_dist(cls, db, device, group=None):
+        """One process per GPU: this rank uploads only its hash partition of `db` to `device`, the ranks
+        all_gather the CUDA-IPC blobs over torch.distributed, and every rank maps the others' partitions
+        (peer memory over NVLink).  Any backend works for the 152-byte exchange."""
+        import torch
+        import torch.distributed as dist
+        fn = load()
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        keys = np.ascontiguousarray(db.keys, dtype=np.uint64)
+        offsets = np.ascontiguousarray(db.offsets, dtype=np.uint64)
+        post_node = np.ascontiguousarray(db.post_node, dtype=np.uint16)
+        post_score = np.ascontiguousarray(db.post_score, dtype=np.float32)
+        desc = _abi.RpDbDesc(int(db.alphabet), int(db.k), int(db.n_nodes), float(db.thr_log10), float(db.thr_lin), 0,
+                             keys.shape[0], post_node.shape[0])
+        blob = np.zeros(_abi.RP_PART_BLOB_BYTES, np.uint8)
+        h = C.c_void_p()
+        check(fn["db_load_partition"](C.byref(desc), _abi.ptr(keys), _abi.ptr(offsets), _abi.ptr(post_node),
+                                      _abi.ptr(post_score), int(device), rank, world, _abi.ptr(blob), C.byref(h)))
+        self = cls(h, desc)
+        mine = torch.from_numpy(blob)
+        if dist.get_backend(group) == "nccl":
+            mine = mine.to(torch.device("cuda", int(device)))
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine, group=group)
+        blobs = np.ascontiguousarray(torch.stack(gathered).cpu().numpy())
+        check(fn["db_attach_partitions"](self._h, _abi.ptr(blobs), world))
+        return self
+
+    @classmethod
     def from_file(cls, path, devices=(0,), partitioned=False):
         fn = load()
         dev = np.ascontiguousarray(devices, dtype=np.int32)
@@ -130,6 +159,14 @@ class Database:
         check(load()["node_scores"](self._h, C.byref(cfg), _abi.ptr(reads.seq), _abi.ptr(reads.seq_off),
                                     reads.n_reads, _abi.ptr(S), None))
         return S
+
+
+def partition_of_keys(alphabet, k, keys, n_parts) -> np.ndarray:
+    """Owner partition of each k-mer code (host helper, no GPU needed)."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    out = np.zeros(keys.shape[0], np.int32)
+    check(load()["partition_of_keys"](int(alphabet), int(k), _abi.ptr(keys), keys.shape[0], int(n_parts), _abi.ptr(out)))
+    return out
 
 
 def kernel_launch_count() -> int:

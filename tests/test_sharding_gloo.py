@@ -58,3 +58,37 @@ def test_two_rank_sharded_placement_equals_single_process(tmp_path):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok").read_text() == "1001"
+
+
+def _owner_restatement(alphabet, k, keys, n_parts):
+    """numpy restatement of rp_common.h planar_from_code -> mix_key -> owner_of (uint32 arithmetic)."""
+    bits = 2 if alphabet == 0 else 5
+    keys = keys.astype(np.uint64)
+    planar = np.zeros_like(keys)
+    for i in range(k):
+        st = (keys >> np.uint64(bits * i)) & np.uint64((1 << bits) - 1)
+        for p in range(bits):
+            planar |= ((st >> np.uint64(p)) & np.uint64(1)) << np.uint64(p * k + i)
+    M = np.uint64(0xFFFFFFFF)
+    x = (planar & M) ^ (((planar >> np.uint64(32)) * np.uint64(0x9E3779B1)) & M)
+    x ^= x >> np.uint64(16); x = (x * np.uint64(0x7FEB352D)) & M
+    x ^= x >> np.uint64(15); x = (x * np.uint64(0x846CA68B)) & M
+    x ^= x >> np.uint64(16)
+    return (((((x * np.uint64(0x85EBCA6B)) & M) >> np.uint64(16)) * np.uint64(n_parts)) >> np.uint64(16)).astype(np.int32)
+
+
+@pytest.mark.parametrize("alphabet,k", [(0, 10), (0, 15), (0, 20), (1, 6)])
+def test_partition_of_keys_matches_restatement_and_balances(alphabet, k):
+    import rappas_b200 as R
+    rng = np.random.default_rng(k)
+    bits = 2 if alphabet == 0 else 5
+    if alphabet == 0:
+        keys = rng.integers(0, 1 << (bits * k), size=50000, dtype=np.uint64)
+    else:  # 5-bit states 0..19
+        st = rng.integers(0, 20, size=(50000, k), dtype=np.uint64)
+        keys = (st << (np.arange(k, dtype=np.uint64) * np.uint64(5))).sum(axis=1).astype(np.uint64)
+    for w in (1, 2, 3, 8):
+        own = R.partition_of_keys(alphabet, k, keys, w)
+        assert np.array_equal(own, _owner_restatement(alphabet, k, keys, w))
+        cnt = np.bincount(own, minlength=w)
+        assert cnt.min() > 0.9 * len(keys) / w and cnt.max() < 1.1 * len(keys) / w
