@@ -284,7 +284,7 @@ def main():
         d2h = int(sum(v.nbytes for v in outs.values()))
         e2e = {"value": world * n / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": dt * 1e3, "steps": e2e_steps,
-               "api": "rp_place_batch (C ABI, pinned host buffers, 2-stream chunked H2D/kernel/D2H)"}
+               "api": "rp_place_batch (C ABI, pinned host buffers, 2-stream 64k-read chunks: H2D / kernel / D2H overlapped)"}
         assert np.array_equal(outs["n_rows"], dev_out["n_rows"]) and np.array_equal(outs["score"], dev_out["score"])
 
     if rank != 0:

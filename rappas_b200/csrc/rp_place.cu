@@ -974,7 +974,9 @@ static int place_on_device(rp_db* db, DeviceCtx* dc, const rp_place_cfg* cfg, co
   std::lock_guard<std::mutex> lock(dc->mu);
   RP_CUDA_TRY(cudaSetDevice(dc->device));
   const int K = cfg->keep_at_most;
-  const int64_t kChunk = out_dump ? 4096 : (1 << 18);
+  // reads per H2D / kernel / D2H pipeline step (two streams alternate); RP_CHUNK_READS overrides for tuning
+  int64_t kChunk = out_dump ? 4096 : (1 << 16);  // tools/sweep_chunk.sh: 32k-128k reads are equivalent, 256k+ exposes the first H2D
+  if (const char* e = getenv("RP_CHUNK_READS")) if (!out_dump && atoll(e) > 0) kChunk = atoll(e);
   double ms_total = 0.0;
   int64_t pending_lo[2] = {-1, -1};
   float* d_dump[2] = {nullptr, nullptr};
