@@ -148,7 +148,7 @@ __device__ __forceinline__ uint64_t planar_from_states(const uint8_t* c, int k, 
 
 // Adds one posting block straight from global memory into S, in order (PlacementProcess.java:719-735):
 // posting lists too long for the descriptor ring.
-__device__ __noinline__ void accumulate_global(float* __restrict__ S, const uint8_t* p, int len, float QT0, float T,
+__device__ __forceinline__ void accumulate_global(float* __restrict__ S, const uint8_t* p, int len, float QT0, float T,
                                                int lane) {
   for (int base = 0; base < len; base += kSubBlock, p += kSubBlockBytes) {
     const int m = min(kSubBlock, len - base);
@@ -166,7 +166,7 @@ __device__ __noinline__ void accumulate_global(float* __restrict__ S, const uint
 // One ambiguous window (<= max_amb ambiguous residues): treatAmbiguitiesWithMean / WithMax,
 // PlacementProcess.java:1129-1174 / 1185-1236.  Rare path; S_amb/C_amb live in a per-warp global
 // scratch that is all-zero between calls.  `seq` = the window's first character.
-__device__ __noinline__ void ambiguous_window(const AlphabetTables& c_alpha, const DbView& db, const CfgView& cfg,
+__device__ __forceinline__ void ambiguous_window(const AlphabetTables& c_alpha, const DbView& db, const CfgView& cfg,
                                               float* __restrict__ S, const uint8_t* seq, float QT, float* Sa, int* Ca,
                                               int lane) {
   // class bytes of the window (k <= 31), and the ambiguous offsets inside it (ascending)
@@ -266,7 +266,7 @@ __device__ __forceinline__ uint32_t ordered_u32(float f) {
 //   2. nodes with score >= tau (a handful) go through a warp-shuffle insertion into the top-K list
 //      (lane i holds the i-th best; order: score desc, node id asc), and S is reset to the sentinel.
 // `emit` = false only resets (bad read).  Returns rows written, or -1 if no node was touched.
-__device__ __noinline__ int select_and_reset(const CfgView& cfg, float* __restrict__ S, int n_pad, bool emit,
+__device__ __forceinline__ int select_and_reset(const CfgView& cfg, float* __restrict__ S, int n_pad, bool emit,
                                              float* dump_row, int n_nodes, uint16_t* out_node, float* out_score,
                                              double* out_lwr, int lane) {
   const int K = cfg.K;
@@ -691,17 +691,14 @@ __device__ __forceinline__ void consumer(const AlphabetTables& c_alpha, const Db
     float* o_score = bt.score + r * K;
     double* o_lwr = bt.lwr + r * K;
     int status, rows = 0;
-    if (bad) {
-      select_and_reset(cfg, S, n_pad, false, nullptr, db.n_nodes, o_node, o_score, o_lwr, lane);
-      status = RP_STATUS_BAD_CHAR;
-    } else if (g.flags & kGrpTooLong) {
+    if (g.flags & kGrpTooLong) {
       status = RP_STATUS_TOO_LONG;
-    } else if (g.Q < 0) {
+    } else if (g.Q < 0 && !bad) {
       status = RP_STATUS_TOO_SHORT;
-    } else {
-      float* dump_row = bt.dump_scores ? bt.dump_scores + r * (size_t)db.n_nodes : nullptr;
-      rows = select_and_reset(cfg, S, n_pad, true, dump_row, db.n_nodes, o_node, o_score, o_lwr, lane);
-      status = rows < 0 ? RP_STATUS_UNPLACED : RP_STATUS_PLACED;  // L empty -> not placed (:797-806)
+    } else {  // one call site: a bad read only resets S
+      float* dump_row = (bt.dump_scores && !bad) ? bt.dump_scores + r * (size_t)db.n_nodes : nullptr;
+      rows = select_and_reset(cfg, S, n_pad, !bad, dump_row, db.n_nodes, o_node, o_score, o_lwr, lane);
+      status = bad ? RP_STATUS_BAD_CHAR : rows < 0 ? RP_STATUS_UNPLACED : RP_STATUS_PLACED;  // L empty -> not placed (:797-806)
     }
     if (rows <= 0 && status != RP_STATUS_PLACED) {
       rows = 0;
@@ -754,6 +751,10 @@ place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_consta
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  // (Both roles fit the 80 registers a 768-thread CTA gets.  The slow paths -- ambiguous windows, giant
+  // posting lists, selection -- are inlined on purpose: as ABI calls they made ptxas keep loop state in
+  // local memory around them, and with ~227 KB of shared memory carved out there is no L1 left, so every
+  // such spill was an L2 round trip: 20 % of the kernel time, profiles/r01_v5_spill_stalls.txt.)
   if (is_producer) {
     producer(c_alpha, db, cfg, bt, work_counter, w, smem_u32(smem), lane);
   } else {
