@@ -481,6 +481,36 @@ struct PairSmem {
 };
 
 // ---- K1 + K2: the producer warp ----------------------------------------------------------------
+// The table probe of a group is split into issue and resolve so that the probe of group i+1 is in flight
+// while the descriptors and bulk copies of group i are written: the characters of the next group are
+// already in registers (the class bytes of 96 characters are kept, shifted by the number of windows the
+// group consumed, and the following 32 are prefetched), so its keys need no memory access.
+struct ProbeIO {
+  uint4 s0, s1, s2, s3;   // the four candidate slots (in flight after issue)
+  uint32_t klo, khi;
+};
+__device__ __forceinline__ void probe_issue(const DbView& db, uint64_t key, bool active, ProbeIO& io) {
+  io.klo = (uint32_t)key; io.khi = (uint32_t)(key >> 32);
+  io.s0 = io.s1 = io.s2 = io.s3 = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u);  // the empty key never matches
+  if (active) {
+    const uint32_t m = mix_key(key);
+    const int part = db.n_parts > 1 ? (int)owner_of(m, db.n_parts) : 0;
+    const uint4* table = db.table[part];
+    const int shift = db.bucket_shift[part];
+    const uint4* p1 = table + (size_t)bucket1(m, shift) * kBucketSlots;
+    const uint4* p2 = table + (size_t)bucket2(m, shift) * kBucketSlots;
+    io.s0 = __ldg(p1); io.s1 = __ldg(p1 + 1); io.s2 = __ldg(p2); io.s3 = __ldg(p2 + 1);
+  }
+}
+__device__ __forceinline__ bool probe_resolve(const ProbeIO& io, uint64_t& meta) {
+  const bool h0 = io.s0.x == io.klo && io.s0.y == io.khi, h1 = io.s1.x == io.klo && io.s1.y == io.khi;
+  const bool h2 = io.s2.x == io.klo && io.s2.y == io.khi, h3 = io.s3.x == io.klo && io.s3.y == io.khi;
+  const uint32_t z = h0 ? io.s0.z : h1 ? io.s1.z : h2 ? io.s2.z : io.s3.z;
+  const uint32_t w = h0 ? io.s0.w : h1 ? io.s1.w : h2 ? io.s2.w : io.s3.w;
+  meta = (uint64_t)z | ((uint64_t)w << 32);
+  return h0 | h1 | h2 | h3;
+}
+
 __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const DbView& db, const CfgView& cfg,
                                          const BatchView& bt, unsigned long long* work_counter, const PairSmem& w,
                                          uint32_t cls_tab, int lane) {
@@ -493,8 +523,65 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
   long long r = -1;
   const uint8_t* s = nullptr;
   int len = 0, Ql = 0, g0 = 0, n_match = 0, n_amb = 0, n_skip = 0;
-  bool active = false, too_long = false;
+  bool too_long = false;
   float QT = 0.f;
+  // group about to be published: class bytes of characters [g0, g0+64), raw characters [g0+64, g0+96)
+  uint32_t cA = kClsPad, cB = kClsPad, rawC = 0;
+  // its window classification and its probe in flight
+  bool g_bad = false, g_plain = false, g_skip = false, g_ambw = false;
+  int g_nv = 0;
+  ProbeIO io;
+  io.klo = io.khi = 0; io.s0 = io.s1 = io.s2 = io.s3 = make_uint4(0, 0, 0, 0);
+
+  auto cls_of = [&](uint32_t raw, int i) -> uint32_t { return i < len ? lds_u8(cls_tab + raw) : (uint32_t)kClsPad; };
+  // K1 of the group whose class bytes are in cA/cB, and issue of its probes (K2)
+  auto front = [&]() {
+    g_bad = __any_sync(0xffffffffu, cA == kClsBad || cB == kClsBad);
+    g_plain = g_skip = g_ambw = false;
+    g_nv = 0;
+    uint64_t key = 0;
+    if (!g_bad && Ql > 0) {
+      // ambiguityCountPerMer of window g0+lane = popcount of the ambiguity bits of its k characters
+      const uint32_t a0 = __ballot_sync(0xffffffffu, (cA & 0xC0) == kClsAmb);
+      const uint32_t a1 = __ballot_sync(0xffffffffu, (cB & 0xC0) == kClsAmb);
+      const int na = __popc(__funnelshift_r(a0, a1, lane) & kmask);
+      g_nv = min(32, Ql - g0);  // windows left in the read
+      const bool valid = lane < g_nv;
+      // getNextByteWord (:224-233) + processQueries (:691-750)
+      g_plain = valid && na == 0;
+      g_skip = valid && na > 0 && (na > db.max_amb || !cfg.treat_amb);
+      g_ambw = valid && na > 0 && !g_skip;
+      // planar key: plane p of window `lane` = bits [lane, lane+k) of the p-th state-bit ballots
+      for (int p = 0; p < db.bits; p++) {
+        const uint32_t b0 = __ballot_sync(0xffffffffu, (cA >> p) & 1u);
+        const uint32_t b1 = __ballot_sync(0xffffffffu, (cB >> p) & 1u);
+        key |= (uint64_t)(__funnelshift_r(b0, b1, lane) & kmask) << (p * k);
+      }
+    }
+    probe_issue(db, key, g_plain, io);
+  };
+  // next read of this pair: false when the batch is exhausted
+  auto start_read = [&]() -> bool {
+    const unsigned long long rr = __shfl_sync(0xffffffffu, rn_raw, 0);
+    if (rr >= (unsigned long long)bt.n_reads) return false;
+    if (lane == 0) rn_raw = atomicAdd(work_counter, 1ull);  // consumed when this read is finished
+    const uint64_t o0 = bt.seq_off[rr], o1 = bt.seq_off[rr + 1];
+    r = (long long)rr;
+    s = bt.seq + (o0 - bt.seq_base);
+    too_long = (o1 - o0) > (uint64_t)kMaxReadLen;
+    len = too_long ? 0 : (int)(o1 - o0);
+    Ql = len - k + 1;  // sk.getMerCount()
+    QT = __fmul_rn((float)Ql, db.T);  // Q*PPStarThresholdAsLog10 (int*float)
+    g0 = 0;
+    n_match = n_amb = n_skip = 0;
+    cA = lane < len ? lds_u8(cls_tab + s[lane]) : (uint32_t)kClsPad;
+    cB = lane + 32 < len ? lds_u8(cls_tab + s[lane + 32]) : (uint32_t)kClsPad;
+    rawC = lane + 64 < len ? s[lane + 64] : 0u;
+    front();
+    return true;
+  };
+
+  bool have = start_read();
   for (uint32_t batch = 0;; batch++) {
     const int slot = batch % kStages;
     const uint32_t use = batch / kStages;
@@ -509,28 +596,14 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
     uint32_t* pk_arr = reinterpret_cast<uint32_t*>(w.meta + slot * kStageMetaBytes + 64);
     uint64_t* meta_arr = reinterpret_cast<uint64_t*>(w.meta + slot * kStageMetaBytes + 192);
     const uint32_t full = w.bar + 8 * slot;
-    if (!active) {
-      const unsigned long long rr = __shfl_sync(0xffffffffu, rn_raw, 0);
-      if (rr >= (unsigned long long)bt.n_reads) {
-        acquire();
-        if (lane == 0) {
-          hdr->flags = kGrpStop;
-          hdr->n_chunks = 0; hdr->hitm = hdr->ambm = hdr->stagedm = 0;
-          mbar_arrive(full);
-        }
-        return;
+    if (!have) {
+      acquire();
+      if (lane == 0) {
+        hdr->flags = kGrpStop;
+        hdr->n_chunks = 0; hdr->hitm = hdr->ambm = hdr->stagedm = 0;
+        mbar_arrive(full);
       }
-      if (lane == 0) rn_raw = atomicAdd(work_counter, 1ull);  // consumed when this read is finished
-      const uint64_t o0 = bt.seq_off[rr], o1 = bt.seq_off[rr + 1];
-      r = (long long)rr;
-      s = bt.seq + (o0 - bt.seq_base);
-      too_long = (o1 - o0) > (uint64_t)kMaxReadLen;
-      len = too_long ? 0 : (int)(o1 - o0);
-      Ql = len - k + 1;  // sk.getMerCount()
-      QT = __fmul_rn((float)Ql, db.T);  // Q*PPStarThresholdAsLog10 (int*float)
-      g0 = 0;
-      n_match = n_amb = n_skip = 0;
-      active = true;
+      return;
     }
     int flags = too_long ? kGrpTooLong : 0;
     int n_chunks = 0;
@@ -538,97 +611,93 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
     uint32_t copy_dst = 0, copy_bytes = 0;  // this lane's bulk copy, issued once the stage is published
     const uint8_t* copy_src = nullptr;
     const uint8_t* seq_g0 = s + g0;
-    if (Ql <= 0) {
-      // no window; still an unsupported character aborts the reference before the length matters
-      const uint32_t c = (lane < len) ? lds_u8(cls_tab + s[lane]) : kClsPad;
-      if (__any_sync(0xffffffffu, c == kClsBad)) flags |= kGrpBad;
+    // per-lane results of this group that the publication below needs
+    uint64_t meta = 0;
+    uint32_t n_post = 0, bytes = 0, my_chunks = 0, incl_chunks = 0, off = 0, incl = 0;
+    int cons = 0;
+    bool more = false;  // another group of this read follows (its probe is issued below)
+    if (g_bad) {
+      // an unsupported character aborts the reference whatever the length (AmbigSequenceKnife.java:124-128)
+      flags |= kGrpBad | kGrpLast;
+    } else if (Ql <= 0) {
       flags |= kGrpLast;
     } else {
-      // classes of characters [g0, g0+64): 32 window starts + up to k-1 <= 30 look-ahead
-      const int i0 = g0 + lane, i1 = i0 + 32;
-      const uint32_t c0 = (i0 < len) ? lds_u8(cls_tab + s[i0]) : kClsPad;
-      const uint32_t c1 = (i1 < len) ? lds_u8(cls_tab + s[i1]) : kClsPad;
-      if (__any_sync(0xffffffffu, c0 == kClsBad || c1 == kClsBad)) {
-        flags |= kGrpBad | kGrpLast;
-      } else {
-        // ambiguityCountPerMer of window g0+lane = popcount of the ambiguity bits of its k characters
-        const uint32_t a0 = __ballot_sync(0xffffffffu, (c0 & 0xC0) == kClsAmb);
-        const uint32_t a1 = __ballot_sync(0xffffffffu, (c1 & 0xC0) == kClsAmb);
-        const int na = __popc(__funnelshift_r(a0, a1, lane) & kmask);
-        const int nv = min(32, Ql - g0);  // windows left in the read
-        const bool valid = lane < nv;
-        // getNextByteWord (:224-233) + processQueries (:691-750)
-        const bool plain = valid && na == 0;
-        const bool skip = valid && na > 0 && (na > db.max_amb || !cfg.treat_amb);
-        const bool ambw = valid && na > 0 && !skip;
-        // planar key: plane p of window `lane` = bits [lane, lane+k) of the p-th state-bit ballots
-        uint64_t key = 0;
-        for (int p = 0; p < db.bits; p++) {
-          const uint32_t b0 = __ballot_sync(0xffffffffu, (c0 >> p) & 1u);
-          const uint32_t b1 = __ballot_sync(0xffffffffu, (c1 >> p) & 1u);
-          key |= (uint64_t)(__funnelshift_r(b0, b1, lane) & kmask) << (p * k);
-        }
-        uint64_t meta = 0;
-        bool found = false;
-        if (plain) found = table_probe(db, key, meta);
-        // stage assignment: windows are taken in order while their posting blocks fit into the stage;
-        // a block larger than a whole stage is read from global memory by the consumer instead
-        const uint32_t n_post = (uint32_t)(meta & 0xFFFF);
-        const uint32_t bytes = (n_post * 6 + 31) & ~31u;
-        const bool giant = bytes > (uint32_t)stage_bytes;
-        const uint32_t sb = (found && !giant) ? bytes : 0u;
-        // one scan for both prefix sums: bytes in 32 B units (<= 2^15 over the warp) above the chunk count (< 2^13)
-        const uint32_t my_chunks = sb ? (n_post + 31) >> 5 : 0u;
-        uint32_t incl = (sb >> 5 << 13) | my_chunks;
+      const bool found = probe_resolve(io, meta);
+      // stage assignment: windows are taken in order while their posting blocks fit into the stage;
+      // a block larger than a whole stage is read from global memory by the consumer instead
+      n_post = found ? (uint32_t)(meta & 0xFFFF) : 0u;
+      bytes = (n_post * 6 + 31) & ~31u;
+      const bool giant = bytes > (uint32_t)stage_bytes;
+      const uint32_t sb = (found && !giant) ? bytes : 0u;
+      // one scan for both prefix sums: bytes in 32 B units (<= 2^15 over the warp) above the chunk count (< 2^13)
+      my_chunks = sb ? (n_post + 31) >> 5 : 0u;
+      incl = (sb >> 5 << 13) | my_chunks;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-          if (lane >= d) incl += t;
-        }
-        const uint32_t incl_bytes = incl >> 13 << 5, incl_chunks = incl & 0x1FFFu;
-        const uint32_t nofit = __ballot_sync(0xffffffffu, incl_bytes > (uint32_t)stage_bytes);
-        int cons = nofit ? __ffs(nofit) - 1 : 32;  // >= 1: lane 0 alone always fits
-        cons = min(cons, nv);
-        const uint32_t lanes = cons >= 32 ? 0xffffffffu : ((1u << cons) - 1u);
-        hitm = __ballot_sync(0xffffffffu, found) & lanes;
-        ambm = __ballot_sync(0xffffffffu, ambw) & lanes;
-        stagedm = __ballot_sync(0xffffffffu, sb != 0u) & lanes;
-        n_match += __popc(hitm);
-        n_amb += __popc(ambm);
-        n_skip += __popc(__ballot_sync(0xffffffffu, skip) & lanes);
-        const uint32_t off = incl_bytes - sb;
-        acquire();
-        if (ambm | (hitm & ~stagedm)) {  // the consumer's per-window path needs these
-          pk_arr[lane] = (off << 16) | n_post;
-          meta_arr[lane] = meta;
-        }
-        if (stagedm) {
-          const uint32_t last = __shfl_sync(0xffffffffu, incl, cons - 1);
-          total = last >> 13 << 5;
-          n_chunks = (int)(last & 0x1FFFu);
-          const uint32_t stage0 = w.stage + slot * stage_bytes;
-          const uint32_t dl0 = w.desc + slot * w.max_chunks * 8;
-          if ((stagedm >> lane) & 1u) {
-            copy_dst = stage0 + off;
-            copy_src = block_ptr(db, meta);
-            copy_bytes = bytes;
-            // chunk descriptors of this window, in window order
-            uint32_t dl = dl0 + 8 * (incl_chunks - my_chunks);
-            uint32_t a = copy_dst;
-            for (uint32_t left = n_post; left; a += kSubBlockBytes, dl += 8) {
-              const uint32_t m = min(left, 32u);
-              sts_u64(dl, make_uint2(a, m));
-              left -= m;
-            }
-          }
-          if (lane < 8)  // idle descriptors behind the list: the consumer works in rounds of 4 and looks 4 ahead
-            sts_u64(dl0 + 8 * (n_chunks + lane), make_uint2(stage0, 0u));
-        }
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+      }
+      const uint32_t incl_bytes = incl >> 13 << 5;
+      incl_chunks = incl & 0x1FFFu;
+      const uint32_t nofit = __ballot_sync(0xffffffffu, incl_bytes > (uint32_t)stage_bytes);
+      cons = nofit ? __ffs(nofit) - 1 : 32;  // >= 1: lane 0 alone always fits
+      cons = min(cons, g_nv);
+      const uint32_t lanes = cons >= 32 ? 0xffffffffu : ((1u << cons) - 1u);
+      hitm = __ballot_sync(0xffffffffu, found) & lanes;
+      ambm = __ballot_sync(0xffffffffu, g_ambw) & lanes;
+      stagedm = __ballot_sync(0xffffffffu, sb != 0u) & lanes;
+      n_match += __popc(hitm);
+      n_amb += __popc(ambm);
+      n_skip += __popc(__ballot_sync(0xffffffffu, g_skip) & lanes);
+      off = incl_bytes - sb;
+      if (!((stagedm >> lane) & 1u)) bytes = 0;  // only staged windows are copied
+      if (g0 + cons >= Ql) {
+        flags |= kGrpLast;
+      } else {
+        // ---- next group of the read: shift the 96 known class bytes by `cons`, prefetch 32 more characters,
+        // and put its probes in flight before this group's descriptors and copies are written
+        more = true;
+        const uint32_t cC = cls_of(rawC, g0 + 64 + lane);
+        const int j = cons + lane;
+        const uint32_t tA = __shfl_sync(0xffffffffu, cA, j & 31), tB = __shfl_sync(0xffffffffu, cB, j & 31);
+        const uint32_t tC = __shfl_sync(0xffffffffu, cC, j & 31);
+        cA = j < 32 ? tA : tB;
+        cB = j < 32 ? tB : tC;
         g0 += cons;
-        if (g0 >= Ql) flags |= kGrpLast;
+        rawC = g0 + 64 + lane < len ? s[g0 + 64 + lane] : 0u;
       }
     }
+    // what the publication needs from the probe registers is saved: they are reused by the next group now
+    const uint32_t n_post_c = n_post, bytes_c = bytes, my_chunks_c = my_chunks, incl_chunks_c = incl_chunks, off_c = off;
+    const uint64_t meta_c = meta;
+    const uint32_t last_incl = (stagedm && cons > 0) ? __shfl_sync(0xffffffffu, incl, cons - 1) : 0u;
+    if (more) front();
     acquire();
+    if (ambm | (hitm & ~stagedm)) {  // the consumer's per-window path needs these
+      pk_arr[lane] = (off_c << 16) | n_post_c;
+      meta_arr[lane] = meta_c;
+    }
+    if (stagedm) {
+      total = last_incl >> 13 << 5;
+      n_chunks = (int)(last_incl & 0x1FFFu);
+      const uint32_t stage0 = w.stage + slot * stage_bytes;
+      const uint32_t dl0 = w.desc + slot * w.max_chunks * 8;
+      if (bytes_c) {
+        copy_dst = stage0 + off_c;
+        copy_src = block_ptr(db, meta_c);
+        copy_bytes = bytes_c;
+        // chunk descriptors of this window, in window order
+        uint32_t dl = dl0 + 8 * (incl_chunks_c - my_chunks_c);
+        uint32_t a = copy_dst;
+        for (uint32_t left = n_post_c; left; a += kSubBlockBytes, dl += 8) {
+          const uint32_t m = min(left, 32u);
+          sts_u64(dl, make_uint2(a, m));
+          left -= m;
+        }
+      }
+      if (lane < 8)  // idle descriptors behind the list: the consumer works in rounds of 4 and looks 4 ahead
+        sts_u64(dl0 + 8 * (n_chunks + lane), make_uint2(stage0, 0u));
+    }
     if (lane == 0) {
       hdr->r = r; hdr->seq = seq_g0; hdr->Q = Ql; hdr->QT = QT; hdr->flags = flags;
       hdr->n_match = n_match; hdr->n_amb = n_amb; hdr->n_skip = n_skip;
@@ -642,7 +711,7 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
     }
     // (the consumer's reads of this stage are ordered before these async writes by its `empty` arrival)
     if (copy_bytes) bulk_g2s(copy_dst, copy_src, copy_bytes, full);
-    if (flags & kGrpLast) active = false;
+    if (flags & kGrpLast) have = start_read();
   }
 }
 
