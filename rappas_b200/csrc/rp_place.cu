@@ -31,6 +31,7 @@
 // accumulated in exactly the reference's f32 order (bit-exact scores, no atomics).  Untouched entries
 // hold a NaN sentinel; "first touch" (C[x]==0 in the reference) is `S[x] is the sentinel`.
 #include <math.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -56,6 +57,7 @@ __device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatil
 __device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint2 lds_u64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts_u64(uint32_t a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory"); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -517,10 +519,11 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
   const int k = db.k;
   const uint32_t kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
   const int stage_bytes = w.stage_bytes;
-  unsigned long long rn_raw = 0;  // lane 0: result of the atomicAdd that fetched the NEXT read
-  if (lane == 0) rn_raw = atomicAdd(work_counter, 1ull);
+  // (read indices are 32-bit here: rp_place_batch_device refuses batches of 2^31 reads or more)
+  uint32_t rn_raw = 0;  // lane 0: result of the atomicAdd that fetched the read after the next
+  if (lane == 0) rn_raw = (uint32_t)atomicAdd(work_counter, 1ull);
   // read being cut into groups
-  long long r = -1;
+  uint32_t r = 0;
   const uint8_t* s = nullptr;
   int len = 0, Ql = 0, g0 = 0, n_match = 0, n_amb = 0, n_skip = 0;
   bool too_long = false;
@@ -560,16 +563,28 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
     }
     probe_issue(db, key, g_plain, io);
   };
+  // The NEXT read of the pair: its index comes from the atomic issued one read earlier and its two
+  // offsets are requested when the current read starts, so a read start waits for its characters only.
+  // (Prefetching those too costs the producer more registers than it has: it spills.)
+  uint32_t nx_r = 0;
+  uint64_t nx_o0 = 0, nx_o1 = 0;
+  bool nx_have = false;
+  auto fetch_next_offsets = [&]() {
+    nx_r = __shfl_sync(0xffffffffu, rn_raw, 0);
+    nx_have = (long long)nx_r < bt.n_reads;
+    if (nx_have) {
+      if (lane == 0) rn_raw = (uint32_t)atomicAdd(work_counter, 1ull);  // consumed when that read starts
+      nx_o0 = bt.seq_off[nx_r];
+      nx_o1 = bt.seq_off[nx_r + 1];
+    }
+  };
   // next read of this pair: false when the batch is exhausted
   auto start_read = [&]() -> bool {
-    const unsigned long long rr = __shfl_sync(0xffffffffu, rn_raw, 0);
-    if (rr >= (unsigned long long)bt.n_reads) return false;
-    if (lane == 0) rn_raw = atomicAdd(work_counter, 1ull);  // consumed when this read is finished
-    const uint64_t o0 = bt.seq_off[rr], o1 = bt.seq_off[rr + 1];
-    r = (long long)rr;
-    s = bt.seq + (o0 - bt.seq_base);
-    too_long = (o1 - o0) > (uint64_t)kMaxReadLen;
-    len = too_long ? 0 : (int)(o1 - o0);
+    if (!nx_have) return false;
+    r = nx_r;
+    s = bt.seq + (nx_o0 - bt.seq_base);
+    too_long = (nx_o1 - nx_o0) > (uint64_t)kMaxReadLen;
+    len = too_long ? 0 : (int)(nx_o1 - nx_o0);
     Ql = len - k + 1;  // sk.getMerCount()
     QT = __fmul_rn((float)Ql, db.T);  // Q*PPStarThresholdAsLog10 (int*float)
     g0 = 0;
@@ -577,10 +592,12 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
     cA = lane < len ? lds_u8(cls_tab + s[lane]) : (uint32_t)kClsPad;
     cB = lane + 32 < len ? lds_u8(cls_tab + s[lane + 32]) : (uint32_t)kClsPad;
     rawC = lane + 64 < len ? s[lane + 64] : 0u;
+    fetch_next_offsets();
     front();
     return true;
   };
 
+  fetch_next_offsets();
   bool have = start_read();
   for (uint32_t batch = 0;; batch++) {
     const int slot = batch % kStages;
@@ -592,15 +609,13 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       if (!acquired) mbar_wait_sleep(w.bar + 8 * (kStages + slot), (use - 1) & 1u);  // the consumer has released the stage
       acquired = true;
     };
-    StageHdr* hdr = reinterpret_cast<StageHdr*>(w.meta + slot * kStageMetaBytes);
-    uint32_t* pk_arr = reinterpret_cast<uint32_t*>(w.meta + slot * kStageMetaBytes + 64);
-    uint64_t* meta_arr = reinterpret_cast<uint64_t*>(w.meta + slot * kStageMetaBytes + 192);
+    // everything of the pair is addressed from its base (see the layout above): few live registers
+    const uint32_t hdr = w.bar + 64 + slot * kStageMetaBytes;  // StageHdr | pk u32[32] | meta u64[32]
     const uint32_t full = w.bar + 8 * slot;
     if (!have) {
       acquire();
       if (lane == 0) {
-        hdr->flags = kGrpStop;
-        hdr->n_chunks = 0; hdr->hitm = hdr->ambm = hdr->stagedm = 0;
+        sts_u32(hdr + offsetof(StageHdr, flags), kGrpStop);
         mbar_arrive(full);
       }
       return;
@@ -674,14 +689,15 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
     if (more) front();
     acquire();
     if (ambm | (hitm & ~stagedm)) {  // the consumer's per-window path needs these
-      pk_arr[lane] = (off_c << 16) | n_post_c;
-      meta_arr[lane] = meta_c;
+      sts_u32(hdr + 64 + 4 * lane, (off_c << 16) | n_post_c);
+      sts_u64(hdr + 192 + 8 * lane, make_uint2((uint32_t)meta_c, (uint32_t)(meta_c >> 32)));
     }
     if (stagedm) {
       total = last_incl >> 13 << 5;
       n_chunks = (int)(last_incl & 0x1FFFu);
-      const uint32_t stage0 = w.stage + slot * stage_bytes;
-      const uint32_t dl0 = w.desc + slot * w.max_chunks * 8;
+      const uint32_t stages = w.bar + 64 + kStages * kStageMetaBytes;
+      const uint32_t stage0 = stages + slot * stage_bytes;
+      const uint32_t dl0 = stages + kStages * stage_bytes + slot * w.max_chunks * 8;
       if (bytes_c) {
         copy_dst = stage0 + off_c;
         copy_src = block_ptr(db, meta_c);
@@ -699,9 +715,15 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
         sts_u64(dl0 + 8 * (n_chunks + lane), make_uint2(stage0, 0u));
     }
     if (lane == 0) {
-      hdr->r = r; hdr->seq = seq_g0; hdr->Q = Ql; hdr->QT = QT; hdr->flags = flags;
-      hdr->n_match = n_match; hdr->n_amb = n_amb; hdr->n_skip = n_skip;
-      hdr->n_chunks = n_chunks; hdr->hitm = hitm; hdr->ambm = ambm; hdr->stagedm = stagedm;
+      StageHdr h;
+      h.r = r; h.seq = seq_g0; h.Q = Ql; h.QT = QT; h.flags = flags;
+      h.n_match = n_match; h.n_amb = n_amb; h.n_skip = n_skip;
+      h.n_chunks = n_chunks; h.hitm = hitm; h.ambm = ambm; h.stagedm = stagedm;
+      h.pad[0] = h.pad[1] = 0;
+      const uint4* q = reinterpret_cast<const uint4*>(&h);
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(hdr + 16 * i), "r"(q[i].x), "r"(q[i].y), "r"(q[i].z), "r"(q[i].w) : "memory");
     }
     __syncwarp();  // every lane's descriptors / arrays are written before the stage is published
     if (lane == 0) {
@@ -914,7 +936,7 @@ int compute_geometry(const rp_db* db, DeviceCtx* dc) {
   const size_t optin = dc->smem_optin;         // 227 KB on sm_100
   const size_t sm_total = optin + 1024;        // 228 KB per SM, 1 KB reserved per resident CTA
   const double mean_block = db->desc.n_keys ? (double)db->block_bytes / (double)db->desc.n_keys : 32.0;
-  long stage = (long)(32.0 * mean_block * 0.8);  // tools/sweep_stage.sh: flat optimum around 0.65-0.8
+  long stage = (long)(32.0 * mean_block * 0.88);  // tools/sweep_stage.sh: flat optimum 0.8-0.95
   if (const char* e = getenv("RP_STAGE_BYTES")) stage = atol(e);
   stage = std::max(1024L, std::min(stage, 32768L - 128));
   stage = (stage + 127) & ~127L;
@@ -1178,6 +1200,7 @@ int rp_place_batch_device(rp_db* db, int32_t device_index, const rp_place_cfg* c
   if (rc) return rc;
   if (device_index < 0 || device_index >= (int)db->dev.size()) return set_error(RP_E_INVALID, "bad device_index");
   if (n_reads <= 0) return n_reads == 0 ? RP_OK : set_error(RP_E_INVALID, "n_reads < 0");
+  if (n_reads >= (1ll << 31)) return set_error(RP_E_INVALID, "n_reads >= 2^31 in one launch: split the batch");
   DeviceCtx* dc = db->dev[device_index];
   std::lock_guard<std::mutex> lock(dc->mu);
   RP_CUDA_TRY(cudaSetDevice(dc->device));
