@@ -153,6 +153,7 @@ struct LaunchGeom {
   int n_pad = 0;        // S[] entries per pair, multiple of 128
   int stage_bytes = 0;  // one posting stage (kStages per pair), multiple of 128
   int max_chunks = 0;   // chunk descriptors per stage
+  int consumers = 1;    // consumer warps per team (1 producer + `consumers` warps share one read)
 };
 
 struct DeviceCtx {

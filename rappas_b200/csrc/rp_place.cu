@@ -56,6 +56,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint2 lds_u64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts_u64(uint32_t a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory"); }
@@ -151,12 +152,12 @@ __device__ __forceinline__ uint64_t planar_from_states(const uint8_t* c, int k, 
 // Adds one posting block straight from global memory into S, in order (PlacementProcess.java:719-735):
 // posting lists too long for the descriptor ring.
 __device__ __forceinline__ void accumulate_global(float* __restrict__ S, const uint8_t* p, int len, float QT0, float T,
-                                               int lane) {
+                                               int lane, uint32_t lo, uint32_t width) {
   for (int base = 0; base < len; base += kSubBlock, p += kSubBlockBytes) {
     const int m = min(kSubBlock, len - base);
-    if (lane < m) {
+    const unsigned x = lane < m ? __ldg((const unsigned short*)(p + 4 * m) + lane) : 0xFFFFFFFFu;
+    if (x - lo < width) {  // this consumer's nodes only (lanes >= m never qualify)
       const float v = __ldg((const float*)p + lane);
-      const unsigned x = __ldg((const unsigned short*)(p + 4 * m) + lane);
       float s = S[x];
       if (is_sentinel(s)) s = QT0;            // C[x]==0 : L.add(x); S[x]+=Q*T   (:726-729)
       S[x] = __fadd_rn(s, __fsub_rn(v, T));   // S[x]+= v - T   (:733)
@@ -170,7 +171,7 @@ __device__ __forceinline__ void accumulate_global(float* __restrict__ S, const u
 // scratch that is all-zero between calls.  `seq` = the window's first character.
 __device__ __forceinline__ void ambiguous_window(const AlphabetTables& c_alpha, const DbView& db, const CfgView& cfg,
                                               float* __restrict__ S, const uint8_t* seq, float QT, float* Sa, int* Ca,
-                                              int lane) {
+                                              int lane, uint32_t lo, uint32_t width) {
   // class bytes of the window (k <= 31), and the ambiguous offsets inside it (ascending)
   uint8_t cls[32];
   uint32_t wbits = 0;
@@ -205,9 +206,9 @@ __device__ __forceinline__ void ambiguous_window(const AlphabetTables& c_alpha, 
     const uint8_t* p = block_ptr(db, mt);
     for (int base = 0; base < len; base += kSubBlock, p += kSubBlockBytes) {
       const int m = min(kSubBlock, len - base);
-      if (lane < m) {
+      const unsigned x = lane < m ? __ldg((const unsigned short*)(p + 4 * m) + lane) : 0xFFFFFFFFu;
+      if (x - lo < width) {  // this consumer's nodes only
         const float v = __ldg((const float*)p + lane);
-        const unsigned x = __ldg((const unsigned short*)(p + 4 * m) + lane);
         const int c = __ldcg(Ca + x);
         float sa = __ldcg(Sa + x);
         if (cfg.amb_with_max) {
@@ -231,8 +232,8 @@ __device__ __forceinline__ void ambiguous_window(const AlphabetTables& c_alpha, 
     const uint8_t* p = block_ptr(db, mt);
     for (int base = 0; base < len; base += kSubBlock, p += kSubBlockBytes) {
       const int m = min(kSubBlock, len - base);
-      if (lane < m) {
-        const unsigned x = __ldg((const unsigned short*)(p + 4 * m) + lane);
+      const unsigned x = lane < m ? __ldg((const unsigned short*)(p + 4 * m) + lane) : 0xFFFFFFFFu;
+      if (x - lo < width) {
         const int c = __ldcg(Ca + x);
         if (c != 0) {
           const float sa = __ldcg(Sa + x);
@@ -262,44 +263,63 @@ __device__ __forceinline__ uint32_t ordered_u32(float f) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-// K4.  fillBestScoreList (:396-451) + row loop (:974-1000).  Two passes over S:
+// K4.  fillBestScoreList (:396-451) + row loop (:974-1000).
+// select_scan: two passes over the nodes [lo, hi) of S (multiples of 128):
 //   1. every lane takes the maximum of its own nodes; the K-th largest of the 32 lane maxima is a
 //      lower bound tau of the K-th best score (K distinct nodes reach it);
 //   2. nodes with score >= tau (a handful) go through a warp-shuffle insertion into the top-K list
 //      (lane i holds the i-th best; order: score desc, node id asc), and S is reset to the sentinel.
-// `emit` = false only resets (bad read).  Returns rows written, or -1 if no node was touched.
-__device__ __forceinline__ int select_and_reset(const CfgView& cfg, float* __restrict__ S, int n_pad, bool emit,
-                                             float* dump_row, int n_nodes, uint16_t* out_node, float* out_score,
-                                             double* out_lwr, int lane) {
+// `emit` = false only resets (bad read).  The list is returned in (top_s, top_x) of lanes 0..cnt-1.
+struct TopList {
+  float s;   // lane i: score of the i-th best (valid for i < cnt)
+  int x;     // lane i: its node
+  int cnt;   // warp-uniform
+};
+__device__ __forceinline__ void top_insert(TopList& t, float cs, int cx, int K, int lane) {
+  if (t.cnt >= K) {
+    const float tau_s = __shfl_sync(0xffffffffu, t.s, K - 1);
+    const int tau_x = __shfl_sync(0xffffffffu, t.x, K - 1);
+    if (!better(cs, cx, tau_s, tau_x)) return;
+  }
+  // insertion position = number of kept entries that beat the candidate
+  const uint32_t ahead = __ballot_sync(0xffffffffu, lane < t.cnt && better(t.s, t.x, cs, cx));
+  const int pos = __popc(ahead);
+  const float up_s = __shfl_up_sync(0xffffffffu, t.s, 1);
+  const int up_x = __shfl_up_sync(0xffffffffu, t.x, 1);
+  if (lane > pos) { t.s = up_s; t.x = up_x; }
+  if (lane == pos) { t.s = cs; t.x = cx; }
+  if (t.cnt < K) t.cnt++;
+}
+__device__ __forceinline__ TopList select_scan(const CfgView& cfg, float* __restrict__ S, int lo, int hi, bool emit,
+                                               float* dump_row, int n_nodes, int lane) {
   const int K = cfg.K;
+  TopList t;
+  t.s = -INFINITY; t.x = 0xFFFF; t.cnt = 0;
   const float4 sent4 = make_float4(__uint_as_float(kSentinelBits), __uint_as_float(kSentinelBits),
                                    __uint_as_float(kSentinelBits), __uint_as_float(kSentinelBits));
   if (!emit) {
-    for (int i = lane * 4; i < n_pad; i += 128) *reinterpret_cast<float4*>(S + i) = sent4;
+    for (int i = lo + lane * 4; i < hi; i += 128) *reinterpret_cast<float4*>(S + i) = sent4;
     __syncwarp();
-    return 0;
+    return t;
   }
   float m = -INFINITY;  // fmaxf ignores the NaN sentinel
-  for (int i = lane * 4; i < n_pad; i += 128) {
+  for (int i = lo + lane * 4; i < hi; i += 128) {
     const float4 q = *reinterpret_cast<const float4*>(S + i);
     m = fmaxf(m, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
   }
   float tau = -INFINITY;
   {
-    uint32_t t = ordered_u32(m);
+    uint32_t u = ordered_u32(m);
     const uint32_t floor_u = ordered_u32(-INFINITY);
     for (int j = 0; j < K; j++) {
-      const uint32_t mx = __reduce_max_sync(0xffffffffu, t);
+      const uint32_t mx = __reduce_max_sync(0xffffffffu, u);
       if (mx == floor_u) { tau = -INFINITY; break; }
       tau = __uint_as_float((mx & 0x80000000u) ? (mx & 0x7FFFFFFFu) : ~mx);
-      const uint32_t holders = __ballot_sync(0xffffffffu, t == mx);
-      if (lane == __ffs(holders) - 1) t = floor_u;
+      const uint32_t holders = __ballot_sync(0xffffffffu, u == mx);
+      if (lane == __ffs(holders) - 1) u = floor_u;
     }
   }
-  float top_s = -INFINITY;  // lane i holds the i-th best so far (valid for i < cnt)
-  int top_x = 0xFFFF;
-  int cnt = 0;
-  for (int i0 = 0; i0 < n_pad; i0 += 128) {
+  for (int i0 = lo; i0 < hi; i0 += 128) {
     const int i = i0 + lane * 4;
     const float4 q = *reinterpret_cast<const float4*>(S + i);
     *reinterpret_cast<float4*>(S + i) = sent4;
@@ -314,32 +334,26 @@ __device__ __forceinline__ int select_and_reset(const CfgView& cfg, float* __res
     if (!__any_sync(0xffffffffu, c0 | c1 | c2 | c3)) continue;
 #pragma unroll
     for (int c = 0; c < 4; c++) {
-      const float s = c == 0 ? q.x : c == 1 ? q.y : c == 2 ? q.z : q.w;
+      const float sc = c == 0 ? q.x : c == 1 ? q.y : c == 2 ? q.z : q.w;
       const bool cand = c == 0 ? c0 : c == 1 ? c1 : c == 2 ? c2 : c3;
       uint32_t pm = __ballot_sync(0xffffffffu, cand);
       while (pm) {
         const int src = __ffs(pm) - 1;
         pm &= pm - 1;
-        const float cs = __shfl_sync(0xffffffffu, s, src);
-        const int cx = i0 + src * 4 + c;
-        if (cnt >= K) {
-          const float tau_s = __shfl_sync(0xffffffffu, top_s, K - 1);
-          const int tau_x = __shfl_sync(0xffffffffu, top_x, K - 1);
-          if (!better(cs, cx, tau_s, tau_x)) continue;
-        }
-        // insertion position = number of kept entries that beat the candidate
-        const uint32_t ahead = __ballot_sync(0xffffffffu, lane < cnt && better(top_s, top_x, cs, cx));
-        const int pos = __popc(ahead);
-        const float up_s = __shfl_up_sync(0xffffffffu, top_s, 1);
-        const int up_x = __shfl_up_sync(0xffffffffu, top_x, 1);
-        if (lane > pos) { top_s = up_s; top_x = up_x; }
-        if (lane == pos) { top_s = cs; top_x = cx; }
-        if (cnt < K) cnt++;
+        top_insert(t, __shfl_sync(0xffffffffu, sc, src), i0 + src * 4 + c, K, lane);
       }
     }
   }
   __syncwarp();
-  const int nb = cnt;  // numberOfBestScoreToConsiderForOutput = min(keepAtMost, |L|)  (:828-832)
+  return t;
+}
+// LWR of the kept nodes and the rows of the read.  Returns rows written, or -1 if no node was touched.
+__device__ __forceinline__ int finalize_rows(const CfgView& cfg, const TopList& t, uint16_t* out_node, float* out_score,
+                                             double* out_lwr, int lane) {
+  const int K = cfg.K;
+  const float top_s = t.s;
+  const int top_x = t.x;
+  const int nb = t.cnt;  // numberOfBestScoreToConsiderForOutput = min(keepAtMost, |L|)  (:828-832)
   if (nb == 0) return -1;
   const float best = __shfl_sync(0xffffffffu, top_s, 0);
   const float lowest = __shfl_sync(0xffffffffu, top_s, nb - 1);
@@ -397,24 +411,24 @@ static_assert(sizeof(StageHdr) == 64, "StageHdr is one 64 B slot");
 constexpr int kStageMetaBytes = 64 + 128 + 256;
 static_assert((kStages * kStageMetaBytes) % 64 == 0, "stages start 16 B aligned");
 
-// S[x] += v - T for the lanes below m, with the first-touch rule (PlacementProcess.java:726-733), split into
-// the shared-memory load and the dependent tail so that independent work can be scheduled in between.
-// Predicated, no branch; idle lanes do not touch shared memory.  `a` = shared address of S[x].
-__device__ __forceinline__ float rmw_load(uint32_t a, uint32_t lane, uint32_t m) {
+// S[x] += v - T for the lanes whose predicate is set, with the first-touch rule (PlacementProcess.java:726-733),
+// split into the shared-memory load and the dependent tail so that independent work can be scheduled in
+// between.  Predicated, no branch; idle lanes do not touch shared memory.  `a` = shared address of S[x].
+__device__ __forceinline__ float rmw_load(uint32_t a, uint32_t pred) {
   float s;
-  asm volatile("{\n.reg .pred p;\nsetp.lt.u32 p, %2, %3;\n@p ld.shared.f32 %0, [%1];\n}" : "=f"(s) : "r"(a), "r"(lane), "r"(m) : "memory");
+  asm volatile("{\n.reg .pred p;\nsetp.ne.u32 p, %2, 0;\n@p ld.shared.f32 %0, [%1];\n}" : "=f"(s) : "r"(a), "r"(pred) : "memory");
   return s;
 }
-__device__ __forceinline__ void rmw_store(uint32_t a, float s, float d, float QT0, uint32_t lane, uint32_t m) {
+__device__ __forceinline__ void rmw_store(uint32_t a, float s, float d, float QT0, uint32_t pred) {
   asm volatile(
       "{\n.reg .pred p, q;\n.reg .f32 t;\n.reg .b32 sb;\n"
       "mov.b32 sb, %1;\n"
       "setp.eq.u32 q, sb, 0x7FFFFFFF;\n"  // C[x]==0 : L.add(x); S[x]+=Q*T
       "selp.f32 t, %3, %1, q;\n"
       "add.rn.f32 t, t, %2;\n"           // S[x]+= v - T
-      "setp.lt.u32 p, %4, %5;\n"
+      "setp.ne.u32 p, %4, 0;\n"
       "@p st.shared.f32 [%0], t;\n}"
-      ::"r"(a), "f"(s), "f"(d), "f"(QT0), "r"(lane), "r"(m)
+      ::"r"(a), "f"(s), "f"(d), "f"(QT0), "r"(pred)
       : "memory");
 }
 
@@ -423,22 +437,24 @@ __device__ __forceinline__ void rmw_store(uint32_t a, float s, float d, float QT
 // step earlier still, so no instruction of a step waits on a load issued in the same step: the loads of
 // chunk j+4 and the descriptor of chunk j+5 are issued between the S[x] load of chunk j and its
 // dependent tail.  The list is padded with idle descriptors (m = 0) for the rounds of four + look-ahead.
+// SLICED: this warp is one of several consumers of the read and owns the nodes [lo, lo+width) only.
 #define RP_CHUNK_STEP(M_, V_, X_, OFF_)                                                                \
   {                                                                                                    \
-    const uint32_t a_ = s_base + 4 * X_, m_ = M_;                                                      \
-    const float s_ = rmw_load(a_, lane, m_);                                                           \
+    const uint32_t a_ = s_base + 4 * X_;                                                               \
+    const uint32_t p_ = SLICED ? (uint32_t)(lane < M_ && X_ - lo < width) : (uint32_t)(lane < M_);     \
+    const float s_ = rmw_load(a_, p_);                                                                 \
     const float d_ = __fsub_rn(V_, T);                                                                 \
     M_ = dn.y;                                                                                         \
     V_ = lds_f32(dn.x + lane4);                                                                        \
     X_ = lds_u16(dn.x + 4 * dn.y + lane2);                                                             \
     dn = lds_u64(dp + OFF_);                                                                           \
-    rmw_store(a_, s_, d_, QT0, lane, m_);                                                              \
+    rmw_store(a_, s_, d_, QT0, p_);                                                                    \
   }
-__device__ __forceinline__ void accumulate_chunks(float* __restrict__ S, uint32_t dl, int n_chunks, int n_pad, float QT0,
-                                                  float T, int lane) {
+template <bool SLICED>
+__device__ __forceinline__ void accumulate_chunks(float* __restrict__ S, uint32_t dl, int n_chunks, float QT0, float T,
+                                                  int lane, uint32_t lo, uint32_t width) {
   const uint32_t lane4 = lane * 4, lane2 = lane * 2;
   const uint32_t s_base = smem_u32(S);
-  (void)n_pad;
   const uint2 d0 = lds_u64(dl), d1 = lds_u64(dl + 8), d2 = lds_u64(dl + 16), d3 = lds_u64(dl + 24);
   uint2 dn = lds_u64(dl + 32);
   float v0 = lds_f32(d0.x + lane4), v1 = lds_f32(d1.x + lane4), v2 = lds_f32(d2.x + lane4), v3 = lds_f32(d3.x + lane4);
@@ -459,12 +475,13 @@ __device__ __forceinline__ void accumulate_chunks(float* __restrict__ S, uint32_
 #undef RP_CHUNK_STEP
 
 // Same for one posting block, staged (p = shared address) -- slow path of a group with special windows
-__device__ __forceinline__ void accumulate_staged(float* __restrict__ S, uint32_t p, int len, float QT0, float T, int lane) {
+__device__ __forceinline__ void accumulate_staged(float* __restrict__ S, uint32_t p, int len, float QT0, float T, int lane,
+                                                  uint32_t lo, uint32_t width) {
   for (int base = 0; base < len; base += kSubBlock, p += kSubBlockBytes) {
     const int m = min(kSubBlock, len - base);
-    if (lane < m) {
+    const unsigned x = lane < m ? lds_u16(p + 4 * m + 2 * lane) : 0xFFFFFFFFu;
+    if (x - lo < width) {  // this consumer's nodes only
       const float v = lds_f32(p + 4 * lane);
-      const unsigned x = lds_u16(p + 4 * m + 2 * lane);
       float s = S[x];
       if (is_sentinel(s)) s = QT0;
       S[x] = __fadd_rn(s, __fsub_rn(v, T));
@@ -737,11 +754,24 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
   }
 }
 
-// ---- K3 + K4: the consumer warp ------------------------------------------------------------------
+// ---- K3 + K4: the consumer warps ------------------------------------------------------------------
+// C consumers share one read: consumer c owns the nodes [lo, lo+width) of S -- it adds only the postings
+// of its nodes (every consumer walks every chunk, in window order, so the per-node order is kept), selects
+// the top-K of its slice, and consumer 0 merges the C lists and writes the rows.  C = 1 for small trees
+// (the pair of DESIGN.md); big trees, whose S[] leaves room for only a few reads per SM, get more warps
+// per read this way.  Candidate hand-over: cand[c][K] in shared memory, guarded by two mbarriers.
+template <int C>
 __device__ __forceinline__ void consumer(const AlphabetTables& c_alpha, const DbView& db, const CfgView& cfg,
-                                         const BatchView& bt, const PairSmem& w, float* Sa, int* Ca, int n_pad, int lane) {
+                                         const BatchView& bt, const PairSmem& w, float* Sa, int* Ca, int n_pad, int lane,
+                                         int c, uint32_t cand) {
   const int K = cfg.K;
   float* S = w.S;
+  // slice of this consumer, in multiples of 128 nodes (the selection works on float4 x 32 lanes)
+  const int per = ((n_pad / 128 + C - 1) / C) * 128;
+  const int lo_i = min(c * per, n_pad), hi_i = min(lo_i + per, n_pad);
+  const uint32_t lo = C > 1 ? (uint32_t)lo_i : 0u, width = C > 1 ? (uint32_t)(hi_i - lo_i) : 0xFFFFFFFFu;
+  const uint32_t cand_full = w.bar + 8 * (2 * kStages), cand_free = w.bar + 8 * (2 * kStages + 1);
+  uint32_t n_done = 0;  // reads finished (phase of the candidate hand-over)
   for (uint32_t batch = 0;; batch++) {
     const int slot = batch % kStages;
     const uint32_t use = batch / kStages;
@@ -752,7 +782,7 @@ __device__ __forceinline__ void consumer(const AlphabetTables& c_alpha, const Db
     const bool bad = g.flags & kGrpBad;
     if (!bad && !(g.ambm | (g.hitm & ~g.stagedm))) {
       // common case: every matched window of the group is staged
-      if (g.n_chunks) accumulate_chunks(S, w.desc + slot * w.max_chunks * 8, g.n_chunks, n_pad, QT0, db.T, lane);
+      if (g.n_chunks) accumulate_chunks<(C > 1)>(S, w.desc + slot * w.max_chunks * 8, g.n_chunks, QT0, db.T, lane, lo, width);
     } else if (!bad) {
       const uint32_t* pk_arr = reinterpret_cast<const uint32_t*>(w.meta + slot * kStageMetaBytes + 64);
       const uint64_t* meta_arr = reinterpret_cast<const uint64_t*>(w.meta + slot * kStageMetaBytes + 192);
@@ -764,20 +794,50 @@ __device__ __forceinline__ void consumer(const AlphabetTables& c_alpha, const Db
         if ((g.hitm >> l) & 1u) {
           const uint32_t pk = pk_arr[l];
           if ((g.stagedm >> l) & 1u) {
-            accumulate_staged(S, stage + (pk >> 16), (int)(pk & 0xFFFF), QT0, db.T, lane);
+            accumulate_staged(S, stage + (pk >> 16), (int)(pk & 0xFFFF), QT0, db.T, lane, lo, width);
           } else {
-            accumulate_global(S, block_ptr(db, meta_arr[l]), (int)(pk & 0xFFFF), QT0, db.T, lane);
+            accumulate_global(S, block_ptr(db, meta_arr[l]), (int)(pk & 0xFFFF), QT0, db.T, lane, lo, width);
           }
         } else {
-          ambiguous_window(c_alpha, db, cfg, S, g.seq + l, g.QT, Sa, Ca, lane);
+          ambiguous_window(c_alpha, db, cfg, S, g.seq + l, g.QT, Sa, Ca, lane, lo, width);
         }
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(w.bar + 8 * (kStages + slot));  // the stage may be refilled
+    if (lane == 0) mbar_arrive(w.bar + 8 * (kStages + slot));  // the stage may be refilled (all C consumers arrive)
     if (!(g.flags & kGrpLast)) continue;
     // ---- selection / outputs
     const long long r = g.r;
+    const bool no_select = (g.flags & kGrpTooLong) || (g.Q < 0 && !bad);  // nothing was accumulated
+    TopList t;
+    t.s = -INFINITY; t.x = 0xFFFF; t.cnt = 0;
+    if (!no_select) {  // a bad read only resets S
+      float* dump_row = (bt.dump_scores && !bad) ? bt.dump_scores + r * (size_t)db.n_nodes : nullptr;
+      t = select_scan(cfg, S, C > 1 ? lo_i : 0, C > 1 ? hi_i : n_pad, !bad, dump_row, db.n_nodes, lane);
+    }
+    if (C > 1) {
+      if (c > 0) {
+        // hand the slice's list to consumer 0 (once it has finished with the previous read's lists)
+        if (n_done) mbar_wait(cand_free, (n_done - 1) & 1u);
+        if (lane < K) sts_u64(cand + 8 * (c * 32 + lane), make_uint2(__float_as_uint(t.s), (uint32_t)t.x));
+        if (lane == 0) sts_u32(cand + 8 * 32 * C + 4 * c, (uint32_t)t.cnt);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(cand_full);
+        n_done++;
+        continue;
+      }
+      mbar_wait(cand_full, n_done & 1u);
+      for (int cc = 1; cc < C; cc++) {
+        const uint32_t cnt_c = lds_u32(cand + 8 * 32 * C + 4 * cc);
+        for (uint32_t i = 0; i < cnt_c; i++) {
+          const uint2 e = lds_u64(cand + 8 * (cc * 32 + i));
+          top_insert(t, __uint_as_float(e.x), (int)e.y, K, lane);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(cand_free);
+      n_done++;
+    }
     uint16_t* o_node = bt.node + r * K;
     float* o_score = bt.score + r * K;
     double* o_lwr = bt.lwr + r * K;
@@ -786,9 +846,8 @@ __device__ __forceinline__ void consumer(const AlphabetTables& c_alpha, const Db
       status = RP_STATUS_TOO_LONG;
     } else if (g.Q < 0 && !bad) {
       status = RP_STATUS_TOO_SHORT;
-    } else {  // one call site: a bad read only resets S
-      float* dump_row = (bt.dump_scores && !bad) ? bt.dump_scores + r * (size_t)db.n_nodes : nullptr;
-      rows = select_and_reset(cfg, S, n_pad, !bad, dump_row, db.n_nodes, o_node, o_score, o_lwr, lane);
+    } else {
+      rows = bad ? 0 : finalize_rows(cfg, t, o_node, o_score, o_lwr, lane);
       status = bad ? RP_STATUS_BAD_CHAR : rows < 0 ? RP_STATUS_UNPLACED : RP_STATUS_PLACED;  // L empty -> not placed (:797-806)
     }
     if (rows <= 0 && status != RP_STATUS_PLACED) {
@@ -800,15 +859,18 @@ __device__ __forceinline__ void consumer(const AlphabetTables& c_alpha, const Db
       bt.status[r] = status;
       if (bt.counts) {
         const bool ok = status <= RP_STATUS_UNPLACED;
-        int4 c = make_int4(ok ? (g.Q > 0 ? g.Q : 0) : 0, ok ? g.n_match : 0, ok ? g.n_amb : 0, ok ? g.n_skip : 0);
-        *reinterpret_cast<int4*>(bt.counts + 4 * r) = c;
+        int4 cn = make_int4(ok ? (g.Q > 0 ? g.Q : 0) : 0, ok ? g.n_match : 0, ok ? g.n_amb : 0, ok ? g.n_skip : 0);
+        *reinterpret_cast<int4*>(bt.counts + 4 * r) = cn;
       }
     }
   }
 }
 
 // --------------------------------------------------------------------------------- main kernel
-__global__ void __launch_bounds__(kMaxPairsPerCta * 64, 1)
+// Warps 0..teams-1 are the producers, then C consumers per team; blockDim = teams * (1 + C) * 32.
+constexpr int kMaxThreads = kMaxPairsPerCta * 64;
+template <int C>
+__global__ void __launch_bounds__(kMaxThreads, 1)
 place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_constant__ DbView db,
              const __grid_constant__ CfgView cfg, const __grid_constant__ BatchView bt,
              unsigned long long* work_counter, float* amb_S, int* amb_C, int n_pad, int per_pair_bytes,
@@ -816,12 +878,14 @@ place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_consta
   extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int pairs = blockDim.x >> 6;
-  const bool is_producer = warp < pairs;
-  const int pair = is_producer ? warp : warp - pairs;
+  const int teams = (blockDim.x >> 5) / (1 + C);
+  const bool is_producer = warp < teams;
+  const int pair = is_producer ? warp : (warp - teams) / C;
+  const int cidx = is_producer ? 0 : (warp - teams) % C;
   // CTA-wide: character class table
   for (int i = threadIdx.x; i < 256; i += blockDim.x) smem[i] = c_alpha.cls[i];
   PairSmem w;
+  uint32_t cand;
   {
     uint8_t* base = smem + 256 + (size_t)pair * per_pair_bytes;
     w.bar = smem_u32(base);
@@ -832,13 +896,21 @@ place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_consta
     w.desc = smem_u32(p);
     p += (size_t)kStages * max_chunks * 8;
     w.S = reinterpret_cast<float*>(p);
+    p += 4 * (size_t)(n_pad + 32);
+    cand = smem_u32(p);  // C > 1: cand[C][32] x 8 B
     w.stage_bytes = stage_bytes;
     w.max_chunks = max_chunks;
   }
-  if (!is_producer) {
+  if (!is_producer && cidx == 0) {
     for (int i = lane; i < n_pad + 32; i += 32) w.S[i] = __uint_as_float(kSentinelBits);
-    if (lane == 0)
-      for (int i = 0; i < 2 * kStages; i++) mbar_init(w.bar + 8 * i, 1);
+    if (lane == 0) {
+      for (int i = 0; i < kStages; i++) {
+        mbar_init(w.bar + 8 * i, 1);                // full: the producer's arrival (+ the staged bytes)
+        mbar_init(w.bar + 8 * (kStages + i), C);    // empty: every consumer of the team
+      }
+      mbar_init(w.bar + 8 * (2 * kStages), C > 1 ? C - 1 : 1);  // cand_full
+      mbar_init(w.bar + 8 * (2 * kStages + 1), 1);              // cand_free
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -849,8 +921,8 @@ place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_consta
   if (is_producer) {
     producer(c_alpha, db, cfg, bt, work_counter, w, smem_u32(smem), lane);
   } else {
-    const size_t gp = (size_t)blockIdx.x * pairs + pair;
-    consumer(c_alpha, db, cfg, bt, w, amb_S + gp * n_pad, amb_C + gp * n_pad, n_pad, lane);
+    const size_t gp = (size_t)blockIdx.x * teams + pair;
+    consumer<C>(c_alpha, db, cfg, bt, w, amb_S + gp * n_pad, amb_C + gp * n_pad, n_pad, lane, cidx, cand);
   }
 }
 
@@ -926,9 +998,24 @@ __global__ void fill_f32_kernel(float* p, size_t n, float v) {
 }
 
 // ------------------------------------------------------------------------------ host plumbing
-// Shared memory per producer/consumer pair = S[n_pad + 32] + kStages posting stages (+ descriptor lists,
-// stage headers, mbarriers); pairs per CTA x CTAs per SM maximise the resident pairs under the 227 KB
-// budget.  A stage holds about a group's worth of posting blocks; RP_STAGE_BYTES overrides it for tuning.
+// Shared memory per team (one producer + C consumers sharing one read) = S[n_pad + 32] + kStages posting
+// stages (+ descriptor lists, stage headers, mbarriers, candidate lists); teams per CTA x CTAs per SM
+// maximise the resident teams under the 227 KB budget and 768 threads.  A stage holds about a group's
+// worth of posting blocks; RP_STAGE_BYTES / RP_CONSUMERS override for tuning.
+template <int C>
+static int geometry_for(const rp_db* db, DeviceCtx* dc, LaunchGeom& g) {
+  auto kern = place_kernel<C>;
+  RP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+  // what the hardware really keeps resident (registers may bind before shared memory does)
+  int resident = 0;
+  RP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, g.warps_per_cta * 32, g.smem_bytes));
+  if (resident < 1) return set_error(RP_E_CUDA, "placement kernel does not fit on an SM (smem %zu B)", g.smem_bytes);
+  g.ctas_per_sm = resident;
+  g.grid = dc->sm_count * g.ctas_per_sm;
+  (void)db;
+  return RP_OK;
+}
+
 int compute_geometry(const rp_db* db, DeviceCtx* dc) {
   LaunchGeom g;
   g.n_pad = (db->desc.n_nodes + 127) & ~127;
@@ -940,45 +1027,50 @@ int compute_geometry(const rp_db* db, DeviceCtx* dc) {
   if (const char* e = getenv("RP_STAGE_BYTES")) stage = atol(e);
   stage = std::max(1024L, std::min(stage, 32768L - 128));
   stage = (stage + 127) & ~127L;
-  auto pair_bytes = [&](long st) {
+  auto team_bytes = [&](long st, int C) {
     const size_t chunks = (32 + st / kSubBlockBytes + 9 + 1) & ~(size_t)1;  // per window + per extra sub-block + 8 idle
     return (64 + kStages * (size_t)kStageMetaBytes + kStages * 8 * chunks + 4 * (size_t)(g.n_pad + 32) +
-            kStages * (size_t)st + 127) & ~(size_t)127;
+            kStages * (size_t)st + (C > 1 ? (size_t)C * 264 : 0) + 127) & ~(size_t)127;
   };
   // big trees: give the stages up before giving the accumulator up
-  while (stage > 1024 && cta_fixed + 2 * pair_bytes(stage) > optin) stage = std::max(1024L, (stage / 2 + 127) & ~127L);
+  while (stage > 1024 && cta_fixed + 2 * team_bytes(stage, 1) > optin) stage = std::max(1024L, (stage / 2 + 127) & ~127L);
+  // consumers per team: 1.  2 or 4 warps sharing a read's S[] (RP_CONSUMERS) are correct but not faster,
+  // even on big trees: every consumer still walks every chunk, so the instruction count per read grows
+  // with C while only the selection is split (cfg3, N = 9 999: 39.7 / 37.3 / 41.6 ms for C = 1 / 2 / 4,
+  // profiles/r01_v6_team_consumers.txt).  Kept as a knob for the slice-routed lists of the next round.
+  int C = 1;
+  if (const char* e = getenv("RP_CONSUMERS")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) C = v; }
+  g.consumers = C;
   g.stage_bytes = (int)stage;
   g.max_chunks = (32 + g.stage_bytes / kSubBlockBytes + 9 + 1) & ~1;  // even: S stays 16 B aligned behind the lists
-  g.per_warp_bytes = pair_bytes(stage);
+  g.per_warp_bytes = team_bytes(stage, C);
   if (cta_fixed + g.per_warp_bytes > optin)
     return set_error(RP_E_UNSUPPORTED,
                      "n_nodes=%d needs %zu B of shared memory per read (> %zu B per CTA); trees beyond ~54k nodes "
                      "are not supported by the shared-memory accumulator",
                      db->desc.n_nodes, g.per_warp_bytes, optin);
-  int max_pairs_sm = 16;
-  if (const char* e = getenv("RP_PAIRS_PER_SM")) max_pairs_sm = std::max(1, std::min(16, atoi(e)));
-  int best_total = 0;
+  const int max_teams_cta = kMaxThreads / (32 * (1 + C));
+  int max_teams_sm = 16;
+  if (const char* e = getenv("RP_PAIRS_PER_SM")) max_teams_sm = std::max(1, std::min(16, atoi(e)));
+  int best_total = 0, teams_cta = 1;
   for (int c = 1; c <= 8; c++) {
     const size_t budget = std::min(optin, sm_total / c - 1024);
     if (budget < cta_fixed + g.per_warp_bytes) break;
-    int ppc = (int)std::min<size_t>(kMaxPairsPerCta, (budget - cta_fixed) / g.per_warp_bytes);
-    if (c * ppc > max_pairs_sm) ppc = max_pairs_sm / c;
-    if (ppc < 1) break;
-    if (c * ppc > best_total) {
-      best_total = c * ppc;
+    int tpc = (int)std::min<size_t>(max_teams_cta, (budget - cta_fixed) / g.per_warp_bytes);
+    if (c * tpc > max_teams_sm) tpc = max_teams_sm / c;
+    if (c * tpc * (1 + C) * 32 > 2048 / 1) tpc = 2048 / (32 * (1 + C) * c);
+    if (tpc < 1) break;
+    if (c * tpc > best_total) {
+      best_total = c * tpc;
       g.ctas_per_sm = c;
-      g.warps_per_cta = 2 * ppc;
+      teams_cta = tpc;
     }
   }
-  g.smem_bytes = cta_fixed + (g.warps_per_cta / 2) * g.per_warp_bytes;
+  g.warps_per_cta = teams_cta * (1 + C);
+  g.smem_bytes = cta_fixed + teams_cta * g.per_warp_bytes;
   RP_CUDA_TRY(cudaSetDevice(dc->device));
-  RP_CUDA_TRY(cudaFuncSetAttribute(place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-  // what the hardware really keeps resident (registers may bind before shared memory does)
-  int resident = 0;
-  RP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, place_kernel, g.warps_per_cta * 32, g.smem_bytes));
-  if (resident < 1) return set_error(RP_E_CUDA, "placement kernel does not fit on an SM (smem %zu B)", g.smem_bytes);
-  g.ctas_per_sm = resident;
-  g.grid = dc->sm_count * g.ctas_per_sm;
+  int rc = C == 1 ? geometry_for<1>(db, dc, g) : C == 2 ? geometry_for<2>(db, dc, g) : geometry_for<4>(db, dc, g);
+  if (rc) return rc;
   dc->geom = g;
   return RP_OK;
 }
@@ -990,7 +1082,7 @@ int ensure_stream_ctx(const rp_db* db, DeviceCtx* dc, StreamCtx* sc) {
   if (!sc->stream) RP_CUDA_TRY(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
   RP_CUDA_TRY(cudaEventCreate(&sc->ev_k0));
   RP_CUDA_TRY(cudaEventCreate(&sc->ev_k1));
-  const size_t n = (size_t)dc->geom.grid * (dc->geom.warps_per_cta / 2) * dc->geom.n_pad;
+  const size_t n = (size_t)dc->geom.grid * (dc->geom.warps_per_cta / (1 + dc->geom.consumers)) * dc->geom.n_pad;
   RP_CUDA_TRY(cudaMalloc((void**)&sc->d_amb_S, n * sizeof(float)));
   RP_CUDA_TRY(cudaMalloc((void**)&sc->d_amb_C, n * sizeof(int)));
   RP_CUDA_TRY(cudaMemset(sc->d_amb_S, 0, n * sizeof(float)));
@@ -1019,7 +1111,8 @@ static int launch_place(const rp_db* db, DeviceCtx* dc, StreamCtx* sc, const rp_
   const LaunchGeom& g = dc->geom;
   RP_CUDA_TRY(cudaMemsetAsync(sc->d_counter, 0, sizeof(unsigned long long), stream));
   if (time_it) RP_CUDA_TRY(cudaEventRecord(sc->ev_k0, stream));
-  place_kernel<<<g.grid, g.warps_per_cta * 32, g.smem_bytes, stream>>>(
+  auto kern = g.consumers == 1 ? place_kernel<1> : g.consumers == 2 ? place_kernel<2> : place_kernel<4>;
+  kern<<<g.grid, g.warps_per_cta * 32, g.smem_bytes, stream>>>(
       db->alpha, make_db_view(db, dc), make_cfg_view(cfg), bt, sc->d_counter, sc->d_amb_S, sc->d_amb_C, g.n_pad,
       (int)g.per_warp_bytes, g.stage_bytes, g.max_chunks);
   RP_CUDA_TRY(cudaGetLastError());

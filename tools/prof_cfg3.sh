@@ -1,0 +1,4 @@
+set -e
+python bench.py --config 3 --reads 1000000 --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/plain3.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:place_kernel -s 3 -c 1 -f -o gpurun_out/prof_cfg3 python bench.py --config 3 --reads 1000000 --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_cfg3.log 2>&1
+tail -2 gpurun_out/ncu_cfg3.log
