@@ -282,3 +282,21 @@ def test_fasta_to_jplace_through_the_gpu(tmp_path):
     for pg, po in zip(dg["placements"], do["placements"]):
         assert pg["nm"] == po["nm"] and len(pg["p"]) == len(po["p"])
         assert [r[1] for r in pg["p"]] == [r[1] for r in po["p"]]  # likelihood column, bit-identical floats
+
+
+def test_very_large_tree_and_the_limit():
+    """S[] of one read nearly fills an SM's shared memory (40 000 nodes = 160 KB): one pair per SM, minimal
+    stages; beyond ~54 k nodes the shared-memory accumulator does not fit and the load says so."""
+    import rappas_b200 as R
+    from rappas_b200._lib import RappasError
+    db = synth.make_db(0, 8, 40000, n_keys=20000, mean_postings=60, seed=3)
+    rb = synth.make_reads(db, 300, (30, 400), seed=4, n_rate=0.003)
+    g, o = both(db)
+    oo = o.place(rb)
+    parity.assert_placements_equal(g.place(rb), oo, 7, amb_reads(oo))
+    So, _ = o.node_scores(rb, hitcount=False)
+    parity.assert_scores_equal(g.node_scores(rb), So, amb_reads(oo))
+    big = synth.make_db(0, 8, 65535, n_keys=2000, mean_postings=4, seed=5)
+    with pytest.raises(RappasError) as e:
+        R.Database.from_synth(big)
+    assert e.value.code == 5 and "shared memory" in str(e.value)
