@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ambiguity", action="store_true", help="experiment: generate the reads without IUPAC / N characters")
     ap.add_argument("--partitioned", action="store_true",
                     help="hash-partition the DB over the ranks (peer memory over NVLink) instead of replicating it")
     return ap.parse_args()
@@ -202,8 +203,10 @@ def main():
 
     # ---- workload: DB replicated per GPU, reads sharded (each rank draws its own shard) -------------
     w = synth.workload(args.config)
+    if args.no_ambiguity:
+        w.iupac_rate = w.n_rate = 0.0
     n_reads = args.reads or w.n_reads
-    db = synth.make_db(w.alphabet, w.k, w.n_nodes, w.n_keys, w.mean_postings, seed=42 + w.index)
+    db = synth.make_db(w.alphabet, w.k, w.n_nodes, w.n_keys, w.mean_postings, seed=42 + w.index, key_mode=w.key_mode)
     rb = synth.make_reads(db, n_reads, w.read_len, seed=1042 + w.index + 7919 * rank, iupac_rate=w.iupac_rate,
                           n_rate=w.n_rate)
     if args.partitioned and world > 1:

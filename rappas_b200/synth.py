@@ -222,6 +222,7 @@ class Workload:
     read_len: object
     iupac_rate: float = 0.0
     n_rate: float = 0.0
+    key_mode: str | None = None  # None = make_db's default for the alphabet
 
     @property
     def n_nodes(self):
@@ -241,8 +242,10 @@ def workload(index: int, scale: float = 1.0) -> Workload:
     elif index == 5:
         # stress shape, host-materialisable stand-in: k=15 keys drawn sparsely; the >1-GPU DB of
         # SURVEY 8d is generated per partition on device, not here
+        # keys = the k-mers of a random 8 Mbp "genome" and reads = mutated substrings of it: with uniform
+        # random reads a k=15 DB of 8 M keys (0.7 % of the key space) would hardly ever be hit
         w = Workload("cfg5_stress_k15_var_len", 5, ALPHA_NUCL, 15, 5000, 8_000_000, 48, 1_000_000, (50, 1500),
-                     iupac_rate=0.005, n_rate=0.002)
+                     iupac_rate=0.005, n_rate=0.002, key_mode="genome")
     else:
         raise ValueError(index)
     if scale != 1.0:
@@ -252,7 +255,7 @@ def workload(index: int, scale: float = 1.0) -> Workload:
 
 
 def build(w: Workload, reads: bool = True, n_reads: int | None = None):
-    db = make_db(w.alphabet, w.k, w.n_nodes, w.n_keys, w.mean_postings, seed=42 + w.index)
+    db = make_db(w.alphabet, w.k, w.n_nodes, w.n_keys, w.mean_postings, seed=42 + w.index, key_mode=w.key_mode)
     if not reads:
         return db, None
     rb = make_reads(db, n_reads if n_reads is not None else w.n_reads, w.read_len, seed=1042 + w.index,

@@ -3,5 +3,5 @@ python - <<'PY'
 from rappas_b200 import build as b
 b.build(force=True, extra=["-DRP_STAGES=3"])
 PY
-SWEEP="2816 3328 4224" bash tools/sweep_stage.sh
+SWEEP="${SWEEP3:-3072 3584 4096}" bash tools/sweep_stage.sh
 python -m rappas_b200.build --force > /dev/null
