@@ -1022,7 +1022,7 @@ int compute_geometry(const rp_db* db, DeviceCtx* dc) {
   const size_t optin = dc->smem_optin;         // 227 KB on sm_100
   const size_t sm_total = optin + 1024;        // 228 KB per SM, 1 KB reserved per resident CTA
   const double mean_block = db->desc.n_keys ? (double)db->block_bytes / (double)db->desc.n_keys : 32.0;
-  long stage = (long)(32.0 * mean_block * 0.88);  // tools/sweep_stage.sh: flat optimum 0.8-0.95
+  long stage = (long)(32.0 * mean_block * 0.81);  // tools/sweep_stage.sh: flat optimum 0.8-0.9
   if (const char* e = getenv("RP_STAGE_BYTES")) stage = atol(e);
   stage = std::max(1024L, std::min(stage, 32768L - 128));
   stage = (stage + 127) & ~127L;
