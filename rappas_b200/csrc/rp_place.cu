@@ -91,7 +91,10 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) break;
-    __nanosleep(400);
+#ifndef RP_POLL_NS
+#define RP_POLL_NS 400
+#endif
+    if (RP_POLL_NS) __nanosleep(RP_POLL_NS);
   }
 }
 // global -> shared bulk copy (TMA, SASS UBLKCP); dst/src 16 B aligned, bytes % 16 == 0
