@@ -1036,6 +1036,12 @@ int compute_geometry(const rp_db* db, DeviceCtx* dc) {
   };
   // big trees: give the stages up before giving the accumulator up
   while (stage > 1024 && cta_fixed + 2 * team_bytes(stage, 1) > optin) stage = std::max(1024L, (stage / 2 + 127) & ~127L);
+  // a slightly smaller stage that lets one more team fit is the better trade (cfg2: 4992 B -> 11 pairs)
+  if (!getenv("RP_STAGE_BYTES")) {
+    const size_t t0 = (optin - cta_fixed) / team_bytes(stage, 1);
+    for (long st = stage - 128; st >= stage - stage / 16 && st >= 1024; st -= 128)
+      if ((optin - cta_fixed) / team_bytes(st, 1) > t0) { stage = st; break; }
+  }
   // consumers per team: 1.  2 or 4 warps sharing a read's S[] (RP_CONSUMERS) are correct but not faster,
   // even on big trees: every consumer still walks every chunk, so the instruction count per read grows
   // with C while only the selection is split (cfg3, N = 9 999: 39.7 / 37.3 / 41.6 ms for C = 1 / 2 / 4,
