@@ -12,6 +12,9 @@ from . import _abi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(HERE, "librappas_b200.so")
+# development only (tools/sweep_variants.sh): another build of the same library, e.g. with a -D switch
+if os.environ.get("RAPPAS_B200_LIB"):
+    SO_PATH = os.path.abspath(os.environ["RAPPAS_B200_LIB"])
 _fn = None
 _lib = None
 

@@ -390,7 +390,12 @@ __device__ __forceinline__ int finalize_rows(const CfgView& cfg, const TopList& 
 
 // ------------------------------------------------------------------------ producer / consumer
 // What the producer hands over with a stage (warp-uniform part; 64 B, written by its lane 0).
-enum : int { kGrpLast = 1, kGrpBad = 2, kGrpTooLong = 4, kGrpStop = 8 };
+// kGrpAmb: the group is ONE ambiguous window; its staged blocks are those of its alternatives, in
+// alternative order, and the rest of the stage is the consumer's S_amb/C_amb table.  kGrpAmbGlobal: same
+// window, but its alternatives did not fit a stage: the consumer walks them in global memory.
+// Their flags also carry W_size (bits 8-12) and log2 of the table entries per consumer (bits 16-19).
+enum : int { kGrpLast = 1, kGrpBad = 2, kGrpTooLong = 4, kGrpStop = 8, kGrpAmb = 16, kGrpAmbGlobal = 32 };
+constexpr int kGrpWsizeShift = 8, kGrpTabShift = 16;
 struct __align__(16) StageHdr {
   long long r;           // read index in the batch
   const uint8_t* seq;    // character g0 of the read: first window of this group
@@ -399,7 +404,7 @@ struct __align__(16) StageHdr {
   int flags;             // kGrp*
   int n_match, n_amb, n_skip;       // totals of the read, valid on its last group
   int n_chunks;                     // chunk descriptors of the staged windows
-  uint32_t hitm, ambm, stagedm;     // windows (bit l = window g0+l) matched / ambiguous-to-treat / staged
+  uint32_t hitm, staged_bytes, stagedm;  // windows (bit l = window g0+l) matched / bytes staged / windows staged
   int pad[2];
 };
 static_assert(sizeof(StageHdr) == 64, "StageHdr is one 64 B slot");
@@ -492,6 +497,72 @@ __device__ __forceinline__ void accumulate_staged(float* __restrict__ S, uint32_
   }
 }
 
+// One ambiguous window whose alternatives' posting blocks are staged (kGrpAmb): treatAmbiguitiesWithMean /
+// ...WithMax (PlacementProcess.java:1129-1174 / 1185-1236) entirely out of shared memory.  S_amb / C_amb of
+// the reference (two arrays of N per window) become an open-addressing table {node | C_amb << 16, S_amb}
+// of H = 2^log2h entries in the unused tail of the stage: H >= the postings of the window (the producer
+// checked), linear probing, slots claimed with a compare-and-swap because two lanes of a chunk (distinct
+// nodes) may hash to one slot.  Pass 1 walks the chunks in alternative order (a node's S_amb sees its
+// alternatives in order: f32 += f64 narrowing every step, :1155); pass 2 walks the table (every touched
+// node once, :1161-1172 / :1223-1234).
+#define RP_UNLIKELY(x) __builtin_expect(!!(x), 0)
+constexpr uint32_t kTabEmpty = 0xFFFFFFFFu;
+__device__ __forceinline__ uint32_t atoms_cas(uint32_t a, uint32_t cmp, uint32_t val) {
+  uint32_t old;
+  asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(a), "r"(cmp), "r"(val) : "memory");
+  return old;
+}
+__device__ __forceinline__ void ambiguous_staged(const DbView& db, const CfgView& cfg, float* __restrict__ S, uint32_t dl,
+                                                 int n_chunks, uint32_t tab, int log2h, int n, float QT, int lane,
+                                                 uint32_t lo, uint32_t width) {
+  const uint32_t H = 1u << log2h;
+  for (uint32_t i = lane * 16; i < H * 8; i += 512)
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%1,%2};" ::"r"(tab + i), "r"(kTabEmpty), "r"(0u) : "memory");
+  __syncwarp();
+  for (int j = 0; j < n_chunks; j++) {
+    const uint2 d = lds_u64(dl + 8 * j);
+    const uint32_t m = d.y;
+    const uint32_t x = (uint32_t)lane < m ? lds_u16(d.x + 4 * m + 2 * lane) : 0xFFFFFFFFu;
+    if (x - lo < width) {  // this consumer's nodes only (lanes >= m never qualify)
+      const float v = lds_f32(d.x + 4 * lane);
+      uint32_t h = (x * 0x9E3779B1u) >> (32 - log2h), cur;
+      for (;;) {
+        cur = atoms_cas(tab + 8 * h, kTabEmpty, x);
+        if (cur == kTabEmpty || (cur & 0xFFFFu) == x) break;
+        h = (h + 1) & (H - 1);
+      }
+      const uint32_t c = cur == kTabEmpty ? 0u : cur >> 16;
+      float sa = c ? lds_f32(tab + 8 * h + 4) : 0.0f;
+      if (cfg.amb_with_max) {
+        if (c == 0 || v > sa) sa = v;
+      } else {
+        sa = (float)((double)sa + pow(10.0, (double)v));  // S_amb[x]+=Math.pow(10,v) : f32 += f64
+      }
+      sts_u64(tab + 8 * h, make_uint2(x | ((c + 1) << 16), __float_as_uint(sa)));
+    }
+    __syncwarp();
+  }
+  for (uint32_t i = lane; i < H; i += 32) {
+    const uint2 e = lds_u64(tab + 8 * i);
+    if (e.x != kTabEmpty) {
+      const uint32_t x = e.x & 0xFFFFu, c = e.x >> 16;
+      const float sa = __uint_as_float(e.y);
+      float s = S[x];
+      if (is_sentinel(s)) s = QT;  // S[x]=Q*T  (:1163-1166)
+      if (cfg.amb_with_max) {
+        s = __fadd_rn(s, __fsub_rn(sa, db.T));  // :1230
+      } else {
+        // float avgProba=(S_amb[x] + (W_size-C_amb[x])*PPStarThreshold) / W_size;   (:1168)
+        const float avg = __fdiv_rn(__fadd_rn(sa, __fmul_rn((float)(n - (int)c), db.Tlin)), (float)n);
+        // S[x]+=Math.log10(avgProba)-PPStarThresholdAsLog10;   f32 += f64   (:1169)
+        s = (float)((double)s + (log10((double)avg) - (double)db.T));
+      }
+      S[x] = s;
+    }
+  }
+  __syncwarp();
+}
+
 struct PairSmem {
   uint32_t bar;        // shared address of full[0]; full[i] = bar + 8 i, empty[i] = bar + 8 (kStages + i)
   uint8_t* meta;       // kStages x kStageMetaBytes
@@ -532,9 +603,11 @@ __device__ __forceinline__ bool probe_resolve(const ProbeIO& io, uint64_t& meta)
   return h0 | h1 | h2 | h3;
 }
 
+template <int C>
 __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const DbView& db, const CfgView& cfg,
                                          const BatchView& bt, unsigned long long* work_counter, const PairSmem& w,
                                          uint32_t cls_tab, int lane) {
+  constexpr uint32_t n_cons = C;
   const int k = db.k;
   const uint32_t kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
   const int stage_bytes = w.stage_bytes;
@@ -550,16 +623,19 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
   // group about to be published: class bytes of characters [g0, g0+64), raw characters [g0+64, g0+96)
   uint32_t cA = kClsPad, cB = kClsPad, rawC = 0;
   // its window classification and its probe in flight
-  bool g_bad = false, g_plain = false, g_skip = false, g_ambw = false;
+  bool g_bad = false, g_plain = false, g_skip = false;
   int g_nv = 0;
   ProbeIO io;
   io.klo = io.khi = 0; io.s0 = io.s1 = io.s2 = io.s3 = make_uint4(0, 0, 0, 0);
 
   auto cls_of = [&](uint32_t raw, int i) -> uint32_t { return i < len ? lds_u8(cls_tab + raw) : (uint32_t)kClsPad; };
-  // K1 of the group whose class bytes are in cA/cB, and issue of its probes (K2)
+  // K1 of the group whose class bytes are in cA/cB, and issue of its probes (K2).  A group is a run of plain
+  // and skipped windows (lane l = window g0+l) that ends before the first ambiguous window to treat; when
+  // window g0 itself is one, g_nv = 0 and the group is that window alone (its alternatives are probed when
+  // the group is published: they are rare, and any branch here costs the plain path ~8 %).
   auto front = [&]() {
     g_bad = __any_sync(0xffffffffu, cA == kClsBad || cB == kClsBad);
-    g_plain = g_skip = g_ambw = false;
+    g_plain = g_skip = false;
     g_nv = 0;
     uint64_t key = 0;
     if (!g_bad && Ql > 0) {
@@ -567,12 +643,14 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       const uint32_t a0 = __ballot_sync(0xffffffffu, (cA & 0xC0) == kClsAmb);
       const uint32_t a1 = __ballot_sync(0xffffffffu, (cB & 0xC0) == kClsAmb);
       const int na = __popc(__funnelshift_r(a0, a1, lane) & kmask);
-      g_nv = min(32, Ql - g0);  // windows left in the read
-      const bool valid = lane < g_nv;
+      const bool valid = lane < min(32, Ql - g0);  // windows left in the read
       // getNextByteWord (:224-233) + processQueries (:691-750)
-      g_plain = valid && na == 0;
-      g_skip = valid && na > 0 && (na > db.max_amb || !cfg.treat_amb);
-      g_ambw = valid && na > 0 && !g_skip;
+      const bool skip = na > 0 && (na > db.max_amb || !cfg.treat_amb);
+      const uint32_t ambw = __ballot_sync(0xffffffffu, valid && na > 0 && !skip);
+      const uint32_t below = (ambw & (0u - ambw)) - 1u;  // the lanes before the first ambiguous window to treat
+      g_nv = min(min(32, Ql - g0), __popc(below));
+      g_plain = valid && na == 0 && ((below >> lane) & 1u);
+      g_skip = valid && skip && ((below >> lane) & 1u);
       // planar key: plane p of window `lane` = bits [lane, lane+k) of the p-th state-bit ballots
       for (int p = 0; p < db.bits; p++) {
         const uint32_t b0 = __ballot_sync(0xffffffffu, (cA >> p) & 1u);
@@ -581,6 +659,25 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       }
     }
     probe_issue(db, key, g_plain, io);
+  };
+  // The alternatives of the ambiguous window g0 (class bytes in cA): lane t < W_size probes alternative t,
+  // in which position o_m takes A_m[t mod |A_m|]  (AmbigSequenceKnife.java:249-256).  Returns W_size.
+  auto probe_alternatives = [&](bool& found, uint64_t& meta) -> int {
+    const uint32_t wbits = __ballot_sync(0xffffffffu, (cA & 0xC0) == kClsAmb) & kmask, rest = wbits & (wbits - 1);
+    const int o1 = __ffs(wbits) - 1, o2 = rest ? __ffs(rest) - 1 : o1;
+    const int id1 = __shfl_sync(0xffffffffu, cA, o1) & 0x3F, id2 = __shfl_sync(0xffffffffu, cA, o2) & 0x3F;
+    const int n1 = c_alpha.alt_n[id1], n2 = rest ? c_alpha.alt_n[id2] : 1;
+    const int wsize = n1 * n2;  // <= 20 (amino) / 16 (nucl, 2 ambiguities)
+    const uint32_t st1 = c_alpha.alt_states[id1][lane % n1], st2 = c_alpha.alt_states[id2][lane % n2];
+    uint64_t key = 0;
+    for (int p = 0; p < db.bits; p++) {
+      uint64_t plane = __ballot_sync(0xffffffffu, (cA >> p) & 1u) & kmask & ~((1u << o1) | (1u << o2));
+      if (rest) plane |= (uint64_t)((st2 >> p) & 1u) << o2;
+      plane |= (uint64_t)((st1 >> p) & 1u) << o1;
+      key |= plane << (p * k);
+    }
+    found = lane < wsize && table_probe(db, key, meta);
+    return wsize;
   };
   // The NEXT read of the pair: its index comes from the atomic issued one read earlier and its two
   // offsets are requested when the current read starts, so a read start waits for its characters only.
@@ -641,22 +738,23 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
     }
     int flags = too_long ? kGrpTooLong : 0;
     int n_chunks = 0;
-    uint32_t hitm = 0, ambm = 0, stagedm = 0, total = 0;
-    uint32_t copy_dst = 0, copy_bytes = 0;  // this lane's bulk copy, issued once the stage is published
-    const uint8_t* copy_src = nullptr;
+    uint32_t hitm = 0, stagedm = 0, total = 0;
     const uint8_t* seq_g0 = s + g0;
     // per-lane results of this group that the publication below needs
     uint64_t meta = 0;
     uint32_t n_post = 0, bytes = 0, my_chunks = 0, incl_chunks = 0, off = 0, incl = 0;
-    int cons = 0;
+    int cons = 0, last = 0;
     bool more = false;  // another group of this read follows (its probe is issued below)
-    if (g_bad) {
+    if (RP_UNLIKELY(g_bad)) {
       // an unsupported character aborts the reference whatever the length (AmbigSequenceKnife.java:124-128)
       flags |= kGrpBad | kGrpLast;
-    } else if (Ql <= 0) {
+    } else if (RP_UNLIKELY(Ql <= 0)) {
       flags |= kGrpLast;
     } else {
-      const bool found = probe_resolve(io, meta);
+      bool found;
+      int wsize = 0;
+      if (RP_UNLIKELY(g_nv == 0)) wsize = probe_alternatives(found, meta);
+      else found = probe_resolve(io, meta);
       // stage assignment: windows are taken in order while their posting blocks fit into the stage;
       // a block larger than a whole stage is read from global memory by the consumer instead
       n_post = found ? (uint32_t)(meta & 0xFFFF) : 0u;
@@ -674,15 +772,31 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       const uint32_t incl_bytes = incl >> 13 << 5;
       incl_chunks = incl & 0x1FFFu;
       const uint32_t nofit = __ballot_sync(0xffffffffu, incl_bytes > (uint32_t)stage_bytes);
-      cons = nofit ? __ffs(nofit) - 1 : 32;  // >= 1: lane 0 alone always fits
-      cons = min(cons, g_nv);
-      const uint32_t lanes = cons >= 32 ? 0xffffffffu : ((1u << cons) - 1u);
-      hitm = __ballot_sync(0xffffffffu, found) & lanes;
-      ambm = __ballot_sync(0xffffffffu, g_ambw) & lanes;
-      stagedm = __ballot_sync(0xffffffffu, sb != 0u) & lanes;
-      n_match += __popc(hitm);
-      n_amb += __popc(ambm);
-      n_skip += __popc(__ballot_sync(0xffffffffu, g_skip) & lanes);
+      if (RP_UNLIKELY(wsize != 0)) {
+        // all the alternatives found, plus a table of >= as many entries as they have postings (per
+        // consumer), in one stage -- or nothing is staged and the consumer reads them from global memory
+        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t tot_bytes = tot >> 13 << 5, tot_chunks = tot & 0x1FFFu;
+        const uint32_t foundm = __ballot_sync(0xffffffffu, found), giantm = __ballot_sync(0xffffffffu, found && giant);
+        const uint32_t room = (tot_bytes <= (uint32_t)stage_bytes ? (uint32_t)stage_bytes - tot_bytes : 0u) / (8u * n_cons);
+        uint32_t lg = room ? 31 - __clz(room) : 0;                         // the largest table that fits ...
+        if (tot_chunks) lg = min(lg, 32u - __clz(64u * tot_chunks - 1u));  // ... up to twice the postings
+        const bool staged = !nofit && !giantm && (1u << lg) >= 32u * tot_chunks && lg >= 5;
+        flags |= (staged ? kGrpAmb : kGrpAmbGlobal) | (wsize << kGrpWsizeShift) | (lg << kGrpTabShift);
+        hitm = stagedm = staged ? foundm : 0u;
+        cons = 1;
+        last = 31;
+        n_amb += 1;  // (matches inside the helpers are not counted: queryKmerMatchingDB is passed by value, :741-743)
+      } else {
+        cons = nofit ? __ffs(nofit) - 1 : 32;  // >= 1: lane 0 alone always fits
+        cons = min(cons, g_nv);
+        last = cons - 1;
+        const uint32_t lanes = cons >= 32 ? 0xffffffffu : ((1u << cons) - 1u);
+        hitm = __ballot_sync(0xffffffffu, found) & lanes;
+        stagedm = __ballot_sync(0xffffffffu, sb != 0u) & lanes;
+        n_match += __popc(hitm);
+        n_skip += __popc(__ballot_sync(0xffffffffu, g_skip) & lanes);
+      }
       off = incl_bytes - sb;
       if (!((stagedm >> lane) & 1u)) bytes = 0;  // only staged windows are copied
       if (g0 + cons >= Ql) {
@@ -704,10 +818,10 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
     // what the publication needs from the probe registers is saved: they are reused by the next group now
     const uint32_t n_post_c = n_post, bytes_c = bytes, my_chunks_c = my_chunks, incl_chunks_c = incl_chunks, off_c = off;
     const uint64_t meta_c = meta;
-    const uint32_t last_incl = (stagedm && cons > 0) ? __shfl_sync(0xffffffffu, incl, cons - 1) : 0u;
+    const uint32_t last_incl = (stagedm && cons > 0) ? __shfl_sync(0xffffffffu, incl, last) : 0u;
     if (more) front();
     acquire();
-    if (ambm | (hitm & ~stagedm)) {  // the consumer's per-window path needs these
+    if (hitm & ~stagedm) {  // the consumer's per-window path needs these
       sts_u32(hdr + 64 + 4 * lane, (off_c << 16) | n_post_c);
       sts_u64(hdr + 192 + 8 * lane, make_uint2((uint32_t)meta_c, (uint32_t)(meta_c >> 32)));
     }
@@ -718,12 +832,9 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       const uint32_t stage0 = stages + slot * stage_bytes;
       const uint32_t dl0 = stages + kStages * stage_bytes + slot * w.max_chunks * 8;
       if (bytes_c) {
-        copy_dst = stage0 + off_c;
-        copy_src = block_ptr(db, meta_c);
-        copy_bytes = bytes_c;
         // chunk descriptors of this window, in window order
         uint32_t dl = dl0 + 8 * (incl_chunks_c - my_chunks_c);
-        uint32_t a = copy_dst;
+        uint32_t a = stage0 + off_c;
         for (uint32_t left = n_post_c; left; a += kSubBlockBytes, dl += 8) {
           const uint32_t m = min(left, 32u);
           sts_u64(dl, make_uint2(a, m));
@@ -737,7 +848,7 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       StageHdr h;
       h.r = r; h.seq = seq_g0; h.Q = Ql; h.QT = QT; h.flags = flags;
       h.n_match = n_match; h.n_amb = n_amb; h.n_skip = n_skip;
-      h.n_chunks = n_chunks; h.hitm = hitm; h.ambm = ambm; h.stagedm = stagedm;
+      h.n_chunks = n_chunks; h.hitm = hitm; h.staged_bytes = total; h.stagedm = stagedm;
       h.pad[0] = h.pad[1] = 0;
       const uint4* q = reinterpret_cast<const uint4*>(&h);
 #pragma unroll
@@ -751,7 +862,9 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       else mbar_arrive(full);
     }
     // (the consumer's reads of this stage are ordered before these async writes by its `empty` arrival)
-    if (copy_bytes) bulk_g2s(copy_dst, copy_src, copy_bytes, full);
+    // this lane's bulk copy (bytes_c != 0 only for the staged windows of the group)
+    if (bytes_c)
+      bulk_g2s(w.bar + 64 + kStages * kStageMetaBytes + slot * stage_bytes + off_c, block_ptr(db, meta_c), bytes_c, full);
     if (flags & kGrpLast) have = start_read();
   }
 }
@@ -782,26 +895,35 @@ __device__ __forceinline__ void consumer(const AlphabetTables& c_alpha, const Db
     if (g.flags & kGrpStop) return;
     const float QT0 = __fadd_rn(0.0f, g.QT);  // S[x]+=Q*T on a zeroed S[x]
     const bool bad = g.flags & kGrpBad;
-    if (!bad && !(g.ambm | (g.hitm & ~g.stagedm))) {
+    if (!bad && !((g.flags & (kGrpAmb | kGrpAmbGlobal)) | (g.hitm & ~g.stagedm))) {
       // common case: every matched window of the group is staged
       if (g.n_chunks) accumulate_chunks<(C > 1)>(S, w.desc + slot * w.max_chunks * 8, g.n_chunks, QT0, db.T, lane, lo, width);
     } else if (!bad) {
-      const uint32_t* pk_arr = reinterpret_cast<const uint32_t*>(w.meta + slot * kStageMetaBytes + 64);
-      const uint64_t* meta_arr = reinterpret_cast<const uint64_t*>(w.meta + slot * kStageMetaBytes + 192);
-      const uint32_t stage = w.stage + slot * w.stage_bytes;
-      // windows in order: a node's S[x] must see its contributions in window order
-      for (uint32_t todo = g.hitm | g.ambm; todo;) {
-        const int l = __ffs(todo) - 1;
-        todo &= todo - 1;
-        if ((g.hitm >> l) & 1u) {
+      if (g.flags & kGrpAmb) {
+        // one ambiguous window, its alternatives staged; the table of consumer c follows the blocks
+        const int tab_log2 = (g.flags >> kGrpTabShift) & 0xF;
+        if (g.n_chunks)
+          ambiguous_staged(db, cfg, S, w.desc + slot * w.max_chunks * 8, g.n_chunks,
+                           w.stage + slot * w.stage_bytes + g.staged_bytes + ((uint32_t)c << (tab_log2 + 3)), tab_log2,
+                           (g.flags >> kGrpWsizeShift) & 0x1F, g.QT, lane, lo, width);
+      } else if (g.flags & kGrpAmbGlobal) {
+        // one ambiguous window whose alternatives did not fit a stage
+        ambiguous_window(c_alpha, db, cfg, S, g.seq, g.QT, Sa, Ca, lane, lo, width);
+      } else {
+        // a posting block larger than a stage: windows one by one, in order (a node's S[x] must see its
+        // contributions in window order)
+        const uint32_t* pk_arr = reinterpret_cast<const uint32_t*>(w.meta + slot * kStageMetaBytes + 64);
+        const uint64_t* meta_arr = reinterpret_cast<const uint64_t*>(w.meta + slot * kStageMetaBytes + 192);
+        const uint32_t stage = w.stage + slot * w.stage_bytes;
+        for (uint32_t todo = g.hitm; todo;) {
+          const int l = __ffs(todo) - 1;
+          todo &= todo - 1;
           const uint32_t pk = pk_arr[l];
           if ((g.stagedm >> l) & 1u) {
             accumulate_staged(S, stage + (pk >> 16), (int)(pk & 0xFFFF), QT0, db.T, lane, lo, width);
           } else {
             accumulate_global(S, block_ptr(db, meta_arr[l]), (int)(pk & 0xFFFF), QT0, db.T, lane, lo, width);
           }
-        } else {
-          ambiguous_window(c_alpha, db, cfg, S, g.seq + l, g.QT, Sa, Ca, lane, lo, width);
         }
       }
     }
@@ -921,7 +1043,7 @@ place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_consta
   // local memory around them, and with ~227 KB of shared memory carved out there is no L1 left, so every
   // such spill was an L2 round trip: 20 % of the kernel time, profiles/r01_v5_spill_stalls.txt.)
   if (is_producer) {
-    producer(c_alpha, db, cfg, bt, work_counter, w, smem_u32(smem), lane);
+    producer<C>(c_alpha, db, cfg, bt, work_counter, w, smem_u32(smem), lane);
   } else {
     const size_t gp = (size_t)blockIdx.x * teams + pair;
     consumer<C>(c_alpha, db, cfg, bt, w, amb_S + gp * n_pad, amb_C + gp * n_pad, n_pad, lane, cidx, cand);

@@ -300,3 +300,32 @@ def test_very_large_tree_and_the_limit():
     with pytest.raises(RappasError) as e:
         R.Database.from_synth(big)
     assert e.value.code == 5 and "shared memory" in str(e.value)
+
+
+@pytest.mark.parametrize("env", [dict(RP_STAGE_BYTES="1024"), dict(RP_STAGE_BYTES="16384"), dict(RP_CONSUMERS="2"),
+                                 dict(RP_CONSUMERS="4", RP_STAGE_BYTES="2048")],
+                         ids=lambda e: ",".join("%s=%s" % kv for kv in sorted(e.items())))
+@pytest.mark.parametrize("name", ["nucl_k6_ambig", "nucl_k10_long_lists", "nucl_k16_two_ambig", "amino_k3"])
+def test_ambiguous_windows_staged_and_from_global_memory(name, env, monkeypatch):
+    """An ambiguous window is a group of its own: its alternatives' blocks are staged and S_amb / C_amb is a
+    table in the stage's tail -- or, when they do not fit, the consumer walks them in global memory.  The
+    geometry knobs (read when the DB is loaded) push the same reads down both branches, and through the
+    teams of 2 and 4 consumers that share a read (one table per consumer)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    spec = CASES[name]
+    db = synth.make_db(**spec["db"])
+    rb = synth.make_reads(db, **spec["reads"])
+    g, o = both(db)
+    try:
+        for with_max in (False, True):
+            cfg = _abi.place_cfg(amb_with_max=with_max)
+            oo = o.place(rb, cfg)
+            assert amb_reads(oo).sum() > 20
+            amb = None if with_max else amb_reads(oo)  # --ambwithmax is pure f32: bit-exact
+            So, _ = o.node_scores(rb, cfg, hitcount=False)
+            parity.assert_scores_equal(g.node_scores(rb, cfg), So, amb)
+            parity.assert_placements_equal(g.place(rb, cfg), oo, cfg.keep_at_most, amb)
+    finally:
+        g.close()
+        o.close()
