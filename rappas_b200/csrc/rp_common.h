@@ -107,9 +107,13 @@ struct DbView {
 __host__ __device__ inline uint32_t owner_of(uint32_t mix, int n_parts) {
   return (((mix * 0x85EBCA6Bu) >> 16) * (uint32_t)n_parts) >> 16;
 }
-// meta = (partition << 61) | (block_offset_in_32B_units << 16) | n_postings
+// meta = (partition << 61) | (qmax << 57) | (qmin << 53) | (block_offset_in_32B_units << 16) | n_postings
+// [qmin, qmax] = the sixteenths of the (padded) node range that the list's nodes fall into: the consumers
+// of a team own node slices, and a window is routed to the consumers whose slice its list can touch.
 constexpr int kMetaPartShift = 61;
-constexpr uint64_t kMetaOffMask = (1ull << 45) - 1;
+constexpr int kMetaQminShift = 53, kMetaQmaxShift = 57;
+constexpr uint64_t kMetaOffMask = (1ull << 37) - 1;  // 2^37 x 32 B = 4 TB of posting blocks per partition
+__host__ __device__ inline int padded_nodes(int n_nodes) { return (n_nodes + 127) & ~127; }
 
 struct CfgView {
   int K;

@@ -172,7 +172,7 @@ static int build_image(const rp_db_desc* d, const uint64_t* keys, const uint64_t
     boff[j + 1] = boff[j] + block_bytes_for(P) / kBlockAlign;
     max_bb = std::max(max_bb, block_bytes_for(P));
   }
-  if (boff[nk] > kMetaOffMask) return set_error(RP_E_INVALID, "posting blocks exceed 2^45 * 32 B");
+  if (boff[nk] > kMetaOffMask) return set_error(RP_E_INVALID, "posting blocks exceed 2^37 * 32 B");
   img->block_bytes = boff[nk] * kBlockAlign;
   img->max_block_bytes = max_bb;
   img->blocks = (uint8_t*)calloc(img->block_bytes ? img->block_bytes : 32, 1);
@@ -214,7 +214,11 @@ static int build_image(const rp_db_desc* d, const uint64_t* keys, const uint64_t
       }
       // greedy 2-choice placement (lock-free: CAS on the key word, then publish meta)
       const uint64_t key = planar_from_code(keys[i], bits, k);
-      const uint64_t meta = ((uint64_t)part << kMetaPartShift) | (boff[j] << 16) | P;
+      // node range of the list in sixteenths of the padded tree (tmp is sorted by node here)
+      const uint64_t n_pad = (uint64_t)padded_nodes(n_nodes);
+      const uint64_t qmin = P ? (uint64_t)tmp[0].first * 16 / n_pad : 0, qmax = P ? (uint64_t)tmp[P - 1].first * 16 / n_pad : 0;
+      const uint64_t meta = ((uint64_t)part << kMetaPartShift) | (qmax << kMetaQmaxShift) | (qmin << kMetaQminShift) |
+                            (boff[j] << 16) | P;
       const uint32_t m32 = mix_key(key);
       const uint32_t bk[2] = {bucket1(m32, shift), bucket2(m32, shift)};
       bool placed = false;

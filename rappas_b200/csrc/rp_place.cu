@@ -413,7 +413,7 @@ static_assert(sizeof(StageHdr) == 64, "StageHdr is one 64 B slot");
 //   [0,32)    full[kStages], empty[kStages] mbarriers
 //   [64, ..)  kStages x { StageHdr (64 B) | pk u32[32] | meta u64[32] }  = 448 B each
 //   stage     kStages x stage_bytes        posting blocks as they lie in HBM
-//   desc      kStages x max_chunks x 8 B   chunk descriptors {shared address of the scores, m}
+//   desc      kStages x C x max_chunks x 8 B   chunk descriptors {shared address of the scores, m}, one list per consumer
 //   S         f32[n_pad + 32]              (+32: per-lane dummies for the idle lanes of a short chunk)
 constexpr int kStageMetaBytes = 64 + 128 + 256;
 static_assert((kStages * kStageMetaBytes) % 64 == 0, "stages start 16 B aligned");
@@ -606,8 +606,20 @@ __device__ __forceinline__ bool probe_resolve(const ProbeIO& io, uint64_t& meta)
 template <int C>
 __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const DbView& db, const CfgView& cfg,
                                          const BatchView& bt, unsigned long long* work_counter, const PairSmem& w,
-                                         uint32_t cls_tab, int lane) {
+                                         uint32_t cls_tab, int lane, int n_pad) {
   constexpr uint32_t n_cons = C;
+  // C > 1: consumer c owns the node slice [c*per, (c+1)*per); qb holds, per consumer, the first and the last
+  // sixteenth of the padded node range that its slice overlaps (4 + 4 bits each) -- a window whose list
+  // spans the sixteenths [qmin, qmax] (kept in its table entry) is routed to consumer c iff they intersect
+  uint32_t qb = 0;
+  if (C > 1) {
+    const int per = ((n_pad / 128 + C - 1) / C) * 128, u = n_pad / 16;
+    for (int c = 0; c < C; c++) {
+      const int lo_c = min(c * per, n_pad), hi_c = min(lo_c + per, n_pad);
+      const int qlo = lo_c / u, qhi = hi_c > lo_c ? (hi_c - 1) / u : 0;
+      qb |= (uint32_t)((hi_c > lo_c ? qlo : 15) | (qhi << 4)) << (8 * c);  // empty slice: qlo 15 > qhi 0, never hit
+    }
+  }
   const int k = db.k;
   const uint32_t kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
   const int stage_bytes = w.stage_bytes;
@@ -819,6 +831,30 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
     const uint32_t n_post_c = n_post, bytes_c = bytes, my_chunks_c = my_chunks, incl_chunks_c = incl_chunks, off_c = off;
     const uint64_t meta_c = meta;
     const uint32_t last_incl = (stagedm && cons > 0) ? __shfl_sync(0xffffffffu, incl, last) : 0u;
+    // C > 1: the chunks of a window go to the lists of the consumers whose slice the window's nodes can touch
+    // (all of them for the alternatives of an ambiguous window: every consumer needs the whole W_size picture
+    // of its own nodes only, but the table pass is cheap and the case rare)
+    uint32_t route = 0;          // this lane's consumers
+    uint64_t rincl = 0, rtot = 0;  // per consumer (13 bits each): inclusive prefix of the routed chunks, totals
+    if (C > 1 && stagedm) {
+      if (bytes_c) {
+        const uint32_t qmin = (uint32_t)(meta_c >> kMetaQminShift) & 15u, qmax = (uint32_t)(meta_c >> kMetaQmaxShift) & 15u;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+          const uint32_t b = qb >> (8 * c);
+          if ((flags & kGrpAmb) || (qmin <= ((b >> 4) & 15u) && qmax >= (b & 15u))) route |= 1u << c;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < C; c++)
+        if ((route >> c) & 1u) rincl |= (uint64_t)my_chunks_c << (13 * c);
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t t = __shfl_up_sync(0xffffffffu, rincl, d);
+        if (lane >= d) rincl += t;
+      }
+      rtot = __shfl_sync(0xffffffffu, rincl, last);
+    }
     if (more) front();
     acquire();
     if (hitm & ~stagedm) {  // the consumer's per-window path needs these
@@ -830,26 +866,45 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       n_chunks = (int)(last_incl & 0x1FFFu);
       const uint32_t stages = w.bar + 64 + kStages * kStageMetaBytes;
       const uint32_t stage0 = stages + slot * stage_bytes;
-      const uint32_t dl0 = stages + kStages * stage_bytes + slot * w.max_chunks * 8;
-      if (bytes_c) {
-        // chunk descriptors of this window, in window order
-        uint32_t dl = dl0 + 8 * (incl_chunks_c - my_chunks_c);
-        uint32_t a = stage0 + off_c;
-        for (uint32_t left = n_post_c; left; a += kSubBlockBytes, dl += 8) {
-          const uint32_t m = min(left, 32u);
-          sts_u64(dl, make_uint2(a, m));
-          left -= m;
+      const uint32_t dl0 = stages + kStages * stage_bytes + slot * (C * w.max_chunks * 8);  // C lists per stage
+      if (C == 1) {
+        if (bytes_c) {
+          // chunk descriptors of this window, in window order
+          uint32_t dl = dl0 + 8 * (incl_chunks_c - my_chunks_c);
+          uint32_t a = stage0 + off_c;
+          for (uint32_t left = n_post_c; left; a += kSubBlockBytes, dl += 8) {
+            const uint32_t m = min(left, 32u);
+            sts_u64(dl, make_uint2(a, m));
+            left -= m;
+          }
+        }
+        if (lane < 8)  // idle descriptors behind the list: the consumer works in rounds of 4 and looks 4 ahead
+          sts_u64(dl0 + 8 * (n_chunks + lane), make_uint2(stage0, 0u));
+      } else {
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+          const uint32_t dlc = dl0 + c * (w.max_chunks * 8);
+          if ((route >> c) & 1u) {
+            uint32_t dl = dlc + 8 * ((uint32_t)(rincl >> (13 * c)) & 0x1FFFu) - 8 * my_chunks_c;
+            uint32_t a = stage0 + off_c;
+            for (uint32_t left = n_post_c; left; a += kSubBlockBytes, dl += 8) {
+              const uint32_t m = min(left, 32u);
+              sts_u64(dl, make_uint2(a, m));
+              left -= m;
+            }
+          }
+          if (lane < 8) sts_u64(dlc + 8 * (((uint32_t)(rtot >> (13 * c)) & 0x1FFFu) + lane), make_uint2(stage0, 0u));
         }
       }
-      if (lane < 8)  // idle descriptors behind the list: the consumer works in rounds of 4 and looks 4 ahead
-        sts_u64(dl0 + 8 * (n_chunks + lane), make_uint2(stage0, 0u));
     }
     if (lane == 0) {
       StageHdr h;
       h.r = r; h.seq = seq_g0; h.Q = Ql; h.QT = QT; h.flags = flags;
       h.n_match = n_match; h.n_amb = n_amb; h.n_skip = n_skip;
       h.n_chunks = n_chunks; h.hitm = hitm; h.staged_bytes = total; h.stagedm = stagedm;
-      h.pad[0] = h.pad[1] = 0;
+      // C > 1: the length of each consumer's list, 16 bits each
+      h.pad[0] = (int)(((uint32_t)rtot & 0x1FFFu) | (((uint32_t)(rtot >> 13) & 0x1FFFu) << 16));
+      h.pad[1] = (int)(((uint32_t)(rtot >> 26) & 0x1FFFu) | (((uint32_t)(rtot >> 39) & 0x1FFFu) << 16));
       const uint4* q = reinterpret_cast<const uint4*>(&h);
 #pragma unroll
       for (int i = 0; i < 4; i++)
@@ -871,8 +926,8 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
 
 // ---- K3 + K4: the consumer warps ------------------------------------------------------------------
 // C consumers share one read: consumer c owns the nodes [lo, lo+width) of S -- it adds only the postings
-// of its nodes (every consumer walks every chunk, in window order, so the per-node order is kept), selects
-// the top-K of its slice, and consumer 0 merges the C lists and writes the rows.  C = 1 for small trees
+// of its nodes (it walks, in window order, the chunks of the windows routed to its slice, so the per-node
+// order is kept), selects the top-K of its slice, and consumer 0 merges the C lists and writes the rows.  C = 1 for small trees
 // (the pair of DESIGN.md); big trees, whose S[] leaves room for only a few reads per SM, get more warps
 // per read this way.  Candidate hand-over: cand[c][K] in shared memory, guarded by two mbarriers.
 template <int C>
@@ -894,16 +949,19 @@ __device__ __forceinline__ void consumer(const AlphabetTables& c_alpha, const Db
     const StageHdr g = *reinterpret_cast<const StageHdr*>(w.meta + slot * kStageMetaBytes);
     if (g.flags & kGrpStop) return;
     const float QT0 = __fadd_rn(0.0f, g.QT);  // S[x]+=Q*T on a zeroed S[x]
+    // this consumer's chunk list of the stage and its length (C > 1: only the windows routed to its slice)
+    const uint32_t my_list = w.desc + (slot * C + c) * (w.max_chunks * 8);
+    const int my_chunks = C > 1 ? (int)(((uint32_t)((c >> 1) ? g.pad[1] : g.pad[0]) >> (16 * (c & 1))) & 0xFFFFu) : g.n_chunks;
     const bool bad = g.flags & kGrpBad;
     if (!bad && !((g.flags & (kGrpAmb | kGrpAmbGlobal)) | (g.hitm & ~g.stagedm))) {
       // common case: every matched window of the group is staged
-      if (g.n_chunks) accumulate_chunks<(C > 1)>(S, w.desc + slot * w.max_chunks * 8, g.n_chunks, QT0, db.T, lane, lo, width);
+      if (my_chunks) accumulate_chunks<(C > 1)>(S, my_list, my_chunks, QT0, db.T, lane, lo, width);
     } else if (!bad) {
       if (g.flags & kGrpAmb) {
         // one ambiguous window, its alternatives staged; the table of consumer c follows the blocks
         const int tab_log2 = (g.flags >> kGrpTabShift) & 0xF;
-        if (g.n_chunks)
-          ambiguous_staged(db, cfg, S, w.desc + slot * w.max_chunks * 8, g.n_chunks,
+        if (my_chunks)
+          ambiguous_staged(db, cfg, S, my_list, my_chunks,
                            w.stage + slot * w.stage_bytes + g.staged_bytes + ((uint32_t)c << (tab_log2 + 3)), tab_log2,
                            (g.flags >> kGrpWsizeShift) & 0x1F, g.QT, lane, lo, width);
       } else if (g.flags & kGrpAmbGlobal) {
@@ -993,8 +1051,10 @@ __device__ __forceinline__ void consumer(const AlphabetTables& c_alpha, const Db
 // --------------------------------------------------------------------------------- main kernel
 // Warps 0..teams-1 are the producers, then C consumers per team; blockDim = teams * (1 + C) * 32.
 constexpr int kMaxThreads = kMaxPairsPerCta * 64;
+// teams of several consumers only run where S[] leaves room for a few reads per SM: fewer threads, more registers
+constexpr int max_threads_for(int C) { return C == 1 ? kMaxThreads : 640; }
 template <int C>
-__global__ void __launch_bounds__(kMaxThreads, 1)
+__global__ void __launch_bounds__(max_threads_for(C), 1)
 place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_constant__ DbView db,
              const __grid_constant__ CfgView cfg, const __grid_constant__ BatchView bt,
              unsigned long long* work_counter, float* amb_S, int* amb_C, int n_pad, int per_pair_bytes,
@@ -1018,7 +1078,7 @@ place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_consta
     w.stage = smem_u32(p);  // idle lanes of a short chunk read (and ignore) up to 160 B past it: keep the stages inside
     p += (size_t)kStages * stage_bytes;
     w.desc = smem_u32(p);
-    p += (size_t)kStages * max_chunks * 8;
+    p += (size_t)kStages * C * max_chunks * 8;
     w.S = reinterpret_cast<float*>(p);
     p += 4 * (size_t)(n_pad + 32);
     cand = smem_u32(p);  // C > 1: cand[C][32] x 8 B
@@ -1043,7 +1103,7 @@ place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_consta
   // local memory around them, and with ~227 KB of shared memory carved out there is no L1 left, so every
   // such spill was an L2 round trip: 20 % of the kernel time, profiles/r01_v5_spill_stalls.txt.)
   if (is_producer) {
-    producer<C>(c_alpha, db, cfg, bt, work_counter, w, smem_u32(smem), lane);
+    producer<C>(c_alpha, db, cfg, bt, work_counter, w, smem_u32(smem), lane, n_pad);
   } else {
     const size_t gp = (size_t)blockIdx.x * teams + pair;
     consumer<C>(c_alpha, db, cfg, bt, w, amb_S + gp * n_pad, amb_C + gp * n_pad, n_pad, lane, cidx, cand);
@@ -1153,7 +1213,7 @@ int compute_geometry(const rp_db* db, DeviceCtx* dc) {
   stage = (stage + 127) & ~127L;
   auto team_bytes = [&](long st, int C) {
     const size_t chunks = (32 + st / kSubBlockBytes + 9 + 1) & ~(size_t)1;  // per window + per extra sub-block + 8 idle
-    return (64 + kStages * (size_t)kStageMetaBytes + kStages * 8 * chunks + 4 * (size_t)(g.n_pad + 32) +
+    return (64 + kStages * (size_t)kStageMetaBytes + kStages * 8 * chunks * C + 4 * (size_t)(g.n_pad + 32) +
             kStages * (size_t)st + (C > 1 ? (size_t)C * 264 : 0) + 127) & ~(size_t)127;
   };
   // big trees: give the stages up before giving the accumulator up
@@ -1165,9 +1225,10 @@ int compute_geometry(const rp_db* db, DeviceCtx* dc) {
       if ((optin - cta_fixed) / team_bytes(st, 1) > t0) { stage = st; break; }
   }
   // consumers per team: 1.  2 or 4 warps sharing a read's S[] (RP_CONSUMERS) are correct but not faster,
-  // even on big trees: every consumer still walks every chunk, so the instruction count per read grows
-  // with C while only the selection is split (cfg3, N = 9 999: 39.7 / 37.3 / 41.6 ms for C = 1 / 2 / 4,
-  // profiles/r01_v6_team_consumers.txt).  Kept as a knob for the slice-routed lists of the next round.
+  // even on big trees and even though every window is routed to the consumers whose node slice its list
+  // can touch (cfg3, N = 9 999, 4 teams per SM: 30.5 / 31.6 / 43.7 ms for C = 1 / 2 / 4,
+  // tools/sweep_teams_stage.sh): what bounds a big tree is the producer, which pays one table round trip
+  // per group.  Kept as a tested knob.
   int C = 1;
   if (const char* e = getenv("RP_CONSUMERS")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) C = v; }
   g.consumers = C;
@@ -1179,9 +1240,16 @@ int compute_geometry(const rp_db* db, DeviceCtx* dc) {
                      "n_nodes=%d needs %zu B of shared memory per read (> %zu B per CTA); trees beyond ~54k nodes "
                      "are not supported by the shared-memory accumulator",
                      db->desc.n_nodes, g.per_warp_bytes, optin);
-  const int max_teams_cta = kMaxThreads / (32 * (1 + C));
+  const int max_teams_cta = max_threads_for(C) / (32 * (1 + C));
   int max_teams_sm = 16;
   if (const char* e = getenv("RP_PAIRS_PER_SM")) max_teams_sm = std::max(1, std::min(16, atoi(e)));
+  // registers bind before shared memory does on small trees (768 threads x 80 registers fill the file):
+  // a split into several CTAs only counts for what the register file keeps resident
+  RP_CUDA_TRY(cudaSetDevice(dc->device));
+  cudaFuncAttributes fa;
+  RP_CUDA_TRY(C == 1 ? cudaFuncGetAttributes(&fa, place_kernel<1>)
+                     : C == 2 ? cudaFuncGetAttributes(&fa, place_kernel<2>) : cudaFuncGetAttributes(&fa, place_kernel<4>));
+  const int regs_sm = 65536;
   int best_total = 0, teams_cta = 1;
   for (int c = 1; c <= 8; c++) {
     const size_t budget = std::min(optin, sm_total / c - 1024);
@@ -1189,6 +1257,7 @@ int compute_geometry(const rp_db* db, DeviceCtx* dc) {
     int tpc = (int)std::min<size_t>(max_teams_cta, (budget - cta_fixed) / g.per_warp_bytes);
     if (c * tpc > max_teams_sm) tpc = max_teams_sm / c;
     if (c * tpc * (1 + C) * 32 > 2048 / 1) tpc = 2048 / (32 * (1 + C) * c);
+    while (tpc >= 1 && (long)c * (((long)tpc * (1 + C) * 32 * fa.numRegs + 511) & ~511L) > regs_sm) tpc--;
     if (tpc < 1) break;
     if (c * tpc > best_total) {
       best_total = c * tpc;
@@ -1202,6 +1271,10 @@ int compute_geometry(const rp_db* db, DeviceCtx* dc) {
   int rc = C == 1 ? geometry_for<1>(db, dc, g) : C == 2 ? geometry_for<2>(db, dc, g) : geometry_for<4>(db, dc, g);
   if (rc) return rc;
   dc->geom = g;
+  if (getenv("RP_DEBUG_GEOM"))
+    fprintf(stderr, "rappas_b200 geometry: n_pad=%d consumers=%d teams/CTA=%d CTAs/SM=%d stage=%d B team=%zu B smem/CTA=%zu B\n",
+            g.n_pad, g.consumers, g.warps_per_cta / (1 + g.consumers), g.ctas_per_sm, g.stage_bytes, g.per_warp_bytes,
+            g.smem_bytes);
   return RP_OK;
 }
 
