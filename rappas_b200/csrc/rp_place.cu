@@ -58,6 +58,7 @@ __device__ __forceinline__ float lds_f32(uint32_t a) { float v; asm volatile("ld
 __device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint2 lds_u64(uint32_t a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ uint4 lds_u128(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts_u64(uint32_t a, uint2 v) { asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(a), "r"(v.x), "r"(v.y) : "memory"); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -107,6 +108,13 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 // ------------------------------------------------------------------------------------ helpers
 // Cuckoo lookup: both candidate buckets (2 x 2 slots of 16 B) are loaded unconditionally.
 // In partitioned mode the owner partition's table is probed (peer memory over NVLink if it is remote).
+// one bucket = 2 slots = one 32 B sector: a single 256-bit load (LDG.E.256) instead of two 128-bit ones halves
+// the load-pipe work of a probe (32 lanes, 32 different sectors per instruction)
+__device__ __forceinline__ void ldg_bucket(const uint4* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
 __device__ __forceinline__ bool table_probe(const DbView& db, uint64_t key, uint64_t& meta) {
   const uint32_t m = mix_key(key);
   const int part = db.n_parts > 1 ? (int)owner_of(m, db.n_parts) : 0;
@@ -114,7 +122,9 @@ __device__ __forceinline__ bool table_probe(const DbView& db, uint64_t key, uint
   const int shift = db.bucket_shift[part];
   const uint4* p1 = table + (size_t)bucket1(m, shift) * kBucketSlots;
   const uint4* p2 = table + (size_t)bucket2(m, shift) * kBucketSlots;
-  const uint4 s0 = __ldg(p1), s1 = __ldg(p1 + 1), s2 = __ldg(p2), s3 = __ldg(p2 + 1);
+  uint4 s0, s1, s2, s3;
+  ldg_bucket(p1, s0, s1);
+  ldg_bucket(p2, s2, s3);
   const uint32_t klo = (uint32_t)key, khi = (uint32_t)(key >> 32);
   const bool h0 = s0.x == klo && s0.y == khi, h1 = s1.x == klo && s1.y == khi;
   const bool h2 = s2.x == klo && s2.y == khi, h3 = s3.x == klo && s3.y == khi;
@@ -440,21 +450,22 @@ __device__ __forceinline__ void rmw_store(uint32_t a, float s, float d, float QT
 }
 
 // Adds the staged posting blocks of a whole group into S, chunk by chunk, in window order.  Four register
-// slots (m, score, node) rotate through the descriptor list and the descriptor itself is fetched one
-// step earlier still, so no instruction of a step waits on a load issued in the same step: the loads of
-// chunk j+4 and the descriptor of chunk j+5 are issued between the S[x] load of chunk j and its
-// dependent tail.  The list is padded with idle descriptors (m = 0) for the rounds of four + look-ahead.
+// slots (m, score, node) rotate through the descriptor list and the descriptors themselves are fetched
+// earlier still, so no instruction of a step waits on a load issued in the same step: the loads of
+// chunk j+4 are issued between the S[x] load of chunk j and its dependent tail.  The list is padded with
+// idle descriptors (m = 0) for the rounds of four + look-ahead.  Every shared-memory instruction counts
+// here (the load/store pipe is shared with the producers' probes): descriptors are read two per LDS.128.
 // SLICED: this warp is one of several consumers of the read and owns the nodes [lo, lo+width) only.
-#define RP_CHUNK_STEP(M_, V_, X_, OFF_)                                                                \
+#define RP_CHUNK_STEP(M_, V_, X_, DX_, DY_, FETCH_)                                                    \
   {                                                                                                    \
     const uint32_t a_ = s_base + 4 * X_;                                                               \
     const uint32_t p_ = SLICED ? (uint32_t)(lane < M_ && X_ - lo < width) : (uint32_t)(lane < M_);     \
     const float s_ = rmw_load(a_, p_);                                                                 \
     const float d_ = __fsub_rn(V_, T);                                                                 \
-    M_ = dn.y;                                                                                         \
-    V_ = lds_f32(dn.x + lane4);                                                                        \
-    X_ = lds_u16(dn.x + 4 * dn.y + lane2);                                                             \
-    dn = lds_u64(dp + OFF_);                                                                           \
+    M_ = DY_;                                                                                          \
+    V_ = lds_f32(DX_ + lane4);                                                                         \
+    X_ = lds_u16(DX_ + 4 * DY_ + lane2);                                                               \
+    FETCH_                                                                                             \
     rmw_store(a_, s_, d_, QT0, p_);                                                                    \
   }
 template <bool SLICED>
@@ -462,20 +473,22 @@ __device__ __forceinline__ void accumulate_chunks(float* __restrict__ S, uint32_
                                                   int lane, uint32_t lo, uint32_t width) {
   const uint32_t lane4 = lane * 4, lane2 = lane * 2;
   const uint32_t s_base = smem_u32(S);
-  const uint2 d0 = lds_u64(dl), d1 = lds_u64(dl + 8), d2 = lds_u64(dl + 16), d3 = lds_u64(dl + 24);
-  uint2 dn = lds_u64(dl + 32);
-  float v0 = lds_f32(d0.x + lane4), v1 = lds_f32(d1.x + lane4), v2 = lds_f32(d2.x + lane4), v3 = lds_f32(d3.x + lane4);
-  uint32_t x0 = lds_u16(d0.x + 4 * d0.y + lane2), x1 = lds_u16(d1.x + 4 * d1.y + lane2);
-  uint32_t x2 = lds_u16(d2.x + 4 * d2.y + lane2), x3 = lds_u16(d3.x + 4 * d3.y + lane2);
-  uint32_t m0 = d0.y, m1 = d1.y, m2 = d2.y, m3 = d3.y;
-  uint32_t dp = dl + 40;  // descriptor j+5 of the round's first chunk
-  const uint32_t dend = dl + 40 + 8 * n_chunks;
+  // descriptors travel in pairs (one LDS.128 per two chunks; the lists are 16 B aligned): e = chunks j+4, j+5
+  // of the round, f = chunks j+6, j+7, each fetched two steps before its first use
+  const uint4 d01 = lds_u128(dl), d23 = lds_u128(dl + 16);
+  uint4 e = lds_u128(dl + 32), f;
+  float v0 = lds_f32(d01.x + lane4), v1 = lds_f32(d01.z + lane4), v2 = lds_f32(d23.x + lane4), v3 = lds_f32(d23.z + lane4);
+  uint32_t x0 = lds_u16(d01.x + 4 * d01.y + lane2), x1 = lds_u16(d01.z + 4 * d01.w + lane2);
+  uint32_t x2 = lds_u16(d23.x + 4 * d23.y + lane2), x3 = lds_u16(d23.z + 4 * d23.w + lane2);
+  uint32_t m0 = d01.y, m1 = d01.w, m2 = d23.y, m3 = d23.w;
+  uint32_t dp = dl + 48;  // descriptors j+6, j+7 of the round's first chunk
+  const uint32_t dend = dl + 48 + 8 * n_chunks;
 #pragma unroll 1
   for (; dp < dend; dp += 32) {
-    RP_CHUNK_STEP(m0, v0, x0, 0)
-    RP_CHUNK_STEP(m1, v1, x1, 8)
-    RP_CHUNK_STEP(m2, v2, x2, 16)
-    RP_CHUNK_STEP(m3, v3, x3, 24)
+    RP_CHUNK_STEP(m0, v0, x0, e.x, e.y, f = lds_u128(dp);)
+    RP_CHUNK_STEP(m1, v1, x1, e.z, e.w, )
+    RP_CHUNK_STEP(m2, v2, x2, f.x, f.y, e = lds_u128(dp + 16);)
+    RP_CHUNK_STEP(m3, v3, x3, f.z, f.w, )
   }
   __syncwarp();
 }
@@ -591,7 +604,8 @@ __device__ __forceinline__ void probe_issue(const DbView& db, uint64_t key, bool
     const int shift = db.bucket_shift[part];
     const uint4* p1 = table + (size_t)bucket1(m, shift) * kBucketSlots;
     const uint4* p2 = table + (size_t)bucket2(m, shift) * kBucketSlots;
-    io.s0 = __ldg(p1); io.s1 = __ldg(p1 + 1); io.s2 = __ldg(p2); io.s3 = __ldg(p2 + 1);
+    ldg_bucket(p1, io.s0, io.s1);
+    ldg_bucket(p2, io.s2, io.s3);
   }
 }
 __device__ __forceinline__ bool probe_resolve(const ProbeIO& io, uint64_t& meta) {
@@ -878,7 +892,7 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
             left -= m;
           }
         }
-        if (lane < 8)  // idle descriptors behind the list: the consumer works in rounds of 4 and looks 4 ahead
+        if (lane < 12)  // idle descriptors behind the list: the consumer works in rounds of 4 and looks 8 ahead
           sts_u64(dl0 + 8 * (n_chunks + lane), make_uint2(stage0, 0u));
       } else {
 #pragma unroll
@@ -893,7 +907,7 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
               left -= m;
             }
           }
-          if (lane < 8) sts_u64(dlc + 8 * (((uint32_t)(rtot >> (13 * c)) & 0x1FFFu) + lane), make_uint2(stage0, 0u));
+          if (lane < 12) sts_u64(dlc + 8 * (((uint32_t)(rtot >> (13 * c)) & 0x1FFFu) + lane), make_uint2(stage0, 0u));
         }
       }
     }
@@ -1212,7 +1226,7 @@ int compute_geometry(const rp_db* db, DeviceCtx* dc) {
   stage = std::max(1024L, std::min(stage, 32768L - 128));
   stage = (stage + 127) & ~127L;
   auto team_bytes = [&](long st, int C) {
-    const size_t chunks = (32 + st / kSubBlockBytes + 9 + 1) & ~(size_t)1;  // per window + per extra sub-block + 8 idle
+    const size_t chunks = (32 + st / kSubBlockBytes + 13 + 1) & ~(size_t)1;  // per window + per extra sub-block + 12 idle
     return (64 + kStages * (size_t)kStageMetaBytes + kStages * 8 * chunks * C + 4 * (size_t)(g.n_pad + 32) +
             kStages * (size_t)st + (C > 1 ? (size_t)C * 264 : 0) + 127) & ~(size_t)127;
   };
@@ -1233,7 +1247,7 @@ int compute_geometry(const rp_db* db, DeviceCtx* dc) {
   if (const char* e = getenv("RP_CONSUMERS")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) C = v; }
   g.consumers = C;
   g.stage_bytes = (int)stage;
-  g.max_chunks = (32 + g.stage_bytes / kSubBlockBytes + 9 + 1) & ~1;  // even: S stays 16 B aligned behind the lists
+  g.max_chunks = (32 + g.stage_bytes / kSubBlockBytes + 13 + 1) & ~1;  // even: S stays 16 B aligned behind the lists
   g.per_warp_bytes = team_bytes(stage, C);
   if (cta_fixed + g.per_warp_bytes > optin)
     return set_error(RP_E_UNSUPPORTED,
