@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--no-ambiguity", action="store_true", help="experiment: generate the reads without IUPAC / N characters")
     ap.add_argument("--partitioned", action="store_true",
                     help="hash-partition the DB over the ranks (peer memory over NVLink) instead of replicating it")
+    ap.add_argument("--replicate-table", action="store_true",
+                    help="with --partitioned: partition only the posting blocks, keep the whole table on every GPU")
     return ap.parse_args()
 
 
@@ -210,7 +212,7 @@ def main():
     rb = synth.make_reads(db, n_reads, w.read_len, seed=1042 + w.index + 7919 * rank, iupac_rate=w.iupac_rate,
                           n_rate=w.n_rate)
     if args.partitioned and world > 1:
-        gdb = R.Database.from_synth_partitioned_dist(db, device=local_rank)
+        gdb = R.Database.from_synth_partitioned_dist(db, device=local_rank, replicate_table=args.replicate_table)
     else:
         gdb = R.Database.from_synth(db, devices=(local_rank,))
     cfg = _abi.place_cfg()
@@ -334,7 +336,9 @@ def main():
         "config": {"workload": w.name, "alphabet": "nucl" if w.alphabet == 0 else "amino", "k": w.k,
                    "n_nodes": w.n_nodes, "n_keys": db.n_keys, "n_postings": db.n_postings,
                    "reads_per_gpu": n, "read_len": w.read_len, "keep_at_most": K, "keep_factor": 0.01,
-                   "db_layout": ("hash-partitioned over the GPUs (peer memory over NVLink), reads sharded, no collective"
+                   "db_layout": (("postings hash-partitioned over the GPUs, table replicated (gathers over NVLink peer memory), "
+                                  "reads sharded, no collective") if args.partitioned and world > 1 and args.replicate_table else
+                                 "hash-partitioned over the GPUs (peer memory over NVLink), reads sharded, no collective"
                                  if args.partitioned and world > 1 else "replicated per GPU, reads sharded, no collective"),
                    "l2_policy": "inputs larger than L2 (reads+DB+outputs %d MB per step vs 126 MB)"
                                 % ((rb.seq.nbytes + tbytes + bbytes + n * (K * 14 + 24)) >> 20)},

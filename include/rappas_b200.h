@@ -110,6 +110,10 @@ uint64_t rp_pack_kmer(int32_t alphabet, const uint8_t* states, int32_t k);
  *                       of the keys and their postings (DBs > one GPU's HBM); the distinct devices
  *                       peer-map each other's memory and each places its slice of the reads, probing
  *                       and gathering from the owner's HBM over NVLink.  Same rows as replicated.
+ * partitioned = 2       only the posting blocks are partitioned (the bulk of a DB); every partition's device
+ *                       also holds the WHOLE table, so probes are local loads and only the posting gathers
+ *                       (bulk copies, overlapped) cross NVLink.  For DBs whose table fits beside 1/n of the
+ *                       postings.  Same rows again.
  */
 int  rp_db_load(const rp_db_desc* desc, const uint64_t* keys, const uint64_t* offsets,
                 const uint16_t* post_node, const float* post_score,
@@ -123,11 +127,12 @@ int  rp_db_save_file(const char* path, const rp_db_desc* desc, const uint64_t* k
  * only its partition on `device` and gets a RP_PART_BLOB_BYTES blob (CUDA IPC handles + sizes); the ranks
  * exchange the blobs (e.g. torch.distributed all_gather) and each calls rp_db_attach_partitions with all
  * n_parts blobs in partition order, which maps the other GPUs' partitions into this process.  After
- * that the handle behaves like rp_db_load(partitioned = 1) restricted to this rank's device. */
+ * that the handle behaves like rp_db_load(partitioned = 1) restricted to this rank's device
+ * (replicate_table != 0: like partitioned = 2, this rank building the whole table and its own blocks). */
 #define RP_PART_BLOB_BYTES 152
 int  rp_db_load_partition(const rp_db_desc* desc, const uint64_t* keys, const uint64_t* offsets,
                           const uint16_t* post_node, const float* post_score, int32_t device, int32_t part,
-                          int32_t n_parts, uint8_t* blob_out, rp_db** out);
+                          int32_t n_parts, int32_t replicate_table, uint8_t* blob_out, rp_db** out);
 int  rp_db_attach_partitions(rp_db* db, const uint8_t* blobs, int32_t n_parts);
 /* owner partition (0..n_parts-1) of each k-mer code, as rp_db_load / the kernels compute it */
 int  rp_partition_of_keys(int32_t alphabet, int32_t k, const uint64_t* keys, uint64_t n_keys, int32_t n_parts,

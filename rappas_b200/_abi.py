@@ -48,7 +48,7 @@ PROTOTYPES = {
     "db_load": (C.c_int, [C.POINTER(RpDbDesc), _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.POINTER(_P)]),
     "db_load_file": (C.c_int, [C.c_char_p, _P, C.c_int32, C.c_int32, C.POINTER(_P)]),
     "db_save_file": (C.c_int, [C.c_char_p, C.POINTER(RpDbDesc), _P, _P, _P, _P]),
-    "db_load_partition": (C.c_int, [C.POINTER(RpDbDesc), _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.POINTER(_P)]),
+    "db_load_partition": (C.c_int, [C.POINTER(RpDbDesc), _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.POINTER(_P)]),
     "db_attach_partitions": (C.c_int, [_P, _P, C.c_int32]),
     "partition_of_keys": (C.c_int, [C.c_int32, C.c_int32, _P, C.c_uint64, C.c_int32, _P]),
     "db_free": (None, [_P]),

@@ -98,7 +98,8 @@ struct DbView {
   const uint4* table[kMaxParts];      // [n_buckets][2] slots of partition p
   const uint8_t* blocks[kMaxParts];   // posting blocks of partition p
   int bucket_shift[kMaxParts];        // 32 - log2(n_buckets)
-  int n_parts;
+  int n_parts;      // partitions of the posting blocks
+  int table_parts;  // partitions of the table: n_parts, or 1 when every device holds the whole table (slot 0)
   int alphabet, k, bits, n_nodes, max_amb;
   float T, Tlin;
 };
@@ -165,6 +166,7 @@ struct DeviceCtx {
   int sm_count = 0;
   size_t smem_optin = 0;
   std::vector<int> parts;  // indices into rp_db::parts this device's kernels use (1 if replicated, all if partitioned)
+  int local_part = 0;      // a partition resident on this device
   LaunchGeom geom;
   StreamCtx sc[2];  // double buffering for host-buffer calls (rp_place_batch)
   StreamCtx sc_dev; // scheduler counter + scratch of device-buffer calls (rp_place_batch_device)
@@ -190,6 +192,7 @@ struct rp_db {
   uint64_t block_bytes = 0;
   uint64_t max_block_bytes = 0;
   int partitioned = 0;
+  bool table_replicated = false;  // partitioned postings, but the whole table on every partition's device
   rp::AlphabetTables alpha{};
   std::vector<rp::DeviceCtx*> dev;
   std::atomic<double> last_kernel_ms{0.0};

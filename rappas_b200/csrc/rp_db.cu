@@ -91,11 +91,17 @@ DbView make_db_view(const rp_db* db, const DeviceCtx* dc) {
   DbView v;
   memset(&v, 0, sizeof v);
   v.n_parts = (int)dc->parts.size();
+  v.table_parts = db->table_replicated ? 1 : v.n_parts;
   for (int i = 0; i < v.n_parts; i++) {
     const Partition& pt = db->parts[dc->parts[i]];
     v.table[i] = pt.d_table;
     v.blocks[i] = pt.d_blocks;
     v.bucket_shift[i] = 32 - log2_u64(pt.n_buckets);
+  }
+  if (db->table_replicated) {  // every partition's device holds the whole table: probe the local copy
+    const Partition& pt = db->parts[dc->local_part];
+    v.table[0] = pt.d_table;
+    v.bucket_shift[0] = 32 - log2_u64(pt.n_buckets);
   }
   v.alphabet = db->desc.alphabet;
   v.k = db->desc.k;
@@ -146,10 +152,15 @@ static bool cuckoo_insert(std::vector<uint64_t>& tab, int shift, uint64_t key, u
 }
 
 // Builds the image of the keys sel[0..n_sel) (all keys if sel == nullptr) as partition `part`.
+// owners != nullptr (with sel == nullptr): the table holds ALL keys, key i pointing into the posting blocks
+// of partition owners[i] (offsets counted per partition, in key order, so every builder agrees on them),
+// and only the blocks of partition `part` are materialised -- the layout with a replicated table.
 static int build_image(const rp_db_desc* d, const uint64_t* keys, const uint64_t* offsets, const uint16_t* post_node,
-                       const float* post_score, const uint64_t* sel, uint64_t n_sel, int part, HostImage* img) {
+                       const float* post_score, const uint64_t* sel, uint64_t n_sel, int part, HostImage* img,
+                       const uint8_t* owners = nullptr) {
   const uint64_t nk = sel ? n_sel : d->n_keys;
   auto key_at = [&](uint64_t j) { return sel ? sel[j] : j; };
+  auto owner_at = [&](uint64_t j) { return owners ? (int)owners[key_at(j)] : part; };
   if (offsets && d->n_keys && offsets[d->n_keys] != d->n_postings)
     return set_error(RP_E_INVALID, "offsets[n_keys]=%llu != n_postings=%llu", (unsigned long long)offsets[d->n_keys],
                      (unsigned long long)d->n_postings);
@@ -161,19 +172,22 @@ static int build_image(const rp_db_desc* d, const uint64_t* keys, const uint64_t
   const uint64_t n_slots = nb * kBucketSlots;
   img->table.assign(2 * n_slots, 0);
   for (uint64_t i = 0; i < n_slots; i++) img->table[2 * i] = kEmptyKey;
-  // block offsets (32 B units)
+  // block offsets (32 B units) of key j inside its owner partition's blocks
   std::vector<uint64_t> boff(nk + 1, 0);
+  uint64_t run[kMaxParts] = {0};
   uint64_t max_bb = 0;
   for (uint64_t j = 0; j < nk; j++) {
     const uint64_t i = key_at(j);
     if (offsets[i + 1] < offsets[i]) return set_error(RP_E_INVALID, "offsets not monotone at key %llu", (unsigned long long)i);
     uint64_t P = offsets[i + 1] - offsets[i];
     if (P > 65535) return set_error(RP_E_INVALID, "key %llu has %llu postings (> 65535)", (unsigned long long)i, (unsigned long long)P);
-    boff[j + 1] = boff[j] + block_bytes_for(P) / kBlockAlign;
+    uint64_t& r = run[owners ? owner_at(j) : 0];
+    boff[j] = r;
+    r += block_bytes_for(P) / kBlockAlign;
+    if (r > kMetaOffMask) return set_error(RP_E_INVALID, "posting blocks exceed 2^37 * 32 B");
     max_bb = std::max(max_bb, block_bytes_for(P));
   }
-  if (boff[nk] > kMetaOffMask) return set_error(RP_E_INVALID, "posting blocks exceed 2^37 * 32 B");
-  img->block_bytes = boff[nk] * kBlockAlign;
+  img->block_bytes = run[owners ? part : 0] * kBlockAlign;
   img->max_block_bytes = max_bb;
   img->blocks = (uint8_t*)calloc(img->block_bytes ? img->block_bytes : 32, 1);
   if (!img->blocks) return set_error(RP_E_NOMEM, "cannot allocate %llu B for posting blocks", (unsigned long long)img->block_bytes);
@@ -205,8 +219,9 @@ static int build_image(const rp_db_desc* d, const uint64_t* keys, const uint64_t
         for (uint64_t p = 1; p < P; p++)
           if (tmp[p].first == tmp[p - 1].first) { err = 2; return; }  // one value per (k-mer,node): CustomHash_v4:76-89
       }
+      const int own = owner_at(j);
       uint8_t* blk = img->blocks + boff[j] * kBlockAlign;
-      for (uint64_t base = 0; base < P; base += kSubBlock) {
+      for (uint64_t base = 0; base < P && own == part; base += kSubBlock) {
         uint64_t m = std::min<uint64_t>(kSubBlock, P - base);
         float* sc = (float*)(blk + (base / kSubBlock) * kSubBlockBytes);
         uint16_t* nd = (uint16_t*)((uint8_t*)sc + 4 * m);
@@ -217,7 +232,7 @@ static int build_image(const rp_db_desc* d, const uint64_t* keys, const uint64_t
       // node range of the list in sixteenths of the padded tree (tmp is sorted by node here)
       const uint64_t n_pad = (uint64_t)padded_nodes(n_nodes);
       const uint64_t qmin = P ? (uint64_t)tmp[0].first * 16 / n_pad : 0, qmax = P ? (uint64_t)tmp[P - 1].first * 16 / n_pad : 0;
-      const uint64_t meta = ((uint64_t)part << kMetaPartShift) | (qmax << kMetaQmaxShift) | (qmin << kMetaQminShift) |
+      const uint64_t meta = ((uint64_t)own << kMetaPartShift) | (qmax << kMetaQmaxShift) | (qmin << kMetaQminShift) |
                             (boff[j] << 16) | P;
       const uint32_t m32 = mix_key(key);
       const uint32_t bk[2] = {bucket1(m32, shift), bucket2(m32, shift)};
@@ -342,9 +357,11 @@ int rp_db_load(const rp_db_desc* desc, const uint64_t* keys, const uint64_t* off
   const int n_parts = partitioned ? n_devices : 1;
   if (n_parts > kMaxParts) return set_error(RP_E_UNSUPPORTED, "at most %d partitions", kMaxParts);
 
+  if (partitioned < 0 || partitioned > 2) return set_error(RP_E_INVALID, "partitioned must be 0, 1 or 2");
   rp_db* db = new rp_db();
   db->desc = *desc;
   db->partitioned = partitioned ? 1 : 0;
+  db->table_replicated = partitioned == 2;
   build_alphabet_tables(desc->alphabet, &db->alpha);
   auto fail = [&](int code) { rp_db_free(db); return code; };
   auto upload = [&](const HostImage& img, int device) -> int {
@@ -382,11 +399,15 @@ int rp_db_load(const rp_db_desc* desc, const uint64_t* keys, const uint64_t* off
     // keys go to partition owner_of(mix(planar key)): the kernel recomputes the same owner from the key
     const int bits = alphabet_bits(desc->alphabet);
     std::vector<std::vector<uint64_t>> sel(n_parts);
-    for (uint64_t i = 0; i < desc->n_keys; i++)
-      sel[owner_of(mix_key(planar_from_code(keys[i], bits, desc->k)), n_parts)].push_back(i);
+    std::vector<uint8_t> owners(desc->n_keys);
+    for (uint64_t i = 0; i < desc->n_keys; i++) {
+      owners[i] = (uint8_t)owner_of(mix_key(planar_from_code(keys[i], bits, desc->k)), n_parts);
+      sel[owners[i]].push_back(i);
+    }
     for (int p = 0; p < n_parts; p++) {
       HostImage img;
-      rc = build_image(desc, keys, offsets, post_node, post_score, sel[p].data(), sel[p].size(), p, &img);
+      rc = partitioned == 2 ? build_image(desc, keys, offsets, post_node, post_score, nullptr, 0, p, &img, owners.data())
+                            : build_image(desc, keys, offsets, post_node, post_score, sel[p].data(), sel[p].size(), p, &img);
       if (rc) return fail(rc);
       db->n_buckets = std::max(db->n_buckets, img.n_buckets);
       db->block_bytes += img.block_bytes;
@@ -415,6 +436,9 @@ int rp_db_load(const rp_db_desc* desc, const uint64_t* keys, const uint64_t* off
     dc->device = exec[i];
     if (partitioned) for (int p = 0; p < n_parts; p++) dc->parts.push_back(p);
     else dc->parts.push_back((int)i);
+    if (partitioned)  // a partition resident on this device (its table is the one this device probes when replicated)
+      for (int p = n_parts - 1; p >= 0; p--)
+        if (devices[p] == exec[i]) dc->local_part = p;
     cudaDeviceProp prop;
     cudaError_t e = cudaSetDevice(dc->device);
     if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, dc->device);
@@ -439,7 +463,7 @@ static_assert(sizeof(PartBlob) == RP_PART_BLOB_BYTES, "blob layout");
 
 int rp_db_load_partition(const rp_db_desc* desc, const uint64_t* keys, const uint64_t* offsets,
                          const uint16_t* post_node, const float* post_score, int32_t device, int32_t part,
-                         int32_t n_parts, uint8_t* blob_out, rp_db** out) {
+                         int32_t n_parts, int32_t replicate_table, uint8_t* blob_out, rp_db** out) {
   int rc = check_desc(desc);
   if (rc) return rc;
   if (!out || !blob_out) return set_error(RP_E_INVALID, "NULL argument");
@@ -450,14 +474,19 @@ int rp_db_load_partition(const rp_db_desc* desc, const uint64_t* keys, const uin
   if (!desc->n_keys) offsets = zero_off;
   const int bits = alphabet_bits(desc->alphabet);
   std::vector<uint64_t> sel;
-  for (uint64_t i = 0; i < desc->n_keys; i++)
-    if ((int)owner_of(mix_key(planar_from_code(keys[i], bits, desc->k)), n_parts) == part) sel.push_back(i);
+  std::vector<uint8_t> owners(desc->n_keys);
+  for (uint64_t i = 0; i < desc->n_keys; i++) {
+    owners[i] = (uint8_t)owner_of(mix_key(planar_from_code(keys[i], bits, desc->k)), n_parts);
+    if ((int)owners[i] == part) sel.push_back(i);
+  }
   HostImage img;
-  rc = build_image(desc, keys, offsets, post_node, post_score, sel.data(), sel.size(), part, &img);
+  rc = replicate_table ? build_image(desc, keys, offsets, post_node, post_score, nullptr, 0, part, &img, owners.data())
+                       : build_image(desc, keys, offsets, post_node, post_score, sel.data(), sel.size(), part, &img);
   if (rc) return rc;
   rp_db* db = new rp_db();
   db->desc = *desc;
   db->partitioned = 2;  // 2 = waiting for rp_db_attach_partitions
+  db->table_replicated = replicate_table != 0;
   build_alphabet_tables(desc->alphabet, &db->alpha);
   db->parts.resize(n_parts);
   Partition& pt = db->parts[part];
@@ -487,6 +516,7 @@ int rp_db_load_partition(const rp_db_desc* desc, const uint64_t* keys, const uin
   memcpy(blob_out, &blob, sizeof blob);
   DeviceCtx* dc = new DeviceCtx();
   dc->device = device;
+  dc->local_part = part;
   db->dev.push_back(dc);
   *out = db;
   return RP_OK;

@@ -117,7 +117,7 @@ __device__ __forceinline__ void ldg_bucket(const uint4* p, uint4& a, uint4& b) {
 }
 __device__ __forceinline__ bool table_probe(const DbView& db, uint64_t key, uint64_t& meta) {
   const uint32_t m = mix_key(key);
-  const int part = db.n_parts > 1 ? (int)owner_of(m, db.n_parts) : 0;
+  const int part = db.table_parts > 1 ? (int)owner_of(m, db.table_parts) : 0;
   const uint4* table = db.table[part];
   const int shift = db.bucket_shift[part];
   const uint4* p1 = table + (size_t)bucket1(m, shift) * kBucketSlots;
@@ -599,7 +599,7 @@ __device__ __forceinline__ void probe_issue(const DbView& db, uint64_t key, bool
   io.s0 = io.s1 = io.s2 = io.s3 = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u);  // the empty key never matches
   if (active) {
     const uint32_t m = mix_key(key);
-    const int part = db.n_parts > 1 ? (int)owner_of(m, db.n_parts) : 0;
+    const int part = db.table_parts > 1 ? (int)owner_of(m, db.table_parts) : 0;
     const uint4* table = db.table[part];
     const int shift = db.bucket_shift[part];
     const uint4* p1 = table + (size_t)bucket1(m, shift) * kBucketSlots;

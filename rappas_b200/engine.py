@@ -34,18 +34,20 @@ class Database:
         dev = np.ascontiguousarray(devices, dtype=np.int32)
         h = C.c_void_p()
         check(fn["db_load"](C.byref(desc), _abi.ptr(keys), _abi.ptr(offsets), _abi.ptr(post_node),
-                            _abi.ptr(post_score), _abi.ptr(dev), dev.shape[0], int(bool(partitioned)), C.byref(h)))
+                            _abi.ptr(post_score), _abi.ptr(dev), dev.shape[0], int(partitioned), C.byref(h)))
         return cls(h, desc)
 
     @classmethod
     def from_synth(cls, db, devices=(0,), partitioned=False):
-        """partitioned=True: every entry of `devices` holds one hash partition of the DB (an entry may repeat a
-        device); the kernels of every distinct device reach all partitions through peer-mapped memory."""
+        """partitioned=True (1): every entry of `devices` holds one hash partition of the DB (an entry may repeat a
+        device); the kernels of every distinct device reach all partitions through peer-mapped memory.
+        partitioned=2: only the posting blocks are partitioned; every partition's device holds the whole table,
+        so probes stay local and only the bulk gathers cross NVLink."""
         return cls.from_arrays(db.alphabet, db.k, db.n_nodes, db.thr_lin, db.thr_log10, db.keys, db.offsets,
                                db.post_node, db.post_score, devices=devices, partitioned=partitioned)
 
     @classmethod
-    def from_synth_partitioned_dist(cls, db, device, group=None):
+    def from_synth_partitioned_dist(cls, db, device, group=None, replicate_table=False):
         """One process per GPU: this rank uploads only its hash partition of `db` to `device`, the ranks
         all_gather the CUDA-IPC blobs over torch.distributed, and every rank maps the others' partitions
         (peer memory over NVLink).  Any backend works for the 152-byte exchange."""
@@ -62,7 +64,8 @@ class Database:
         blob = np.zeros(_abi.RP_PART_BLOB_BYTES, np.uint8)
         h = C.c_void_p()
         check(fn["db_load_partition"](C.byref(desc), _abi.ptr(keys), _abi.ptr(offsets), _abi.ptr(post_node),
-                                      _abi.ptr(post_score), int(device), rank, world, _abi.ptr(blob), C.byref(h)))
+                                      _abi.ptr(post_score), int(device), rank, world, int(bool(replicate_table)), _abi.ptr(blob),
+                                      C.byref(h)))
         self = cls(h, desc)
         mine = torch.from_numpy(blob)
         if dist.get_backend(group) == "nccl":
@@ -78,7 +81,7 @@ class Database:
         fn = load()
         dev = np.ascontiguousarray(devices, dtype=np.int32)
         h = C.c_void_p()
-        check(fn["db_load_file"](str(path).encode(), _abi.ptr(dev), dev.shape[0], int(bool(partitioned)), C.byref(h)))
+        check(fn["db_load_file"](str(path).encode(), _abi.ptr(dev), dev.shape[0], int(partitioned), C.byref(h)))
         desc = _abi.RpDbDesc()
         check(fn["db_describe"](h, C.byref(desc)))
         return cls(h, desc)

@@ -15,7 +15,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, tmp):
+def _worker(rank, world, port, tmp, replicate_table):
     import torch
     import torch.distributed as dist
     import oracle_lib as O
@@ -28,7 +28,7 @@ def _worker(rank, world, port, tmp):
     try:
         db = synth.make_db(0, 10, 1999, n_keys=150000, mean_postings=24, seed=7)
         rb = synth.make_reads(db, 4000, (50, 300), seed=100 + rank, n_rate=0.002)
-        g = R.Database.from_synth_partitioned_dist(db, device=rank)
+        g = R.Database.from_synth_partitioned_dist(db, device=rank, replicate_table=replicate_table)
         out = g.place(rb)
         oo = O.OracleDB(db).place(rb)
         parity.assert_placements_equal(out, oo, 7, oo["counts"][:, _abi.CNT_AMBIG] > 0)
@@ -39,11 +39,12 @@ def _worker(rank, world, port, tmp):
         dist.destroy_process_group()
 
 
-def test_partitioned_db_one_process_per_gpu(tmp_path):
+@pytest.mark.parametrize("replicate_table", [False, True], ids=["table+postings", "postings-only"])
+def test_partitioned_db_one_process_per_gpu(tmp_path, replicate_table):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), replicate_table), nprocs=world, join=True)
     assert all((tmp_path / ("ok%d" % r)).exists() for r in range(world))

@@ -222,14 +222,16 @@ def test_multi_device_in_process_matches_single_device():
         assert np.array_equal(a[key], b[key], equal_nan=True), key
 
 
+@pytest.mark.parametrize("layout", [1, 2], ids=["table+postings", "postings-only"])
 @pytest.mark.parametrize("n_parts", [2, 3, 8])
-def test_hash_partitioned_db_on_one_device(n_parts):
+def test_hash_partitioned_db_on_one_device(n_parts, layout):
     """Partitioned mode with every partition in the same HBM (how a 1-GPU box exercises it): same rows,
-    same k-mer hits and same per-node scores as the replicated DB and the oracle."""
+    same k-mer hits and same per-node scores as the replicated DB and the oracle.  layout 1 partitions the
+    table with the postings, layout 2 keeps the whole table beside every partition of the postings."""
     import rappas_b200 as R
     db = synth.make_db(0, 10, 1999, n_keys=100000, mean_postings=24, seed=7)
     rb = synth.make_reads(db, 1500, (50, 400), seed=8, iupac_rate=0.005, n_rate=0.002)
-    part = R.Database.from_synth(db, devices=(0,) * n_parts, partitioned=True)
+    part = R.Database.from_synth(db, devices=(0,) * n_parts, partitioned=layout)
     o = O.OracleDB(db)
     parity.assert_extract_equal(part.extract(rb), o.extract(rb))
     oo = o.place(rb)
@@ -240,7 +242,8 @@ def test_hash_partitioned_db_on_one_device(n_parts):
     assert bb > 0 and tb >= n_parts * 32 * 32
 
 
-def test_hash_partitioned_db_over_peer_memory():
+@pytest.mark.parametrize("layout", [1, 2], ids=["table+postings", "postings-only"])
+def test_hash_partitioned_db_over_peer_memory(layout):
     """One partition per GPU; every GPU places its slice of the reads, probing and gathering from the
     owner's HBM over NVLink (peer-mapped pointers, no collective)."""
     import rappas_b200 as R
@@ -249,7 +252,7 @@ def test_hash_partitioned_db_over_peer_memory():
         pytest.skip("needs >= 2 GPUs")
     db = synth.make_db(0, 10, 1999, n_keys=200000, mean_postings=32, seed=7)
     rb = synth.make_reads(db, 30001, 150, seed=8, n_rate=0.002)
-    part = R.Database.from_synth(db, devices=tuple(range(nd)), partitioned=True)
+    part = R.Database.from_synth(db, devices=tuple(range(nd)), partitioned=layout)
     one = R.Database.from_synth(db, devices=(0,))
     a, b = one.place(rb), part.place(rb)
     for key in a:

@@ -1,8 +1,8 @@
-export RP_DEBUG_GEOM=1
-run() { # consumers pairs
-  RP_CONSUMERS=$1 RP_PAIRS_PER_SM=$2 timeout 300 python bench.py --config 2 --steps 4 --warmup 3 --no-cpu --no-e2e 2>gpurun_out/geom.err | python -c "
-import sys,json
-for l in sys.stdin:
-    j=json.loads(l); print('consumers=$1 teams<=$2', 'ms=%.3f'%j['ms_per_step'], 'reads/s=%.3e'%j['value'])
-"; grep -m1 geometry gpurun_out/geom.err | cut -c20-130; }
-run 1 6; run 2 6; run 1 4; run 2 4; run 4 4; run 1 3; run 4 3
+i=0
+for extra in "" "--replicate-table"; do
+i=$((i+1))
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2957$i bench.py --gpus 2 --partitioned $extra --steps 5 --warmup 3 --no-cpu > gpurun_out/bench_v10_n2_partitioned_layout$i.json 2>gpurun_out/part$i.err
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 2958$i bench.py --gpus 2 --config 5 --reads 200000 --partitioned $extra --steps 3 --warmup 2 --no-cpu --no-e2e > gpurun_out/bench_v10_cfg5_n2_partitioned_layout$i.json 2>gpurun_out/part5$i.err
+done
+grep -h -o '"value": [0-9.e+]*, "unit": "reads/s", "n_gpus": 2[^}]*"ms_per_step": [0-9.]*' gpurun_out/bench_v10_*n2_partitioned_layout*.json
+tail -3 gpurun_out/part*.err | cut -c1-200
