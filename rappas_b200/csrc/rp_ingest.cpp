@@ -10,14 +10,17 @@
 #include <fcntl.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <time.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <charconv>
 #include <string>
-#include <unordered_map>
+#include <thread>
 #include <vector>
 
 #include "../../include/rappas_b200.h"
@@ -27,125 +30,282 @@ int set_error(int code, const char* fmt, ...);
 }
 using rp::set_error;
 
+// byte buffer that is NOT zero-filled when sized (the parallel gathers overwrite every byte; a vector's
+// resize would first memset hundreds of MB)
+struct RawBytes {
+  uint8_t* p = nullptr;
+  size_t n = 0;
+  RawBytes() = default;
+  RawBytes(const RawBytes&) = delete;
+  RawBytes& operator=(const RawBytes&) = delete;
+  ~RawBytes() { free(p); }
+  bool resize(size_t bytes) { free(p); p = (uint8_t*)malloc(bytes ? bytes : 1); n = p ? bytes : 0; return p != nullptr; }
+  uint8_t* data() { return p; }
+  const uint8_t* data() const { return p; }
+  size_t size() const { return n; }
+  uint8_t operator[](size_t i) const { return p[i]; }
+};
+
 struct rp_reads {
   // every FASTA record, in file order
-  std::vector<uint8_t> hdr;        // headers (first line without '>'), concatenated
+  RawBytes hdr;                    // headers (first line without '>'), concatenated
   std::vector<uint64_t> hdr_off;   // [n_records + 1]
   std::vector<uint32_t> unique_of; // record -> index of its exact sequence among the unique ones
   std::vector<uint32_t> group_of;  // record -> id of its gap-stripped sequence (the reference's MD5 key)
   // distinct exact sequences (gaps kept: Main_PLACEMENT_v07.java:195), in order of first appearance
-  std::vector<uint8_t> seq;
+  RawBytes seq;
   std::vector<uint64_t> seq_off;   // [n_unique + 1]
   uint32_t n_groups = 0;
 };
 
 namespace {
 
-struct Slice {
-  const uint8_t* p;
-  size_t n;
-  bool operator==(const Slice& o) const { return n == o.n && (n == 0 || memcmp(p, o.p, n) == 0); }
-};
-struct SliceHash {
-  size_t operator()(const Slice& s) const {  // FNV-1a 64; equality is checked on the bytes, so this only buckets
-    uint64_t h = 1469598103934665603ull;
-    for (size_t i = 0; i < s.n; i++) { h ^= s.p[i]; h *= 1099511628211ull; }
-    return (size_t)h;
-  }
-};
+unsigned host_threads(size_t work_items, size_t per_thread_min) {
+  unsigned nt = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  if (const char* e = getenv("RP_HOST_THREADS")) return (unsigned)std::max(1, std::min(64, atoi(e)));  // tests: forced
+  while (nt > 1 && work_items / nt < per_thread_min) nt--;
+  return nt;
+}
 
-// java.io.BufferedReader.readLine: a line ends at \n, \r or \r\n
+// 64-bit hash of a byte string, 8 bytes per step (it only buckets: equality is always checked on the bytes)
+inline uint64_t mix64(uint64_t x) {
+  x ^= x >> 32; x *= 0xd6e8feb86659fd93ull; x ^= x >> 32; x *= 0xd6e8feb86659fd93ull; x ^= x >> 32;
+  return x;
+}
+inline uint64_t hash_bytes(const uint8_t* p, size_t n) {
+  uint64_t h = 0x9E3779B97F4A7C15ull ^ (n * 0xff51afd7ed558ccdull);
+  size_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    uint64_t w;
+    memcpy(&w, p + i, 8);
+    h = (h ^ w) * 0x9FB21C651E98DF25ull;
+    h ^= h >> 29;
+  }
+  if (i < n) {
+    uint64_t w = 0;
+    memcpy(&w, p + i, n - i);
+    h = (h ^ w) * 0x9FB21C651E98DF25ull;
+    h ^= h >> 29;
+  }
+  return mix64(h);
+}
+
+// java.io.BufferedReader.readLine: a line ends at \n, \r or \r\n.  The scan is two memchr calls per line.
 inline size_t next_line(const uint8_t* t, size_t n, size_t pos, size_t* line_end) {
-  size_t e = pos;
-  while (e < n && t[e] != '\n' && t[e] != '\r') e++;
+  const uint8_t* nl = (const uint8_t*)memchr(t + pos, '\n', n - pos);
+  size_t e = nl ? (size_t)(nl - t) : n;
+  const uint8_t* cr = (const uint8_t*)memchr(t + pos, '\r', e - pos);
+  if (cr) e = (size_t)(cr - t);
   *line_end = e;
   if (e < n && t[e] == '\r' && e + 1 < n && t[e + 1] == '\n') return e + 2;
   return e < n ? e + 1 : n;
 }
 
-int parse(const uint8_t* t, size_t n, rp_reads* R) {
-  // pass 1: records -> (header, joined + trimmed sequence) in a scratch arena
-  std::vector<uint8_t> all_seq;
-  std::vector<uint64_t> all_off{0};
-  R->hdr_off.assign(1, 0);
+// the records of one piece of the text (a piece starts at a header line, except possibly the first)
+struct Piece {
+  std::vector<uint8_t> hdr, seq;
+  std::vector<uint32_t> hdr_len, seq_len;
+  std::vector<uint64_t> hash;      // of the joined + trimmed sequence
+  bool any_gap = false, data_before_header = false;
+};
+
+void parse_piece(const uint8_t* t, size_t begin, size_t end, Piece* P) {
   bool in_record = false;
-  size_t pos = 0;
+  size_t rec_start = 0;  // of the current record in P->seq
   auto close_record = [&]() {
     // String.trim(): strip code points <= U+0020 from both ends of the joined sequence (FASTAPointer.java:143-145)
-    size_t b = all_off.back(), e = all_seq.size();
-    while (e > b && all_seq[e - 1] <= 0x20) e--;
+    size_t b = rec_start, e = P->seq.size();
+    while (e > b && P->seq[e - 1] <= 0x20) e--;
     size_t s = b;
-    while (s < e && all_seq[s] <= 0x20) s++;
-    if (s > b) memmove(&all_seq[b], &all_seq[s], e - s);
-    all_seq.resize(b + (e - s));
-    all_off.push_back(all_seq.size());
+    while (s < e && P->seq[s] <= 0x20) s++;
+    if (s > b) memmove(&P->seq[b], &P->seq[s], e - s);
+    P->seq.resize(b + (e - s));
+    P->seq_len.push_back((uint32_t)(e - s));
+    P->hash.push_back(hash_bytes(P->seq.data() + b, e - s));
+    if (!P->any_gap && memchr(P->seq.data() + b, '-', e - s)) P->any_gap = true;
   };
-  while (pos < n) {
+  P->hdr.reserve((end - begin) / 4);
+  P->seq.reserve(end - begin);
+  size_t pos = begin;
+  while (pos < end) {
     size_t le;
-    const size_t nxt = next_line(t, n, pos, &le);
+    const size_t nxt = next_line(t, end, pos, &le);
     const uint8_t* line = t + pos;
     const size_t len = le - pos;
     pos = nxt;
     if (len == 0 || line[0] == '#') continue;  // empty and '#' lines are skipped (FASTAPointer.java:82-87)
     if (line[0] == '>') {
       if (in_record) close_record();
-      R->hdr.insert(R->hdr.end(), line + 1, line + len);
-      R->hdr_off.push_back(R->hdr.size());
+      P->hdr.insert(P->hdr.end(), line + 1, line + len);
+      P->hdr_len.push_back((uint32_t)(len - 1));
       in_record = true;
+      rec_start = P->seq.size();
       continue;
     }
-    if (!in_record) return set_error(RP_E_IO, "FASTA: sequence data before the first '>' header");
-    all_seq.insert(all_seq.end(), line, line + len);
+    if (!in_record) { P->data_before_header = true; return; }
+    P->seq.insert(P->seq.end(), line, line + len);
   }
   if (in_record) close_record();
-  const size_t nrec = R->hdr_off.size() - 1;
+}
+
+// open-addressing set of byte strings kept elsewhere: slot = {hash, id + 1}
+struct FlatSet {
+  std::vector<uint64_t> h;
+  std::vector<uint32_t> id;
+  uint64_t mask;
+  explicit FlatSet(size_t n) {
+    size_t cap = 16;
+    while (cap < 2 * n + 2) cap <<= 1;
+    h.assign(cap, 0);
+    id.assign(cap, 0);
+    mask = cap - 1;
+  }
+  // eq(id) tells whether the stored string `id` equals the probed one; returns the id found, or inserts new_id
+  template <typename Eq>
+  uint32_t find_or_insert(uint64_t hash, uint32_t new_id, Eq eq, bool* inserted) {
+    for (uint64_t i = hash & mask;; i = (i + 1) & mask) {
+      if (id[i] == 0) { h[i] = hash; id[i] = new_id + 1; *inserted = true; return new_id; }
+      if (h[i] == hash && eq(id[i] - 1)) { *inserted = false; return id[i] - 1; }
+    }
+  }
+  void prefetch(uint64_t hash) const { __builtin_prefetch(&h[hash & mask]); __builtin_prefetch(&id[hash & mask]); }
+};
+
+int parse(const uint8_t* t, size_t n, rp_reads* R) {
+  const bool dbg = getenv("RP_DEBUG_INGEST") != nullptr;
+  auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+  const double t0 = now();
+  // pass 1, parallel: the text is cut at header lines into one piece per thread; every piece yields its
+  // records (header, joined + trimmed sequence, hash of the sequence)
+  const unsigned nt = host_threads(n, 1 << 20);
+  std::vector<size_t> cut(nt + 1, n);
+  cut[0] = 0;
+  for (unsigned i = 1; i < nt; i++) {
+    // the first line start at or after i*n/nt that begins with '>'
+    size_t pos = std::max(cut[i - 1], n / nt * i);
+    size_t found = n;
+    while (pos < n) {
+      const uint8_t* g = (const uint8_t*)memchr(t + pos, '>', n - pos);
+      if (!g) break;
+      const size_t q = (size_t)(g - t);
+      if (q == 0 || t[q - 1] == '\n' || t[q - 1] == '\r') { found = q; break; }
+      pos = q + 1;
+    }
+    cut[i] = found;
+  }
+  std::vector<Piece> pieces(nt);
+  {
+    std::vector<std::thread> th;
+    for (unsigned i = 1; i < nt; i++)
+      if (cut[i] < cut[i + 1]) th.emplace_back(parse_piece, t, cut[i], cut[i + 1], &pieces[i]);
+    parse_piece(t, cut[0], cut[1], &pieces[0]);
+    for (auto& x : th) x.join();
+  }
+  const double t1 = now();
+  if (pieces[0].data_before_header) return set_error(RP_E_IO, "FASTA: sequence data before the first '>' header");
+  size_t nrec = 0, hdr_bytes = 0, seq_bytes = 0;
+  bool any_gap = false;
+  std::vector<size_t> rec0(nt + 1, 0), hdr0(nt + 1, 0), seq0(nt + 1, 0);
+  for (unsigned i = 0; i < nt; i++) {
+    nrec += pieces[i].hdr_len.size(); hdr_bytes += pieces[i].hdr.size(); seq_bytes += pieces[i].seq.size();
+    rec0[i + 1] = nrec; hdr0[i + 1] = hdr_bytes; seq0[i + 1] = seq_bytes;
+    any_gap |= pieces[i].any_gap;
+  }
   if (nrec == 0) return set_error(RP_E_IO, "No valid fasta sequences were found");  // FASTAPointer.checkSize :238-241
   if (nrec >= 0xFFFFFFFFull) return set_error(RP_E_UNSUPPORTED, "more than 2^32-2 records");
-  // pass 2: exact-sequence uniques (what is placed) and gap-stripped groups (the reference's checksum key)
+  // gather the pieces (parallel): headers into R; the sequences stay where the pieces parsed them
+  std::vector<const uint8_t*> sptr(nrec);
+  std::vector<uint32_t> slen(nrec);
+  std::vector<uint64_t> hashes(nrec);
+  if (!R->hdr.resize(hdr_bytes)) return set_error(RP_E_NOMEM, "out of memory for %zu B of headers", hdr_bytes);
+  R->hdr_off.resize(nrec + 1);
+  auto run_parallel = [&](unsigned n_jobs, auto&& job) {
+    std::vector<std::thread> th;
+    for (unsigned i = 1; i < n_jobs; i++) th.emplace_back(job, i);
+    job(0u);
+    for (auto& x : th) x.join();
+  };
+  run_parallel(nt, [&](unsigned i) {
+    const Piece& P = pieces[i];
+    if (!P.hdr.empty()) memcpy(R->hdr.data() + hdr0[i], P.hdr.data(), P.hdr.size());
+    size_t ho = hdr0[i];
+    const uint8_t* sp = P.seq.data();
+    for (size_t j = 0; j < P.hdr_len.size(); j++) {
+      const size_t r = rec0[i] + j;
+      R->hdr_off[r] = ho; sptr[r] = sp; slen[r] = P.seq_len[j]; hashes[r] = P.hash[j];
+      ho += P.hdr_len[j]; sp += P.seq_len[j];
+    }
+  });
+  R->hdr_off[nrec] = hdr_bytes;
+  const double t2 = now();
+  // pass 2: exact-sequence uniques (what is placed), numbered in order of first appearance.  The hash space
+  // is split over the threads: thread p finds, among the records whose hash falls to it, the first record of
+  // every distinct sequence; ids then come from a prefix count over the records that are such a first.
+  std::vector<uint32_t> first_of(nrec);
+  const unsigned np = nt;
+  run_parallel(np, [&](unsigned p) {
+    size_t mine = 0;
+    for (size_t r = 0; r < nrec; r++) mine += (unsigned)((hashes[r] >> 40) % np) == p;
+    FlatSet set(mine);
+    for (size_t r = 0; r < nrec; r++) {
+      if ((unsigned)((hashes[r] >> 40) % np) != p) continue;
+      const uint8_t* sp = sptr[r];
+      const uint32_t sn = slen[r];
+      bool ins;
+      first_of[r] = set.find_or_insert(hashes[r], (uint32_t)r, [&](uint32_t o) {
+        return slen[o] == sn && (sn == 0 || memcmp(sptr[o], sp, sn) == 0);
+      }, &ins);
+    }
+  });
   R->unique_of.resize(nrec);
   R->group_of.resize(nrec);
   R->seq_off.assign(1, 0);
-  R->seq.reserve(all_seq.size());
-  std::unordered_map<Slice, uint32_t, SliceHash> uniq, groups;
-  uniq.reserve(nrec * 2);
-  groups.reserve(nrec * 2);
-  std::vector<std::vector<uint8_t>> stripped_store;  // keeps the gap-stripped keys that differ from their sequence alive
-  for (size_t r = 0; r < nrec; r++) {
-    Slice s{all_seq.data() + all_off[r], (size_t)(all_off[r + 1] - all_off[r])};
-    auto it = uniq.find(s);
-    if (it == uniq.end()) {
-      // note: slices must point into storage that never moves -> R->seq was reserved for the worst case
-      const size_t b = R->seq.size();
-      R->seq.insert(R->seq.end(), s.p, s.p + s.n);
-      R->seq_off.push_back(R->seq.size());
-      const uint32_t id = (uint32_t)(R->seq_off.size() - 2);
-      uniq.emplace(Slice{R->seq.data() + b, s.n}, id);
-      R->unique_of[r] = id;
-    } else {
-      R->unique_of[r] = it->second;
+  std::vector<uint32_t> first_rec;  // unique id -> its first record
+  for (size_t r = 0; r < nrec; r++)
+    if (first_of[r] == r) {
+      R->unique_of[r] = (uint32_t)first_rec.size();
+      first_rec.push_back((uint32_t)r);
+      R->seq_off.push_back(R->seq_off.back() + slen[r]);
     }
-    // fasta.getSequence(true): '-' removed (Fasta.java:35-39), PlacementProcess.java:593
-    Slice g = s;
-    if (memchr(s.p, '-', s.n)) {
-      std::vector<uint8_t> st;
-      st.reserve(s.n);
-      for (size_t i = 0; i < s.n; i++)
-        if (s.p[i] != '-') st.push_back(s.p[i]);
-      stripped_store.push_back(std::move(st));
-      g = Slice{stripped_store.back().data(), stripped_store.back().size()};
-    } else {
-      // point into R->seq (stable) rather than the scratch arena
-      const uint32_t u = R->unique_of[r];
-      g = Slice{R->seq.data() + R->seq_off[u], s.n};
-    }
-    auto gt = groups.find(g);
-    if (gt == groups.end()) {
-      groups.emplace(g, R->n_groups);
-      R->group_of[r] = R->n_groups++;
-    } else {
-      R->group_of[r] = gt->second;
+  const size_t n_unique = first_rec.size();
+  if (!R->seq.resize(R->seq_off.back())) return set_error(RP_E_NOMEM, "out of memory for %zu B of sequences", (size_t)R->seq_off.back());
+  run_parallel(nt, [&](unsigned i) {
+    for (size_t r = nrec * i / nt; r < nrec * (i + 1) / nt; r++)
+      if (first_of[r] != r) R->unique_of[r] = R->unique_of[first_of[r]];
+    for (size_t u = n_unique * i / nt; u < n_unique * (i + 1) / nt; u++)
+      if (slen[first_rec[u]]) memcpy(R->seq.data() + R->seq_off[u], sptr[first_rec[u]], slen[first_rec[u]]);
+  });
+  pieces.clear();
+  if (dbg) fprintf(stderr, "ingest: parse %.3f s (%u threads), gather %.3f s, unique %.3f s\n", t1 - t0, nt, t2 - t1, now() - t2);
+  // gap-stripped groups (the reference's checksum key: fasta.getSequence(true) removes '-', Fasta.java:35-39,
+  // PlacementProcess.java:593).  Without any '-' in the file a group is a unique sequence.
+  if (!any_gap) {
+    R->group_of = R->unique_of;
+    R->n_groups = (uint32_t)n_unique;
+    return RP_OK;
+  }
+  std::vector<uint32_t> group_of_unique(n_unique);
+  {
+    // stripped keys, per unique sequence, in order of first appearance (= the order groups are numbered in)
+    std::vector<uint8_t> stripped;
+    std::vector<uint64_t> st_off(1, 0);
+    stripped.reserve(R->seq.size());
+    FlatSet groups(n_unique);
+    for (size_t u = 0; u < n_unique; u++) {
+      const size_t b = stripped.size();
+      for (uint64_t i = R->seq_off[u]; i < R->seq_off[u + 1]; i++)
+        if (R->seq[i] != '-') stripped.push_back(R->seq[i]);
+      const size_t gn = stripped.size() - b;
+      bool ins;
+      const uint32_t g = groups.find_or_insert(hash_bytes(stripped.data() + b, gn), R->n_groups, [&](uint32_t o) {
+        return st_off[o + 1] - st_off[o] == gn && (gn == 0 || memcmp(stripped.data() + st_off[o], stripped.data() + b, gn) == 0);
+      }, &ins);
+      if (ins) { st_off.push_back(stripped.size()); R->n_groups++; }
+      else stripped.resize(b);
+      group_of_unique[u] = g;
     }
   }
+  for (size_t r = 0; r < nrec; r++) R->group_of[r] = group_of_unique[R->unique_of[r]];
   return RP_OK;
 }
 
@@ -156,41 +316,54 @@ template <typename T>
 void java_number(std::string& out, T v) {
   if (isnan(v) || isinf(v)) { out += "null"; return; }  // JSONValue.toJSONString: NaN / Infinity -> null
   if (v == 0) { out += signbit(v) ? "-0.0" : "0.0"; return; }
-  char buf[64];
+  char buf[48], o[64];
   auto res = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::scientific);  // shortest round-trip digits
-  std::string s(buf, res.ptr);
-  // s = [-]d[.ddd]e[+-]xx
-  const bool neg = s[0] == '-';
-  const size_t ms = neg ? 1 : 0, ep = s.find('e');
-  std::string digits;
-  for (size_t i = ms; i < ep; i++)
-    if (s[i] != '.') digits += s[i];
-  const int exp10 = atoi(s.c_str() + ep + 1);
-  if (neg) out += '-';
+  // buf = [-]d[.ddd]e[+-]xx  ->  digits, decimal exponent
+  const char* p = buf;
+  char* w = o;
+  if (*p == '-') { *w++ = '-'; p++; }
+  char digits[24];
+  int nd = 0;
+  for (; *p != 'e'; p++)
+    if (*p != '.') digits[nd++] = *p;
+  p++;
+  const bool eneg = *p == '-';
+  p++;
+  int exp10 = 0;
+  for (; p < res.ptr; p++) exp10 = exp10 * 10 + (*p - '0');
+  if (eneg) exp10 = -exp10;
   if (exp10 >= -3 && exp10 < 7) {
     if (exp10 >= 0) {
-      for (int i = 0; i <= exp10; i++) out += i < (int)digits.size() ? digits[i] : '0';
-      out += '.';
-      if ((int)digits.size() > exp10 + 1) out.append(digits, exp10 + 1, std::string::npos);
-      else out += '0';
+      for (int i = 0; i <= exp10; i++) *w++ = i < nd ? digits[i] : '0';
+      *w++ = '.';
+      if (nd > exp10 + 1) { memcpy(w, digits + exp10 + 1, nd - exp10 - 1); w += nd - exp10 - 1; }
+      else *w++ = '0';
     } else {
-      out += "0.";
-      for (int i = 0; i < -exp10 - 1; i++) out += '0';
-      out += digits;
+      *w++ = '0'; *w++ = '.';
+      for (int i = 0; i < -exp10 - 1; i++) *w++ = '0';
+      memcpy(w, digits, nd); w += nd;
     }
   } else {
-    out += digits[0];
-    out += '.';
-    if (digits.size() > 1) out.append(digits, 1, std::string::npos);
-    else out += '0';
-    out += 'E';
-    out += std::to_string(exp10);
+    *w++ = digits[0];
+    *w++ = '.';
+    if (nd > 1) { memcpy(w, digits + 1, nd - 1); w += nd - 1; }
+    else *w++ = '0';
+    *w++ = 'E';
+    w = std::to_chars(w, o + sizeof o, exp10).ptr;
   }
+  out.append(o, (size_t)(w - o));
+}
+inline void append_int(std::string& out, int v) {
+  char b[16];
+  out.append(b, (size_t)(std::to_chars(b, b + sizeof b, v).ptr - b));
 }
 
 void json_string(std::string& out, const uint8_t* p, size_t n) {  // JSONValue.escape
   out += '"';
   for (size_t i = 0; i < n; i++) {
+    size_t j = i;  // run of characters that need no escape
+    while (j < n && p[j] >= 0x20 && p[j] != 0x7F && p[j] != '"' && p[j] != '\\' && p[j] != '/') j++;
+    if (j > i) { out.append((const char*)p + i, j - i); i = j; if (i == n) break; }
     const uint8_t c = p[i];
     switch (c) {
       case '"': out += "\\\""; break;
@@ -286,12 +459,23 @@ int rp_jplace_write(const char* path, const rp_reads* r, int32_t keep_at_most, c
   // sequence is already REGISTERED only adds [name-up-to-first-space, 1] to that placement's "nm" (:596-624);
   // a placement is registered only once it produced rows (:1047 sits inside the nsBound block, after the
   // unplaced `continue` :797-806), so duplicates of an unplaced sequence are placed again on their own.
+  const bool dbg = getenv("RP_DEBUG_INGEST") != nullptr;
+  auto now = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+  const double t0 = now();
+  double t_fmt = 0, t_wr = 0;
   std::vector<int64_t> placement_of_group(r->n_groups, -1);
-  struct Placement { uint32_t first_record; std::vector<uint32_t> dups; };
-  std::vector<Placement> placements;
+  constexpr uint32_t kNil = 0xFFFFFFFFu;
+  std::vector<uint32_t> first_record, dup_head, dup_tail;  // per placement; its duplicates form a list through dup_next
+  std::vector<uint32_t> dup_next(nrec, kNil);
   for (size_t i = 0; i < nrec; i++) {
     const uint32_t g = r->group_of[i], u = r->unique_of[i];
-    if (placement_of_group[g] >= 0) { placements[(size_t)placement_of_group[g]].dups.push_back((uint32_t)i); continue; }
+    if (placement_of_group[g] >= 0) {
+      const size_t p = (size_t)placement_of_group[g];
+      if (dup_head[p] == kNil) dup_head[p] = (uint32_t)i;
+      else dup_next[dup_tail[p]] = (uint32_t)i;
+      dup_tail[p] = (uint32_t)i;
+      continue;
+    }
     if (status[u] == RP_STATUS_BAD_CHAR || status[u] == RP_STATUS_TOO_SHORT || status[u] == RP_STATUS_TOO_LONG) {
       // the reference stops here (System.exit / exception); the caller decides -- the writer refuses
       fclose(f);
@@ -303,31 +487,29 @@ int rp_jplace_write(const char* path, const rp_reads* r, int32_t keep_at_most, c
       continue;
     }
     if (n_rows[u] <= 0) continue;  // below nsBound: nothing written, nothing registered (:974)
-    placement_of_group[g] = (int64_t)placements.size();
-    placements.push_back({(uint32_t)i, {}});
+    placement_of_group[g] = (int64_t)first_record.size();
+    first_record.push_back((uint32_t)i);
+    dup_head.push_back(kNil);
+    dup_tail.push_back(kNil);
   }
-  std::string o;
-  o.reserve(1 << 20);
-  o += "{\n\"tree\":";
-  if (tree_newick) json_string(o, (const uint8_t*)tree_newick, strlen(tree_newick));
-  else o += "null";
-  o += ",\n\"placements\":\n[";
-  bool ok = true;
-  for (size_t p = 0; p < placements.size() && ok; p++) {
-    const uint32_t i = placements[p].first_record, u = r->unique_of[i];
+  const size_t n_pl = first_record.size();
+  const double t1 = now();
+  // one placement object, appended to o; false if a row names a node the tree does not have
+  auto format_placement = [&](std::string& o, size_t p) -> bool {
+    const uint32_t i = first_record[p], u = r->unique_of[i];
     o += p ? ",\n{\n\t\"p\":\n\t[" : "\n{\n\t\"p\":\n\t[";
     for (int k = 0; k < n_rows[u]; k++) {
       const size_t at = (size_t)u * K + k;
       const unsigned x = node[at];
-      if ((int)x >= n_nodes) { ok = false; break; }
+      if ((int)x >= n_nodes) return false;
       if (k) o += ",\n\t";
       o += '[';
       const float distal = branch_len[x] / 2.0f;  // getBranchLengthToAncestor()/2 (:1015, :1022)
       if (guppy_compat) {  // distal_length, edge_num, like_weight_ratio, likelihood, pendant_length (:1005-1016)
-        java_number(o, distal); o += ','; o += std::to_string(edge_id[x]); o += ',';
+        java_number(o, distal); o += ','; append_int(o, edge_id[x]); o += ',';
         java_number(o, lwr[at]); o += ','; java_number(o, score[at]); o += ",0.0";
       } else {             // edge_num, likelihood, like_weight_ratio, distal_length, pendant_length (:1017-1024)
-        o += std::to_string(edge_id[x]); o += ','; java_number(o, score[at]); o += ',';
+        append_int(o, edge_id[x]); o += ','; java_number(o, score[at]); o += ',';
         java_number(o, lwr[at]); o += ','; java_number(o, distal); o += ",0.0";
       }
       o += ']';
@@ -335,7 +517,7 @@ int rp_jplace_write(const char* path, const rp_reads* r, int32_t keep_at_most, c
     o += "],\n\t\"nm\":\n\t[[";
     json_string(o, r->hdr.data() + r->hdr_off[i], r->hdr_off[i + 1] - r->hdr_off[i]);  // full header (:1041)
     o += ",1]";
-    for (uint32_t d : placements[p].dups) {
+    for (uint32_t d = dup_head[p]; d != kNil; d = dup_next[d]) {
       const uint8_t* h = r->hdr.data() + r->hdr_off[d];
       size_t n = r->hdr_off[d + 1] - r->hdr_off[d];
       const void* sp = memchr(h, ' ', n);  // header up to the first space (:598-602)
@@ -345,8 +527,43 @@ int rp_jplace_write(const char* path, const rp_reads* r, int32_t keep_at_most, c
       o += ",1]";
     }
     o += "]\n}";
-    if (o.size() > (1 << 20)) { ok = fwrite(o.data(), 1, o.size(), f) == o.size(); o.clear(); }
+    return true;
+  };
+  std::string o;
+  o.reserve(1 << 20);
+  o += "{\n\"tree\":";
+  if (tree_newick) json_string(o, (const uint8_t*)tree_newick, strlen(tree_newick));
+  else o += "null";
+  o += ",\n\"placements\":\n[";
+  bool ok = fwrite(o.data(), 1, o.size(), f) == o.size();
+  o.clear();
+  // the placements are formatted in blocks, one block per thread and round, and written in order
+  constexpr size_t kBlock = 8192;
+  const unsigned nt = host_threads(n_pl, kBlock);
+  std::vector<std::string> buf(nt);
+  std::vector<char> good(nt, 1);
+  for (size_t base = 0; base < n_pl && ok; base += (size_t)nt * kBlock) {
+    auto job = [&](unsigned t) {
+      std::string& b = buf[t];
+      b.clear();
+      const size_t lo = base + (size_t)t * kBlock, hi = std::min(n_pl, lo + kBlock);
+      for (size_t p = lo; p < hi && good[t]; p++) good[t] = format_placement(b, p);
+    };
+    const double ta = now();
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; t++)
+      if (base + (size_t)t * kBlock < n_pl) th.emplace_back(job, t);
+    job(0);
+    for (auto& x : th) x.join();
+    const double tb = now();
+    t_fmt += tb - ta;
+    for (unsigned t = 0; t < nt && ok; t++) {
+      if (base + (size_t)t * kBlock >= n_pl) break;
+      ok = good[t] && fwrite(buf[t].data(), 1, buf[t].size(), f) == buf[t].size();
+    }
+    t_wr += now() - tb;
   }
+  if (dbg) fprintf(stderr, "jplace: plan %.3f s, format %.3f s (%u threads), write %.3f s\n", t1 - t0, t_fmt, nt, t_wr);
   if (!ok) {
     fclose(f);
     if (fnp) fclose(fnp);
@@ -359,7 +576,7 @@ int rp_jplace_write(const char* path, const rp_reads* r, int32_t keep_at_most, c
   ok = fwrite(o.data(), 1, o.size(), f) == o.size();
   ok = (fclose(f) == 0) && ok;
   if (fnp) ok = (fclose(fnp) == 0) && ok;
-  if (n_placements) *n_placements = placements.size();
+  if (n_placements) *n_placements = n_pl;
   return ok ? RP_OK : set_error(RP_E_IO, "short write to %s", path);
 }
 

@@ -115,3 +115,38 @@ def test_writer_refuses_reads_the_reference_aborts_on(tmp_path):
     res = O.OracleDB(db).place(q.unique, _abi.place_cfg())
     with pytest.raises(RappasError):
         q.write_jplace(tmp_path / "x.jplace", res, 7, np.arange(41), np.ones(41))
+
+
+@pytest.mark.parametrize("threads", [1, 2, 3, 7])
+def test_parallel_ingest_equals_the_restatement(threads, monkeypatch):
+    """The text is cut at header lines into one piece per thread (RP_HOST_THREADS forces the count on a small
+    input): records, unique sequences and duplicate groups must not depend on where the cuts fall."""
+    monkeypatch.setenv("RP_HOST_THREADS", str(threads))
+    rng = np.random.default_rng(threads)
+    base = ["ACGT" * int(rng.integers(1, 12)) + "ACGTN"[int(rng.integers(0, 5))] for _ in range(40)]
+    parts = ["# leading comment\r\n"]
+    for i in range(400):
+        s = base[int(rng.integers(0, len(base)))]
+        if i % 7 == 3:
+            cut = int(rng.integers(1, len(s)))
+            s = s[:cut] + "-" + s[cut:]                      # gapped duplicate: own unique, shared group
+        eol = ["\n", "\r\n", "\r"][int(rng.integers(0, 3))]
+        hdr = ">r%d some > text %d" % (i, i)                   # '>' inside a header is not a record start
+        if i % 11 == 5:
+            half = len(s) // 2
+            body = s[:half] + eol + eol + "#comment > here" + eol + s[half:]   # wrapped, blank and '#' lines inside
+        else:
+            body = s
+        parts.append(hdr + eol + body + eol)
+    text = "".join(parts)
+    q = ingest.QueryFile.from_text(text)
+    exp = ref_host.read_fasta(text)
+    assert q.n_records == len(exp) == 400
+    assert q.headers == [h for h, _ in exp]
+    assert [q.unique.read(int(u)) for u in q.unique_of] == [s for _, s in exp]
+    # unique ids in order of first appearance of the exact sequence; groups by the gap-stripped sequence
+    first, groups = {}, {}
+    for r, (_, s) in enumerate(exp):
+        assert q.unique_of[r] == first.setdefault(s, len(first))
+        assert q.group_of[r] == groups.setdefault(s.replace("-", ""), len(groups))
+    assert q.n_unique == len(first) and q.n_groups == len(groups)
