@@ -230,6 +230,41 @@ int  rp_jplace_write(const char* path, const rp_reads* r, int32_t keep_at_most, 
 /* Float.toString (as_float != 0) / Double.toString of v, as the writer prints numbers (test hook) */
 int  rp_java_number(double v, int32_t as_float, char* out, int32_t cap);
 
+/* ---- DB build: the phylo-k-mer generation of Main_DBBUILD_3.java:648-750.
+ * For every tested ancestral node and every alignment position, WordExplorer_v3.exploreWords
+ * (core/algos/WordExplorer_v3.java:98-199) walks the k-mers whose summed log10 posterior stays above the
+ * threshold, states in descending-probability order, and registers (k-mer, node, log10 PP*) with
+ * CustomHash_v4_FastUtil81.addTuple (core/hash/CustomHash_v4_FastUtil81.java:73-90: the maximum per
+ * (k-mer, node)).  One GPU thread runs one (node, position) explorer, in the reference's own visiting
+ * order -- the running sum is an f32 that is added to and subtracted from along the walk, so the order is
+ * part of the result; the tuples are then sorted and max-reduced on the device.  The output is the CSR
+ * form rp_db_load takes (keys ascending, a key's postings by ascending node id).
+ *   pp, states [n_nodes][n_sites][n_states]   PProbasSorted (core/PProbasSorted.java:19-20): log10 posteriors
+ *                                             in descending order per site, and the state of each
+ *   original_id [n_nodes]                     extendedTree.getFakeToOriginalId(nodeMapping.get(nodeId))
+ *   gap_off [n_sites + 1], gap_len            Alignment.getGapIntervals(): the jump lengths registered at a
+ *                                             site (CSR; an empty range = null); NULL = no gap jumps
+ *   gap_jumps                                 0 off, 1 every jump combination, 2 at most one jump per k-mer
+ *                                             (doGapJumps / limitTo1Jump)                                   */
+typedef struct {
+  int32_t alphabet;   /* RP_ALPHA_* */
+  int32_t k;
+  int32_t n_nodes;    /* ancestral nodes tested */
+  int32_t n_sites;    /* alignment columns */
+  int32_t n_states;   /* 4 or 20 */
+  float   thr_log10;  /* PPStarThresholdAsLog10 */
+  int32_t gap_jumps;
+  int32_t reserved0;
+} rp_dbbuild_desc;
+typedef struct rp_dbbuild rp_dbbuild;
+int  rp_dbbuild_run(const rp_dbbuild_desc* desc, const float* pp, const uint8_t* states, const uint16_t* original_id,
+                    const uint64_t* gap_off, const int32_t* gap_len, int32_t device, rp_dbbuild** out);
+/* arrays owned by the handle; n_tuples = addTuple calls (the reference's "Tuples explored"), kernel_ms = device time */
+int  rp_dbbuild_result(const rp_dbbuild* b, uint64_t* n_keys, uint64_t* n_postings, uint64_t* n_tuples,
+                       const uint64_t** keys, const uint64_t** offsets, const uint16_t** post_node,
+                       const float** post_score, double* kernel_ms);
+void rp_dbbuild_free(rp_dbbuild* b);
+
 /* ---- introspection used by bench.py / tests */
 int  rp_device_count(void);
 /* number of kernels this library launched since load (all threads); bench.py's gpu_launches */

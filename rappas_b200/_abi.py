@@ -33,6 +33,13 @@ class RpPlaceCfg(C.Structure):
     ]
 
 
+class RpDbBuildDesc(C.Structure):
+    _fields_ = [
+        ("alphabet", C.c_int32), ("k", C.c_int32), ("n_nodes", C.c_int32), ("n_sites", C.c_int32),
+        ("n_states", C.c_int32), ("thr_log10", C.c_float), ("gap_jumps", C.c_int32), ("reserved0", C.c_int32),
+    ]
+
+
 def place_cfg(keep_at_most=7, keep_factor=0.01, treat_amb=True, amb_with_max=False, ns_bound=-np.inf) -> RpPlaceCfg:
     """Defaults = ArgumentsParser_v2.java:86-91."""
     return RpPlaceCfg(int(keep_at_most), float(keep_factor), int(bool(treat_amb)), int(bool(amb_with_max)),
@@ -52,6 +59,10 @@ PROTOTYPES = {
     "db_attach_partitions": (C.c_int, [_P, _P, C.c_int32]),
     "partition_of_keys": (C.c_int, [C.c_int32, C.c_int32, _P, C.c_uint64, C.c_int32, _P]),
     "db_free": (None, [_P]),
+    "dbbuild_run": (C.c_int, [C.POINTER(RpDbBuildDesc), _P, _P, _P, _P, _P, C.c_int32, C.POINTER(_P)]),
+    "dbbuild_result": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(_P),
+                                 C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_double)]),
+    "dbbuild_free": (None, [_P]),
     "db_describe": (C.c_int, [_P, C.POINTER(RpDbDesc)]),
     "db_device_bytes": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "place_batch": (C.c_int, [_P, C.POINTER(RpPlaceCfg), _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P]),

@@ -1,0 +1,62 @@
+"""DB-build row, CPU side: the recursive C oracle against the literal Python restatement and
+hand-derived answers, and the product's explorer state machine (compiled for the host) against the oracle."""
+import numpy as np
+import pytest
+
+import dbbuild_lib as D
+from oracle import dbbuild_py
+
+
+def py_csr(alphabet, k, pp, states, oid, thr, gaps=None, gap_jumps=0):
+    table, n = dbbuild_py.build(alphabet, k, pp, states, oid, thr, gaps, gap_jumps)
+    codes, nodes, scores = [], [], []
+    for c in sorted(table):
+        for nd in sorted(table[c]):
+            codes.append(c); nodes.append(nd); scores.append(table[c][nd])
+    return D.csr_from_tuples(np.asarray(codes, np.uint64), np.asarray(nodes, np.uint16), np.asarray(scores, np.float32)), n
+
+
+def gaps_as_lists(gap_off, gap_len, n_sites):
+    if gap_off is None:
+        return None
+    return [list(map(int, gap_len[int(gap_off[i]):int(gap_off[i + 1])])) or None for i in range(n_sites)]
+
+
+def test_hand_derived_single_site_chain():
+    """k = 2, 2 sites, one node, threshold -1: the words are the pairs whose summed log10 stays >= -1."""
+    pp = np.log10(np.array([[[0.7, 0.2, 0.06, 0.04], [0.9, 0.05, 0.03, 0.02]]], np.float64)).astype(np.float32)
+    states = np.array([[[3, 0, 2, 1], [1, 2, 0, 3]]], np.uint8)
+    oid = np.array([5], np.uint16)
+    o = D.oracle_build(0, 2, pp, states, oid, -1.0)
+    # 0.7*0.9 = 0.63 and 0.2*0.9 = 0.18 are the only products >= 0.1; code = b0 + 4*b1
+    assert list(o["keys"]) == [0 + 4 * 1, 3 + 4 * 1] and list(o["post_node"]) == [5, 5]
+    exp = [np.float32(np.float32(pp[0, 0, 1]) + np.float32(pp[0, 1, 0])), np.float32(np.float32(pp[0, 0, 0]) + np.float32(pp[0, 1, 0]))]
+    assert [x.view(np.uint32) for x in o["post_score"]] == [x.view(np.uint32) for x in exp]
+    assert o["n_tuples"] == 2
+
+
+@pytest.mark.parametrize("alphabet,k,n_nodes,n_sites,gap_jumps", [(0, 3, 3, 9, 0), (0, 4, 2, 10, 1), (0, 4, 2, 10, 2),
+                                                               (1, 2, 2, 6, 0), (1, 3, 1, 5, 2)])
+def test_c_oracle_equals_python_restatement(alphabet, k, n_nodes, n_sites, gap_jumps):
+    pp, states, oid, goff, glen = D.make_inputs(alphabet, k, n_nodes, n_sites, seed=k * 7 + gap_jumps, peak=0.8,
+                                                gap_rate=0.4 if gap_jumps else 0.0)
+    thr = float(np.float32(np.log10(np.float32((1.5 / (4 if alphabet == 0 else 20)) ** k))))
+    o = D.oracle_build(alphabet, k, pp, states, oid, thr, goff, glen, gap_jumps)
+    p, n = py_csr(alphabet, k, pp, states, oid, thr, gaps_as_lists(goff, glen, n_sites), gap_jumps)
+    assert o["n_tuples"] == n and n > 0
+    D.assert_csr_equal({f: o[f] for f in p}, p)
+
+
+@pytest.mark.parametrize("alphabet,k,n_nodes,n_sites,gap_jumps,peak", [
+    (0, 5, 6, 40, 0, 0.9), (0, 8, 4, 30, 0, 0.93), (0, 6, 5, 30, 1, 0.9), (0, 6, 5, 30, 2, 0.9), (0, 10, 2, 24, 0, 0.95),
+    (1, 3, 3, 20, 0, 0.8), (1, 4, 2, 14, 2, 0.85), (0, 4, 3, 3, 0, 0.9), (0, 1, 2, 5, 0, 0.9)])
+def test_product_explorer_equals_oracle(alphabet, k, n_nodes, n_sites, gap_jumps, peak):
+    """Same tuples (count), same maxima bit for bit: the f32 running sum makes the visiting order part of the
+    result, so this pins the state machine to the recursion."""
+    pp, states, oid, goff, glen = D.make_inputs(alphabet, k, n_nodes, n_sites, seed=100 + k + gap_jumps, peak=peak,
+                                                gap_rate=0.3 if gap_jumps else 0.0)
+    thr = float(np.float32(np.log10(np.float32((1.5 / (4 if alphabet == 0 else 20)) ** k))))
+    o = D.oracle_build(alphabet, k, pp, states, oid, thr, goff, glen, gap_jumps)
+    codes, nodes, scores = D.core_tuples(alphabet, k, pp, states, oid, thr, goff, glen, gap_jumps)
+    assert codes.size == o["n_tuples"]
+    D.assert_csr_equal(D.csr_from_tuples(codes, nodes, scores), {f: o[f] for f in ("keys", "offsets", "post_node", "post_score")})
