@@ -14,7 +14,8 @@ import oracle_lib as O
 import parity
 from rappas_b200 import _abi, synth
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "*.npz"))
+                if not os.path.basename(p).startswith("dbbuild_"))  # those belong to tests/test_golden_dbbuild.py
 
 
 def load(path):
