@@ -150,3 +150,44 @@ def test_parallel_ingest_equals_the_restatement(threads, monkeypatch):
         assert q.unique_of[r] == first.setdefault(s, len(first))
         assert q.group_of[r] == groups.setdefault(s.replace("-", ""), len(groups))
     assert q.n_unique == len(first) and q.n_groups == len(groups)
+
+
+@pytest.mark.parametrize("threads", [1, 3])
+def test_block_parallel_writer_equals_the_restatement(tmp_path, threads, monkeypatch):
+    """More placements than one formatting block (8 192), forced onto 1 and 3 host threads: the document must
+    be the restatement's, placement by placement, whatever thread formatted which block."""
+    monkeypatch.setenv("RP_HOST_THREADS", str(threads))
+    rng = np.random.default_rng(7)
+    n_unique, n_dup, n_nodes, K = 20000, 3000, 101, 7
+    alphabet = np.frombuffer(b"ACGT", np.uint8)
+    seqs = ["".join(map(chr, alphabet[rng.integers(0, 4, 24)])) + "%05d" % i for i in range(n_unique)]  # distinct
+    order = list(range(n_unique)) + [int(x) for x in rng.integers(0, n_unique, n_dup)]
+    rng.shuffle(order)
+    text = "".join(">q%d d%d\n%s\n" % (j, j, seqs[i]) for j, i in enumerate(order))
+    q = ingest.QueryFile.from_text(text)
+    assert q.n_unique == n_unique
+    n_rows = rng.integers(0, 4, n_unique).astype(np.int32)      # 0 rows = below nsBound: not written, not registered
+    status = np.where(rng.random(n_unique) < 0.02, 1, 0).astype(np.int32)  # a few reads without any hit
+    n_rows[status == 1] = 0
+    res = dict(n_rows=n_rows, node=rng.integers(0, n_nodes, (n_unique, K)).astype(np.uint16),
+               score=(-rng.random((n_unique, K)) * 700).astype(np.float32), lwr=rng.random((n_unique, K)), status=status)
+    edge_id = rng.permutation(n_nodes).astype(np.int32)
+    branch = rng.uniform(1e-4, 2.0, n_nodes).astype(np.float32)
+    out, npl = tmp_path / "o.jplace", tmp_path / "np.txt"
+    n = q.write_jplace(out, res, K, edge_id, branch, tree_newick="(a,b);", invocation="t", not_placed_path=npl)
+    by_seq = {}
+    for u in range(n_unique):
+        by_seq[q.unique.read(u)] = u
+
+    def place_one(seq):
+        u = by_seq[seq]
+        return int(status[u]), [(int(res["node"][u, i]), res["score"][u, i], res["lwr"][u, i]) for i in range(int(n_rows[u]))]
+
+    exp, exp_np = ref_host.build_jplace(ref_host.read_fasta(text), place_one, edge_id, branch, False)
+    doc = json.loads(out.read_text())
+    assert n == len(exp) == len(doc["placements"]) > 8192
+    raw = out.read_text()
+    got_rows = re.findall(r"\[([^\[\]\"]+)\]", raw.split('"placements"')[1].split('"version"')[0])
+    assert got_rows == [",".join(str(c) for c in row) for pl in exp for row in pl["p"]]
+    assert [pl["nm"] for pl in doc["placements"]] == [pl["nm"] for pl in exp]
+    assert npl.read_text().splitlines() == exp_np
