@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--no-ambiguity", action="store_true", help="experiment: generate the reads without IUPAC / N characters")
     ap.add_argument("--partitioned", action="store_true",
                     help="hash-partition the DB over the ranks (peer memory over NVLink) instead of replicating it")
+    ap.add_argument("--postings-scale", type=float, default=1.0,
+                    help="experiment: multiply the workload's mean postings per key (the DB's posting blocks grow with it)")
     ap.add_argument("--replicate-table", action="store_true",
                     help="with --partitioned: partition only the posting blocks, keep the whole table on every GPU")
     return ap.parse_args()
@@ -208,6 +210,9 @@ def main():
     if args.no_ambiguity:
         w.iupac_rate = w.n_rate = 0.0
     n_reads = args.reads or w.n_reads
+    if args.postings_scale != 1.0:
+        w.mean_postings = w.mean_postings * args.postings_scale
+        w.name += "_postings_x%g" % args.postings_scale
     db = synth.make_db(w.alphabet, w.k, w.n_nodes, w.n_keys, w.mean_postings, seed=42 + w.index, key_mode=w.key_mode)
     rb = synth.make_reads(db, n_reads, w.read_len, seed=1042 + w.index + 7919 * rank, iupac_rate=w.iupac_rate,
                           n_rate=w.n_rate)
