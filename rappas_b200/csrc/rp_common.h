@@ -19,10 +19,11 @@ namespace rp {
 //
 //  table   : static open addressing, 2-choice bucketed cuckoo placement.  n_buckets = pow2 >= n_keys,
 //            bucket = 2 slots = 32 B = one DRAM/L2 sector, slot = { u64 key, u64 meta } (16 B),
-//            meta = (block_offset_in_32B_units << 16) | n_postings, empty slot: key == kEmptyKey.
-//            A key lives in bucket b1(key) or b2(key); a lookup issues the four LDG.128 of both
-//            buckets up front and never loops, so all 32 lanes of a warp finish in one memory round
-//            trip (linear probing makes a warp wait for its slowest lane: 4-5 dependent rounds).
+//            meta = partition | node-range sixteenths | block_offset_in_32B_units << 16 | n_postings (see
+//            kMeta* below), empty slot: key == kEmptyKey.
+//            A key lives in bucket b1(key) or b2(key); a lookup issues one 256-bit load per bucket up
+//            front and never loops, so all 32 lanes of a warp finish in one memory round trip (linear
+//            probing makes a warp wait for its slowest lane: 4-5 dependent rounds).
 //            Stored keys are in the kernel's PLANAR form (see planar_from_code).
 //  blocks  : posting blocks, 32 B aligned.  A key with P postings (sorted by node id at load) is a
 //            run of sub-blocks of up to 32 postings; sub-block i starts at block + 192*i and holds
