@@ -257,6 +257,14 @@ typedef struct {
   int32_t reserved0;
 } rp_dbbuild_desc;
 typedef struct rp_dbbuild rp_dbbuild;
+/* Raw ancestral-reconstruction posteriors -> the PProbasSorted arrays rp_dbbuild_run takes.  Per (node, site):
+ * clamp at site_pp_threshold (Float.MIN_VALUE in Main_DBBUILD_3.java:164), log10 in double narrowed to float
+ * when as_log10 != 0, then a stable sort, highest first (SiteProba.compareTo, core/SiteProba.java:26-34, under
+ * Collections.sort: equal values keep the column order) -- inputs/PHYMLWrapper.java:206-229 and the same block
+ * of the RAxML-ng / PAML wrappers.  probs [n_nodes][n_sites][n_states] in the column order of the AR file,
+ * state_of_column[n_states] = the state byte of each column.  Host code (multi-threaded), no GPU needed. */
+int  rp_pp_prepare(const float* probs, const uint8_t* state_of_column, int32_t n_nodes, int32_t n_sites,
+                   int32_t n_states, float site_pp_threshold, int32_t as_log10, float* pp_out, uint8_t* states_out);
 int  rp_dbbuild_run(const rp_dbbuild_desc* desc, const float* pp, const uint8_t* states, const uint16_t* original_id,
                     const uint64_t* gap_off, const int32_t* gap_len, int32_t device, rp_dbbuild** out);
 /* arrays owned by the handle; n_tuples = addTuple calls (the reference's "Tuples explored"), kernel_ms = device time */

@@ -580,6 +580,46 @@ int rp_jplace_write(const char* path, const rp_reads* r, int32_t keep_at_most, c
   return ok ? RP_OK : set_error(RP_E_IO, "short write to %s", path);
 }
 
+// inputs/PHYMLWrapper.java:206-229 (and the RAxML-ng / PAML twins): the per-site preparation of the posteriors
+int rp_pp_prepare(const float* probs, const uint8_t* state_of_column, int32_t n_nodes, int32_t n_sites, int32_t n_states,
+                  float site_pp_threshold, int32_t as_log10, float* pp_out, uint8_t* states_out) {
+  if (!probs || !state_of_column || !pp_out || !states_out) return set_error(RP_E_INVALID, "NULL argument");
+  if (n_nodes < 0 || n_sites < 0 || n_states < 1 || n_states > 32) return set_error(RP_E_INVALID, "bad shape");
+  const size_t n_rows = (size_t)n_nodes * (size_t)n_sites;
+  const unsigned nt = host_threads(n_rows, 1 << 14);
+  auto job = [&](unsigned t) {
+    float p[32];
+    uint8_t st[32];
+    for (size_t r = n_rows * t / nt; r < n_rows * (t + 1) / nt; r++) {
+      const float* in = probs + r * n_states;
+      for (int i = 0; i < n_states; i++) {
+        float v = in[i];
+        if (v < site_pp_threshold) v = site_pp_threshold;       // :218-219
+        if (as_log10) v = (float)log10((double)v);              // :220-221  (float)Math.log10(sp.proba)
+        p[i] = v;
+        st[i] = state_of_column[i];
+      }
+      // Collections.sort with SiteProba.compareTo: stable, descending; a stable insertion sort gives the same
+      // order for any input the comparator orders consistently ((a - b) < 0.0 / > 0.0 in float)
+      for (int i = 1; i < n_states; i++) {
+        const float v = p[i];
+        const uint8_t s8 = st[i];
+        int j = i - 1;
+        while (j >= 0 && (p[j] - v) < 0.0f) { p[j + 1] = p[j]; st[j + 1] = st[j]; j--; }
+        p[j + 1] = v;
+        st[j + 1] = s8;
+      }
+      memcpy(pp_out + r * n_states, p, sizeof(float) * n_states);
+      memcpy(states_out + r * n_states, st, n_states);
+    }
+  };
+  std::vector<std::thread> th;
+  for (unsigned t = 1; t < nt; t++) th.emplace_back(job, t);
+  job(0);
+  for (auto& x : th) x.join();
+  return RP_OK;
+}
+
 // test hook: Float.toString / Double.toString as the writer prints them
 int rp_java_number(double v, int32_t as_float, char* out, int32_t cap) {
   std::string s;

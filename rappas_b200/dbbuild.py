@@ -13,6 +13,17 @@ from . import _abi
 from ._lib import check, load
 
 
+def prepare_posteriors(probs, state_of_column, site_pp_threshold=np.float32(1.4e-45), as_log10=True):
+    """Raw AR posteriors [n_nodes][n_sites][n_states] (columns in the AR file's state order) -> (pp, states) as
+    PProbasSorted holds them: clamped, log10, stable-sorted highest first (inputs/PHYMLWrapper.java:206-229)."""
+    probs = np.ascontiguousarray(probs, dtype=np.float32)
+    soc = np.ascontiguousarray(state_of_column, dtype=np.uint8)
+    pp, st = np.empty_like(probs), np.empty(probs.shape, np.uint8)
+    check(load()["pp_prepare"](_abi.ptr(probs), _abi.ptr(soc), probs.shape[0], probs.shape[1], probs.shape[2],
+                               C.c_float(site_pp_threshold), int(bool(as_log10)), _abi.ptr(pp), _abi.ptr(st)))
+    return pp, st
+
+
 def build_db(alphabet, k, pp, states, original_id, thr_log10, gap_off=None, gap_len=None, gap_jumps=0, device=0):
     """pp, states: [n_nodes][n_sites][n_states] (PProbasSorted: log10 posteriors, descending per site, and their
     states); original_id[n_nodes]; gap_off/gap_len: CSR of Alignment.getGapIntervals(); gap_jumps 0 / 1 / 2 =

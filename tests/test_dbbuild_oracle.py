@@ -60,3 +60,30 @@ def test_product_explorer_equals_oracle(alphabet, k, n_nodes, n_sites, gap_jumps
     codes, nodes, scores = D.core_tuples(alphabet, k, pp, states, oid, thr, goff, glen, gap_jumps)
     assert codes.size == o["n_tuples"]
     D.assert_csr_equal(D.csr_from_tuples(codes, nodes, scores), {f: o[f] for f in ("keys", "offsets", "post_node", "post_score")})
+
+
+def test_pp_prepare_equals_the_restatement():
+    """PHYMLWrapper.java:206-229: clamp, (float)Math.log10, Collections.sort (stable, SiteProba.compareTo)."""
+    import functools
+    from rappas_b200 import dbbuild
+    rng = np.random.default_rng(3)
+    for ns, soc in ((4, [0, 2, 3, 1]), (20, list(range(20)))):       # PhyML prints A C G T -> states 0 2 3 1
+        probs = rng.dirichlet(np.ones(ns) * 0.3, (5, 37)).astype(np.float32)
+        probs[0, 0] = 0.25 if ns == 4 else 0.05                        # ties everywhere: column order must survive
+        probs[1, 3, :2] = probs[1, 3, 0]                               # a tie for first place
+        probs[2, 5, 1] = 0.0                                           # clamped to Float.MIN_VALUE before the log
+        pp, st = dbbuild.prepare_posteriors(probs, soc)
+
+        def cmp(a, b):                                                 # SiteProba.compareTo
+            d = np.float32(a[0]) - np.float32(b[0])
+            return 1 if d < 0.0 else (-1 if d > 0.0 else 0)
+        for nd in range(probs.shape[0]):
+            for site in range(probs.shape[1]):
+                row = []
+                for i in range(ns):
+                    v = np.float32(max(probs[nd, site, i], np.float32(1.4e-45)))
+                    row.append((np.float32(np.log10(np.float64(v))), soc[i]))
+                row = sorted(row, key=functools.cmp_to_key(cmp))       # Python's sort is stable, like Collections.sort
+                assert [x[0].view(np.uint32) for x in row] == [x.view(np.uint32) for x in pp[nd, site]], (nd, site)
+                assert [x[1] for x in row] == list(st[nd, site]), (nd, site)
+        assert np.all(np.diff(pp, axis=2) <= 0)
