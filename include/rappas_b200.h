@@ -265,6 +265,12 @@ typedef struct rp_dbbuild rp_dbbuild;
  * state_of_column[n_states] = the state byte of each column.  Host code (multi-threaded), no GPU needed. */
 int  rp_pp_prepare(const float* probs, const uint8_t* state_of_column, int32_t n_nodes, int32_t n_sites,
                    int32_t n_states, float site_pp_threshold, int32_t as_log10, float* pp_out, uint8_t* states_out);
+/* Alignment.updateGapIntervals (alignement/Alignment.java:231-260): for every column at which a run of '-' starts
+ * in some row and ends before the end of that row, the distinct run lengths in order of first appearance (row
+ * by row) -- the jump lengths rp_dbbuild_run explores, in the order it explores them.  chars [n_rows][n_cols];
+ * gap_off [n_cols + 1]; gap_len may be NULL to query *n_len first (RP_E_INVALID if cap is too small). */
+int  rp_gap_intervals(const uint8_t* chars, int32_t n_rows, int32_t n_cols, uint64_t* gap_off, int32_t* gap_len,
+                      uint64_t cap, uint64_t* n_len);
 int  rp_dbbuild_run(const rp_dbbuild_desc* desc, const float* pp, const uint8_t* states, const uint16_t* original_id,
                     const uint64_t* gap_off, const int32_t* gap_len, int32_t device, rp_dbbuild** out);
 /* arrays owned by the handle; n_tuples = addTuple calls (the reference's "Tuples explored"), kernel_ms = device time */

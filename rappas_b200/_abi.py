@@ -59,6 +59,7 @@ PROTOTYPES = {
     "db_attach_partitions": (C.c_int, [_P, _P, C.c_int32]),
     "partition_of_keys": (C.c_int, [C.c_int32, C.c_int32, _P, C.c_uint64, C.c_int32, _P]),
     "db_free": (None, [_P]),
+    "gap_intervals": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "pp_prepare": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, _P, _P]),
     "dbbuild_run": (C.c_int, [C.POINTER(RpDbBuildDesc), _P, _P, _P, _P, _P, C.c_int32, C.POINTER(_P)]),
     "dbbuild_result": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(_P),

@@ -620,6 +620,39 @@ int rp_pp_prepare(const float* probs, const uint8_t* state_of_column, int32_t n_
   return RP_OK;
 }
 
+// alignement/Alignment.java:231-260
+int rp_gap_intervals(const uint8_t* chars, int32_t n_rows, int32_t n_cols, uint64_t* gap_off, int32_t* gap_len, uint64_t cap,
+                     uint64_t* n_len) {
+  if (!chars || !gap_off || !n_len || n_rows < 0 || n_cols < 0) return set_error(RP_E_INVALID, "bad argument");
+  std::vector<std::vector<int32_t>> iv((size_t)n_cols);  // gapIntervals[col]: empty = null
+  for (int i = 0; i < n_rows; i++) {
+    const uint8_t* row = chars + (size_t)i * n_cols;
+    int first = -1;
+    uint8_t prev = 'n';
+    for (int j = 0; j < n_cols; j++) {
+      const uint8_t c = row[j];
+      if (c == '-') {
+        if (prev != '-' && first == -1) first = j;                       // :240-245
+      } else if (first != -1) {
+        const int32_t len = j - first;                                   // :249
+        std::vector<int32_t>& l = iv[(size_t)first];
+        if (std::find(l.begin(), l.end(), len) == l.end()) l.push_back(len);  // :250-252
+        first = -1;
+      }
+      prev = c;
+    }
+  }
+  uint64_t n = 0;
+  for (int j = 0; j < n_cols; j++) { gap_off[j] = n; n += iv[(size_t)j].size(); }
+  gap_off[n_cols] = n;
+  *n_len = n;
+  if (!gap_len) return RP_OK;
+  if (cap < n) return set_error(RP_E_INVALID, "gap_len holds %llu entries, %llu needed", (unsigned long long)cap, (unsigned long long)n);
+  for (int j = 0; j < n_cols; j++)
+    if (!iv[(size_t)j].empty()) memcpy(gap_len + gap_off[j], iv[(size_t)j].data(), iv[(size_t)j].size() * sizeof(int32_t));
+  return RP_OK;
+}
+
 // test hook: Float.toString / Double.toString as the writer prints them
 int rp_java_number(double v, int32_t as_float, char* out, int32_t cap) {
   std::string s;

@@ -24,6 +24,18 @@ def prepare_posteriors(probs, state_of_column, site_pp_threshold=np.float32(1.4e
     return pp, st
 
 
+def gap_intervals(rows):
+    """rows: aligned sequences of equal length (str / bytes) -> (gap_off, gap_len), Alignment.updateGapIntervals."""
+    m = np.ascontiguousarray([np.frombuffer(r.encode() if isinstance(r, str) else bytes(r), np.uint8) for r in rows], dtype=np.uint8)
+    off = np.zeros(m.shape[1] + 1, np.uint64)
+    n = C.c_uint64()
+    fn = load()
+    check(fn["gap_intervals"](_abi.ptr(m), m.shape[0], m.shape[1], _abi.ptr(off), None, 0, C.byref(n)))
+    lens = np.zeros(max(1, n.value), np.int32)
+    check(fn["gap_intervals"](_abi.ptr(m), m.shape[0], m.shape[1], _abi.ptr(off), _abi.ptr(lens), lens.shape[0], C.byref(n)))
+    return off, lens[:n.value]
+
+
 def build_db(alphabet, k, pp, states, original_id, thr_log10, gap_off=None, gap_len=None, gap_jumps=0, device=0):
     """pp, states: [n_nodes][n_sites][n_states] (PProbasSorted: log10 posteriors, descending per site, and their
     states); original_id[n_nodes]; gap_off/gap_len: CSR of Alignment.getGapIntervals(); gap_jumps 0 / 1 / 2 =

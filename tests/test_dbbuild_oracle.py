@@ -87,3 +87,41 @@ def test_pp_prepare_equals_the_restatement():
                 assert [x[0].view(np.uint32) for x in row] == [x.view(np.uint32) for x in pp[nd, site]], (nd, site)
                 assert [x[1] for x in row] == list(st[nd, site]), (nd, site)
         assert np.all(np.diff(pp, axis=2) <= 0)
+
+
+def test_gap_intervals_equal_the_restatement():
+    """Alignment.updateGapIntervals (alignement/Alignment.java:231-260), transliterated."""
+    from rappas_b200 import dbbuild
+
+    def restatement(charMatrix):
+        gapIntervals = [None] * len(charMatrix[0])
+        for i in range(len(charMatrix)):
+            firstGapIndex, previousChar = -1, 'n'
+            for j in range(len(charMatrix[i])):
+                c = charMatrix[i][j]
+                if c == '-':
+                    if previousChar != '-':
+                        if firstGapIndex == -1:
+                            firstGapIndex = j
+                else:
+                    if firstGapIndex != -1:
+                        if gapIntervals[firstGapIndex] is None:
+                            gapIntervals[firstGapIndex] = []
+                        length = j - firstGapIndex
+                        if length not in gapIntervals[firstGapIndex]:
+                            gapIntervals[firstGapIndex].append(length)
+                        firstGapIndex = -1
+                previousChar = c
+        return gapIntervals
+
+    rows = ["AC--GT-A", "AC-TGT--", "--CTG--A", "ACGTGTAA", "AC---T-A", "-C--GT-A"]   # trailing runs are not registered
+    off, lens = dbbuild.gap_intervals(rows)
+    exp = restatement(rows)
+    got = [list(map(int, lens[int(off[j]):int(off[j + 1])])) or None for j in range(len(rows[0]))]
+    assert got == exp and exp[2] == [2, 1, 3] and exp[6] == [1] and exp[0] == [2, 1]
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        rows = ["".join(rng.choice(list("ACGT-"), 40, p=[.2, .2, .2, .2, .2])) for _ in range(int(rng.integers(1, 12)))]
+        off, lens = dbbuild.gap_intervals(rows)
+        got = [list(map(int, lens[int(off[j]):int(off[j + 1])])) or None for j in range(40)]
+        assert got == restatement(rows)
