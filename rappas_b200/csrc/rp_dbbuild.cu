@@ -65,6 +65,12 @@ struct MaxOp {
   __host__ __device__ float operator()(float a, float b) const { return a > b ? a : b; }
 };
 
+struct EventPair {
+  cudaEvent_t a = nullptr, b = nullptr;
+  EventPair() { cudaEventCreate(&a); cudaEventCreate(&b); }
+  ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+};
+
 struct DevBuf {
   void* p = nullptr;
   ~DevBuf() { if (p) cudaFree(p); }
@@ -120,9 +126,8 @@ int rp_dbbuild_run(const rp_dbbuild_desc* d, const float* pp, const uint8_t* sta
   if (n_tasks == 0) { *out = B.release(); return RP_OK; }
   if (n_tasks >= (1ll << 31)) return set_error(RP_E_UNSUPPORTED, "more than 2^31 (node, position) explorers in one pass");
 
-  cudaEvent_t e0, e1;
-  cudaEventCreate(&e0);
-  cudaEventCreate(&e1);
+  EventPair ev;
+  cudaEvent_t e0 = ev.a, e1 = ev.b;
   RP_CUDA_TRY(d_counts.alloc((size_t)n_tasks * 8));
   RP_CUDA_TRY(d_base.alloc((size_t)(n_tasks + 1) * 8));
   const int threads = 128;
@@ -148,7 +153,6 @@ int rp_dbbuild_run(const rp_dbbuild_desc* d, const float* pp, const uint8_t* sta
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     B->kernel_ms = ms;
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     *out = B.release();
     return RP_OK;
   }
@@ -207,7 +211,6 @@ int rp_dbbuild_run(const rp_dbbuild_desc* d, const float* pp, const uint8_t* sta
   float ms = 0;
   cudaEventSynchronize(e1);
   cudaEventElapsedTime(&ms, e0, e1);
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
   B->kernel_ms = ms;
   B->keys.resize(n_keys);
   B->post_node.resize(n_post);
