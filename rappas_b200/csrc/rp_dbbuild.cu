@@ -17,6 +17,7 @@
 
 #include "rp_common.h"
 #include "rp_dbbuild_core.h"
+#include "rp_dbbuild_merge.h"
 
 struct rp_dbbuild {
   std::vector<uint64_t> keys, offsets;
@@ -29,17 +30,21 @@ struct rp_dbbuild {
 namespace rp {
 
 template <bool EMIT>
-__global__ void __launch_bounds__(128) explore_kernel(const BuildView v, int n_nodes, int n_pos, const uint16_t* __restrict__ original_id,
+__global__ void __launch_bounds__(128) explore_kernel(const BuildView v, long long task0, long long n_tasks, int n_pos,
+                                                      const uint16_t* __restrict__ original_id,
                                                       unsigned long long* __restrict__ counts,
-                                                      const unsigned long long* __restrict__ base,
+                                                      const unsigned long long* __restrict__ base, unsigned long long base_shift,
                                                       unsigned long long* __restrict__ out_key, float* __restrict__ out_score) {
-  const long long task = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (task >= (long long)n_nodes * n_pos) return;
+  // explorers [task0, task0 + n_tasks) of the build; an emitting launch writes its tuples from 0 (base_shift =
+  // the prefix count of its first explorer)
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_tasks) return;
+  const long long task = task0 + idx;
   // consecutive threads take consecutive positions of one node: their posteriors overlap in cache
   const int node = (int)(task / n_pos), pos = (int)(task % n_pos);
   unsigned long long n = 0;
   if (EMIT) {
-    const unsigned long long at = base[task];
+    const unsigned long long at = base[task] - base_shift;
     const unsigned long long nd = original_id[node];
     explore_position(v, node, pos, [&](uint64_t code, float s) {
       out_key[at + n] = (code << 16) | nd;
@@ -121,7 +126,6 @@ int rp_dbbuild_run(const rp_dbbuild_desc* d, const float* pp, const uint8_t* sta
     v.gap_len = d_glen.as<int32_t>();
   }
   std::unique_ptr<rp_dbbuild> B(new rp_dbbuild());
-  auto fail = [&](int rc) { return rc; };
   B->offsets.assign(1, 0);
   if (n_tasks == 0) { *out = B.release(); return RP_OK; }
   if (n_tasks >= (1ll << 31)) return set_error(RP_E_UNSUPPORTED, "more than 2^31 (node, position) explorers in one pass");
@@ -133,8 +137,8 @@ int rp_dbbuild_run(const rp_dbbuild_desc* d, const float* pp, const uint8_t* sta
   const int threads = 128;
   const int blocks = (int)((n_tasks + threads - 1) / threads);
   cudaEventRecord(e0);
-  explore_kernel<false><<<blocks, threads>>>(v, d->n_nodes, n_pos, d_oid.as<uint16_t>(), d_counts.as<unsigned long long>(),
-                                             nullptr, nullptr, nullptr);
+  explore_kernel<false><<<blocks, threads>>>(v, 0, n_tasks, n_pos, d_oid.as<uint16_t>(), d_counts.as<unsigned long long>(),
+                                             nullptr, 0ull, nullptr, nullptr);
   g_kernel_launches.fetch_add(1);
   size_t tmp_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_counts.as<unsigned long long>(), d_base.as<unsigned long long>(),
@@ -156,17 +160,71 @@ int rp_dbbuild_run(const rp_dbbuild_desc* d, const float* pp, const uint8_t* sta
     *out = B.release();
     return RP_OK;
   }
-  if (n_tuples >= (1ull << 31)) return fail(set_error(RP_E_UNSUPPORTED, "%llu tuples in one pass (>= 2^31): build in node batches", n_tuples));
+  // one pass if the tuples fit (sort buffers: 2 x 12 B per tuple + temporaries), else batches of consecutive nodes
   size_t free_b = 0, total_b = 0;
   cudaMemGetInfo(&free_b, &total_b);
-  if ((double)n_tuples * 12.0 * 2.2 > (double)free_b)
-    return fail(set_error(RP_E_NOMEM, "%llu tuples need ~%.1f GB of device memory for the merge", n_tuples, n_tuples * 12.0 * 2.2 / 1e9));
+  unsigned long long cap = std::min<unsigned long long>((1ull << 31) - 1, (unsigned long long)((double)free_b / (12.0 * 2.2)));
+  if (const char* e = getenv("RP_DBBUILD_MAX_TUPLES")) cap = std::max(1ll, atoll(e));  // tests: force batches
+  if (n_tuples > cap) {
+    std::vector<unsigned long long> h_base((size_t)n_tasks);
+    RP_CUDA_TRY(cudaMemcpy(h_base.data(), d_base.p, (size_t)n_tasks * 8, cudaMemcpyDeviceToHost));
+    auto tuples_before_node = [&](int node) { return node >= d->n_nodes ? n_tuples : h_base[(size_t)node * n_pos]; };
+    std::vector<BatchPairs> parts;
+    const int end_bit = bits * d->k + 16;
+    for (int n0 = 0; n0 < d->n_nodes;) {
+      int n1 = n0 + 1;
+      while (n1 < d->n_nodes && tuples_before_node(n1 + 1) - tuples_before_node(n0) <= cap) n1++;
+      const unsigned long long nb = tuples_before_node(n1) - tuples_before_node(n0);
+      if (nb > cap && nb >= (1ull << 31))
+        return set_error(RP_E_UNSUPPORTED, "node %d alone yields %llu tuples (>= 2^31)", n0, nb);
+      if (nb) {
+        DevBuf b_key, b_score, b_key2, b_score2, b_runs, b_tmp;
+        RP_CUDA_TRY(b_key.alloc(nb * 8));
+        RP_CUDA_TRY(b_score.alloc(nb * 4));
+        RP_CUDA_TRY(b_key2.alloc(nb * 8));
+        RP_CUDA_TRY(b_score2.alloc(nb * 4));
+        RP_CUDA_TRY(b_runs.alloc(8));
+        const long long t0 = (long long)n0 * n_pos, nt_b = (long long)(n1 - n0) * n_pos;
+        explore_kernel<true><<<(int)((nt_b + threads - 1) / threads), threads>>>(
+            v, t0, nt_b, n_pos, d_oid.as<uint16_t>(), nullptr, d_base.as<unsigned long long>(), tuples_before_node(n0),
+            b_key.as<unsigned long long>(), b_score.as<float>());
+        g_kernel_launches.fetch_add(1);
+        RP_CUDA_TRY(cudaGetLastError());
+        size_t need = 0, need2 = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, need, b_key.as<unsigned long long>(), b_key2.as<unsigned long long>(),
+                                        b_score.as<float>(), b_score2.as<float>(), (int)nb, 0, end_bit);
+        cub::DeviceReduce::ReduceByKey(nullptr, need2, b_key2.as<unsigned long long>(), b_key.as<unsigned long long>(),
+                                       b_score2.as<float>(), b_score.as<float>(), b_runs.as<int>(), MaxOp(), (int)nb);
+        RP_CUDA_TRY(b_tmp.alloc(std::max(need, need2)));
+        RP_CUDA_TRY(cub::DeviceRadixSort::SortPairs(b_tmp.p, need, b_key.as<unsigned long long>(), b_key2.as<unsigned long long>(),
+                                                    b_score.as<float>(), b_score2.as<float>(), (int)nb, 0, end_bit));
+        RP_CUDA_TRY(cub::DeviceReduce::ReduceByKey(b_tmp.p, need2, b_key2.as<unsigned long long>(), b_key.as<unsigned long long>(),
+                                                   b_score2.as<float>(), b_score.as<float>(), b_runs.as<int>(), MaxOp(), (int)nb));
+        int nu = 0;
+        RP_CUDA_TRY(cudaMemcpy(&nu, b_runs.p, 4, cudaMemcpyDeviceToHost));
+        parts.emplace_back();
+        parts.back().key.resize((size_t)nu);
+        parts.back().score.resize((size_t)nu);
+        RP_CUDA_TRY(cudaMemcpy(parts.back().key.data(), b_key.p, (size_t)nu * 8, cudaMemcpyDeviceToHost));
+        RP_CUDA_TRY(cudaMemcpy(parts.back().score.data(), b_score.p, (size_t)nu * 4, cudaMemcpyDeviceToHost));
+      }
+      n0 = n1;
+    }
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    B->kernel_ms = ms;
+    merge_batches(parts, B->keys, B->offsets, B->post_node, B->post_score);
+    *out = B.release();
+    return RP_OK;
+  }
 
   DevBuf d_key, d_score, d_key2, d_score2, d_ukey, d_uscore, d_nruns, d_node, d_code, d_ucode, d_ucount;
   RP_CUDA_TRY(d_key.alloc(n_tuples * 8));
   RP_CUDA_TRY(d_score.alloc(n_tuples * 4));
-  explore_kernel<true><<<blocks, threads>>>(v, d->n_nodes, n_pos, d_oid.as<uint16_t>(), nullptr, d_base.as<unsigned long long>(),
-                                            d_key.as<unsigned long long>(), d_score.as<float>());
+  explore_kernel<true><<<blocks, threads>>>(v, 0, n_tasks, n_pos, d_oid.as<uint16_t>(), nullptr, d_base.as<unsigned long long>(),
+                                            0ull, d_key.as<unsigned long long>(), d_score.as<float>());
   g_kernel_launches.fetch_add(1);
   RP_CUDA_TRY(cudaGetLastError());
   // merge: sort by (code, node), keep the maximum of each run

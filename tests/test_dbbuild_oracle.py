@@ -125,3 +125,40 @@ def test_gap_intervals_equal_the_restatement():
         off, lens = dbbuild.gap_intervals(rows)
         got = [list(map(int, lens[int(off[j]):int(off[j + 1])])) or None for j in range(40)]
         assert got == restatement(rows)
+
+
+@pytest.mark.parametrize("n_batches", [1, 2, 3, 5, 8])
+def test_batch_merge_applies_the_maximum_again(n_batches):
+    """The product's host merge of per-batch results (rp_dbbuild_merge.h, compiled for the host): batches of
+    sorted distinct (code << 16 | node, score) pairs that share pair keys -> the CSR of the maximum."""
+    import ctypes as C
+    import os
+    import subprocess
+    from rappas_b200 import _abi
+    so = os.path.join(D.ROOT, "tests", "helpers", "dbbuild_merge_host.so")
+    src = os.path.join(D.ROOT, "tests", "helpers", "dbbuild_merge_host.cpp")
+    hdr = os.path.join(D.ROOT, "rappas_b200", "csrc", "rp_dbbuild_merge.h")
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src])
+    lib = C.CDLL(so)
+    rng = np.random.default_rng(n_batches)
+    keys, scores, bounds = [], [], [0]
+    for b in range(n_batches):
+        n = int(rng.integers(0, 400))
+        code = rng.integers(0, 60, n).astype(np.uint64)
+        node = rng.integers(0, 12, n).astype(np.uint64)
+        pk = np.unique((code << np.uint64(16)) | node)           # sorted, distinct within the batch
+        keys.append(pk)
+        scores.append((-rng.random(pk.size) * 5).astype(np.float32))
+        bounds.append(bounds[-1] + pk.size)
+    key = np.concatenate(keys) if keys else np.zeros(0, np.uint64)
+    score = np.concatenate(scores) if scores else np.zeros(0, np.float32)
+    bounds = np.asarray(bounds, np.uint64)
+    n = max(1, key.size)
+    ok, oo, on, os_ = np.zeros(n, np.uint64), np.zeros(n + 1, np.uint64), np.zeros(n, np.uint16), np.zeros(n, np.float32)
+    nk, npost = C.c_uint64(), C.c_uint64()
+    lib.merge_host(_abi.ptr(key) if key.size else None, _abi.ptr(score) if key.size else None, _abi.ptr(bounds), n_batches,
+                   C.byref(nk), C.byref(npost), _abi.ptr(ok), _abi.ptr(oo), _abi.ptr(on), _abi.ptr(os_))
+    got = dict(keys=ok[:nk.value], offsets=oo[:nk.value + 1], post_node=on[:npost.value], post_score=os_[:npost.value])
+    exp = D.csr_from_tuples(key >> np.uint64(16), (key & np.uint64(0xFFFF)).astype(np.uint16), score)
+    D.assert_csr_equal(got, exp)

@@ -66,3 +66,19 @@ def test_build_then_place():
     assert (out["status"] == 0).mean() > 0.9
     oo = O.OracleDB(db).place(rb)
     parity.assert_placements_equal(out, oo, 7, oo["counts"][:, _abi.CNT_AMBIG] > 0)
+
+
+@pytest.mark.parametrize("cap", [1, 2000, 9000])
+def test_build_in_node_batches(cap, monkeypatch):
+    """A build whose tuples do not fit one pass runs in batches of consecutive nodes and merges them on the host
+    (RP_DBBUILD_MAX_TUPLES forces it on a small input).  Several ancestral nodes share an original id here, so
+    the same (k-mer, node) pair comes back from different batches and the maximum has to be taken again."""
+    monkeypatch.setenv("RP_DBBUILD_MAX_TUPLES", str(cap))
+    pp, states, oid, goff, glen = D.make_inputs(0, 6, 9, 40, seed=21, peak=0.9, gap_rate=0.3)
+    oid = np.asarray([3, 7, 3, 1, 7, 3, 2, 1, 9], np.uint16)
+    thr = thr_of(0, 6)
+    o = D.oracle_build(0, 6, pp, states, oid, thr, goff, glen, 2)
+    g = dbbuild.build_db(0, 6, pp, states, oid, thr, goff, glen, 2)
+    assert g["n_tuples"] == o["n_tuples"] > 9000
+    D.assert_csr_equal({f: g[f] for f in ("keys", "offsets", "post_node", "post_score")},
+                       {f: o[f] for f in ("keys", "offsets", "post_node", "post_score")})
