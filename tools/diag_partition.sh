@@ -12,6 +12,22 @@ N=${N:-2}
 run $N "" n${N}_x1
 run $N "--postings-scale 1.5" n${N}_x1.5
 run $N "--postings-scale 2" n${N}_x2
+# the same GPUs in ONE process (peer access enabled by the library, no CUDA-IPC mappings): cfg2-like DB, layout 2
+python - <<'PY'
+import time
+import numpy as np
+import rappas_b200 as R
+from rappas_b200 import synth
+nd = R.device_count()
+db = synth.make_db(0, 10, 1999, n_keys=786432, mean_postings=32, seed=44)
+rb = synth.make_reads(db, 400000, 150, seed=1044)
+for layout, devs in ((0, (0,)), (2, tuple(range(nd)))):
+    g = R.Database.from_synth(db, devices=devs, partitioned=layout)
+    g.place(rb)
+    t0 = time.perf_counter(); g.place(rb); dt = time.perf_counter() - t0
+    print("in-process layout %d on %d GPU(s): %.1f M reads/s end to end" % (layout, len(devs), rb.n_reads / dt / 1e6))
+    g.close()
+PY
 python - <<'PY'
 import torch
 n = torch.cuda.device_count()
