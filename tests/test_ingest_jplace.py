@@ -191,3 +191,36 @@ def test_block_parallel_writer_equals_the_restatement(tmp_path, threads, monkeyp
     assert got_rows == [",".join(str(c) for c in row) for pl in exp for row in pl["p"]]
     assert [pl["nm"] for pl in doc["placements"]] == [pl["nm"] for pl in exp]
     assert npl.read_text().splitlines() == exp_np
+
+
+def test_ingest_fuzz_against_the_restatement(monkeypatch):
+    """Random FASTA-ish text over a small alphabet of troublesome bytes, cut into 1-5 pieces: the native parser
+    must agree with the restatement on every record, or fail where the restatement fails."""
+    from rappas_b200._lib import RappasError
+    rng = np.random.default_rng(12345)
+    alphabet = [">", "#", "\n", "\r", " ", "-", "A", "C", "G", "T", "N", "a", "\t", ">r", "\r\n", "ACGT", ">x y\n"]
+    weights = np.array([2, 1, 6, 2, 2, 2, 6, 6, 6, 6, 1, 1, 1, 3, 2, 8, 4], float)
+    weights /= weights.sum()
+    n_ok = n_err = 0
+    for it in range(300):
+        text = ">h0\n" * int(rng.random() < 0.8) + "".join(rng.choice(alphabet, int(rng.integers(0, 120)), p=weights))
+        monkeypatch.setenv("RP_HOST_THREADS", str(1 + it % 5))
+        try:
+            exp = ref_host.read_fasta(text)
+        except Exception:
+            exp = None
+        if exp is not None and len(exp) == 0:
+            exp = None  # "No valid fasta sequences were found"
+        if exp is None:
+            with pytest.raises(RappasError):
+                ingest.QueryFile.from_text(text)
+            n_err += 1
+            continue
+        q = ingest.QueryFile.from_text(text)
+        assert q.headers == [h for h, _ in exp], repr(text)
+        assert [q.unique.read(int(u)) for u in q.unique_of] == [s for _, s in exp], repr(text)
+        groups = {}
+        for r, (_, s) in enumerate(exp):
+            assert q.group_of[r] == groups.setdefault(s.replace("-", ""), len(groups)), repr(text)
+        n_ok += 1
+    assert n_ok > 150 and n_err > 5
