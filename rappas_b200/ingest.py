@@ -38,11 +38,22 @@ class QueryFile:
         self.unique = ReadBatch(_view(seq, int(seq_off[-1]), np.uint8), seq_off)
         hdr, hoff, uo, go = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
         check(fn["reads_records"](self._h, C.byref(hdr), C.byref(hoff), C.byref(uo), C.byref(go)))
-        hdr_off = _view(hoff, self.n_records + 1, np.uint64)
-        raw = _view(hdr, int(hdr_off[-1]), np.uint8).tobytes()
-        self.headers = [raw[int(hdr_off[i]):int(hdr_off[i + 1])].decode("latin-1") for i in range(self.n_records)]
+        self._hdr_off = _view(hoff, self.n_records + 1, np.uint64)
+        self._hdr_raw = _view(hdr, int(self._hdr_off[-1]), np.uint8).tobytes()
+        self._headers = None
         self.unique_of = _view(uo, self.n_records, np.uint32)
         self.group_of = _view(go, self.n_records, np.uint32)
+
+    @property
+    def headers(self):
+        """Header strings of all records (built on first use: a million Python strings take longer than the parse)."""
+        if self._headers is None:
+            o, raw = self._hdr_off, self._hdr_raw
+            self._headers = [raw[int(o[i]):int(o[i + 1])].decode("latin-1") for i in range(self.n_records)]
+        return self._headers
+
+    def header(self, i):
+        return self._hdr_raw[int(self._hdr_off[i]):int(self._hdr_off[i + 1])].decode("latin-1")
 
     @classmethod
     def from_file(cls, path):
