@@ -42,15 +42,23 @@ __host__ __device__ inline uint64_t block_bytes_for(uint64_t n_postings) {
   return (n_postings * 6 + kBlockAlign - 1) / kBlockAlign * kBlockAlign;
 }
 
-// 32-bit avalanche (lowbias32) of the folded key; the two bucket indices are the top bits of the
-// mix and of a second multiplicative hash of the mix.
-__host__ __device__ inline uint32_t mix_key(uint64_t key) {
-  uint32_t x = (uint32_t)key ^ ((uint32_t)(key >> 32) * 0x9E3779B1u);
-  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
-  return x;
+// Two independent 32-bit hashes of the 64-bit key: bucket 1 comes from `a`, bucket 2 from `b`, the owner
+// partition from both.  (Round 1 derived all three from ONE 32-bit mix of the folded key: five keys with
+// the same mix shared both buckets and the owner, so a DB of >= 2^27 keys -- exactly the DBs partitioning is
+// for -- could not be placed.)  For keys that fit 32 bits (nucl k <= 16, amino k <= 6) `a` is a bijection
+// of the key, so no two keys ever share (a, b); otherwise a full collision has probability 2^-64 per pair.
+struct KeyHash { uint32_t a, b; };
+__host__ __device__ inline KeyHash hash_key(uint64_t key) {
+  const uint32_t lo = (uint32_t)key, hi = (uint32_t)(key >> 32);
+  uint32_t a = lo ^ (hi * 0x9E3779B1u);
+  a ^= a >> 16; a *= 0x7feb352dU; a ^= a >> 15; a *= 0x846ca68bU; a ^= a >> 16;     // lowbias32
+  uint32_t b = (hi ^ (lo * 0x85EBCA6Bu)) + 0x7F4A7C15u;
+  b ^= b >> 17; b *= 0xed5ad4bbU; b ^= b >> 11; b *= 0xac4c1b51U; b ^= b >> 15; b *= 0x31848babU; b ^= b >> 14;  // triple32
+  KeyHash h; h.a = a; h.b = b;
+  return h;
 }
-__host__ __device__ inline uint32_t bucket1(uint32_t mix, int shift) { return mix >> shift; }
-__host__ __device__ inline uint32_t bucket2(uint32_t mix, int shift) { return (mix * 0x9E3779B1u + 0x7F4A7C15u) >> shift; }
+__host__ __device__ inline uint32_t bucket1(KeyHash h, int shift) { return h.a >> shift; }
+__host__ __device__ inline uint32_t bucket2(KeyHash h, int shift) { return h.b >> shift; }
 
 // ABI k-mer code (state i in bits [bits*i, bits*i+bits)) -> planar key (bit p of state i at bit
 // p*k + i).  The kernel gets the planes of 32 windows from `bits` pairs of __ballot_sync and one
@@ -99,15 +107,17 @@ struct DbView {
   const uint4* table[kMaxParts];      // [n_buckets][2] slots of partition p
   const uint8_t* blocks[kMaxParts];   // posting blocks of partition p
   int bucket_shift[kMaxParts];        // 32 - log2(n_buckets)
+  const uint64_t* direct;             // direct-address table (meta per planar key, kEmptyKey = absent) or null
   int n_parts;      // partitions of the posting blocks
   int table_parts;  // partitions of the table: n_parts, or 1 when every device holds the whole table (slot 0)
   int alphabet, k, bits, n_nodes, max_amb;
   float T, Tlin;
 };
-// owner partition of a key: a third multiplicative hash of the mix, so that the keys of one partition
-// still spread over all buckets of that partition's table under bucket1 / bucket2
-__host__ __device__ inline uint32_t owner_of(uint32_t mix, int n_parts) {
-  return (((mix * 0x85EBCA6Bu) >> 16) * (uint32_t)n_parts) >> 16;
+// owner partition of a key: a multiplicative hash of both halves, so that the keys of one partition still
+// spread over all buckets of that partition's table under bucket1 / bucket2
+__host__ __device__ inline uint32_t owner_of(KeyHash h, int n_parts) {
+  const uint32_t m = (h.a ^ ((h.b << 16) | (h.b >> 16))) * 0x85EBCA6Bu;
+  return ((m >> 16) * (uint32_t)n_parts) >> 16;
 }
 // meta = (partition << 61) | (qmax << 57) | (qmin << 53) | (block_offset_in_32B_units << 16) | n_postings
 // [qmin, qmax] = the sixteenths of the (padded) node range that the list's nodes fall into: the consumers
@@ -158,8 +168,9 @@ struct LaunchGeom {
   size_t smem_bytes = 0, per_warp_bytes = 0;
   int n_pad = 0;        // S[] entries per pair, multiple of 128
   int stage_bytes = 0;  // one posting stage (kStages per pair), multiple of 128
-  int max_chunks = 0;   // chunk descriptors per stage
-  int consumers = 1;    // consumer warps per team (1 producer + `consumers` warps share one read)
+  int max_chunks = 0;   // step descriptors (16 B: two chunks) per stage
+  int n_pass = 1;       // node-range passes per read: S holds one slice of n_pad / n_pass nodes at a time
+  int slice = 0;        // nodes per slice (multiple of 128); n_pad when n_pass == 1
 };
 
 struct DeviceCtx {
@@ -170,7 +181,14 @@ struct DeviceCtx {
   int local_part = 0;      // a partition resident on this device
   LaunchGeom geom;
   StreamCtx sc[2];  // double buffering for host-buffer calls (rp_place_batch)
-  StreamCtx sc_dev; // scheduler counter + scratch of device-buffer calls (rp_place_batch_device)
+  // rp_place_batch_device: one scheduler counter + ambiguity scratch PER CALLER STREAM (launches on one stream
+  // are ordered; two streams must not share them: the second launch's counter reset would hand the first
+  // kernel's reads out again).  Beyond kMaxDevSlots distinct streams a slot is shared and its `last` event
+  // orders the launches.
+  struct DevSlot { cudaStream_t user = nullptr; StreamCtx sc; cudaEvent_t last = nullptr; bool shared = false; };
+  static constexpr int kMaxDevSlots = 8;
+  std::vector<DevSlot*> dev_slots;
+  uint64_t dev_slot_rr = 0;
   std::mutex mu;
 };
 
@@ -180,6 +198,7 @@ namespace rp {
 struct Partition {   // one table + posting-block image resident on one device
   int device = -1;
   uint4* d_table = nullptr;
+  uint64_t* d_direct = nullptr;  // direct-address table (replicated nucleotide DBs with 4^k <= 2^24 keys), else null
   uint8_t* d_blocks = nullptr;
   uint64_t n_buckets = 0, block_bytes = 0;
   bool ipc = false;  // opened from another process' handle (cudaIpcCloseMemHandle instead of cudaFree)

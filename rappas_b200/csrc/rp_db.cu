@@ -103,6 +103,8 @@ DbView make_db_view(const rp_db* db, const DeviceCtx* dc) {
     v.table[0] = pt.d_table;
     v.bucket_shift[0] = 32 - log2_u64(pt.n_buckets);
   }
+  // direct-address table of a replicated small-key-space DB (this device's copy)
+  v.direct = (!db->partitioned && v.n_parts == 1) ? db->parts[dc->parts[0]].d_direct : nullptr;
   v.alphabet = db->desc.alphabet;
   v.k = db->desc.k;
   v.bits = alphabet_bits(db->desc.alphabet);
@@ -126,6 +128,7 @@ static int check_desc(const rp_db_desc* d) {
 // ---- host build of table + blocks (multi-threaded over key ranges) ------------------------------
 struct HostImage {
   std::vector<uint64_t> table;   // 2 u64 per slot, 2 slots per bucket
+  std::vector<uint64_t> direct;  // meta per planar key (kEmptyKey = absent): whole-DB images of small nucleotide key spaces
   uint8_t* blocks = nullptr;     // malloc'd, block_bytes
   uint64_t n_buckets = 0, block_bytes = 0, max_block_bytes = 0;
   ~HostImage() { free(blocks); }
@@ -135,7 +138,7 @@ struct HostImage {
 // eviction between a key's two buckets.  At load <= 0.5 with 2x2 buckets this is a handful of keys.
 static bool cuckoo_insert(std::vector<uint64_t>& tab, int shift, uint64_t key, uint64_t meta, uint64_t* rng) {
   for (int kick = 0; kick < 2000; kick++) {
-    const uint32_t m = mix_key(key);
+    const KeyHash m = hash_key(key);
     const uint32_t b[2] = {bucket1(m, shift), bucket2(m, shift)};
     for (int c = 0; c < 2; c++)
       for (int s = 0; s < kBucketSlots; s++) {
@@ -197,6 +200,10 @@ static int build_image(const rp_db_desc* d, const uint64_t* keys, const uint64_t
   std::atomic<int> err{0};
   const int n_nodes = d->n_nodes;
   const int bits = alphabet_bits(d->alphabet), k = d->k;
+  // Direct-address table beside the cuckoo table when the whole key space is small (nucleotide k <= 12: 4^k x 8 B
+  // <= 128 MB): one 8 B load per window, no hashing, no key compare.  Whole-DB images only.
+  const bool want_direct = !sel && !owners && d->alphabet == RP_ALPHA_NUCL && 2 * k <= 24 && !getenv("RP_NO_DIRECT");
+  if (want_direct) img->direct.assign((size_t)1 << (2 * k), kEmptyKey);
   const uint64_t code_limit = (bits * k >= 64) ? ~0ull : (1ull << (bits * k));
   std::vector<std::vector<std::pair<uint64_t, uint64_t>>> leftover(nt);
   auto pack_range = [&](unsigned tid, uint64_t k0, uint64_t k1) {
@@ -234,7 +241,8 @@ static int build_image(const rp_db_desc* d, const uint64_t* keys, const uint64_t
       const uint64_t qmin = P ? (uint64_t)tmp[0].first * 16 / n_pad : 0, qmax = P ? (uint64_t)tmp[P - 1].first * 16 / n_pad : 0;
       const uint64_t meta = ((uint64_t)own << kMetaPartShift) | (qmax << kMetaQmaxShift) | (qmin << kMetaQminShift) |
                             (boff[j] << 16) | P;
-      const uint32_t m32 = mix_key(key);
+      if (want_direct) img->direct[key] = meta;  // (a duplicate key is caught by the cuckoo placement below)
+      const KeyHash m32 = hash_key(key);
       const uint32_t bk[2] = {bucket1(m32, shift), bucket2(m32, shift)};
       bool placed = false;
       for (int c = 0; c < 2 && !placed; c++)
@@ -261,7 +269,7 @@ static int build_image(const rp_db_desc* d, const uint64_t* keys, const uint64_t
     for (auto& lv : leftover)
       for (auto& kv : lv) {
         // a key stays inside its own two buckets for ever, so a duplicate is visible there
-        const uint32_t m32 = mix_key(kv.first);
+        const KeyHash m32 = hash_key(kv.first);
         const uint32_t bk[2] = {bucket1(m32, shift), bucket2(m32, shift)};
         for (int c = 0; c < 2; c++)
           for (int s = 0; s < kBucketSlots; s++)
@@ -275,7 +283,8 @@ static int build_image(const rp_db_desc* d, const uint64_t* keys, const uint64_t
     case 2: return set_error(RP_E_INVALID, "a key lists the same node twice");
     case 3: return set_error(RP_E_INVALID, "duplicate key");
     case 4: return set_error(RP_E_INVALID, "key out of range for this alphabet and k (or the reserved 0xFFFFFFFFFFFFFFFF)");
-    case 5: return set_error(RP_E_NOMEM, "cuckoo placement failed (table too dense)");
+    case 5: return set_error(RP_E_INVALID, "cuckoo placement failed: a set of keys shares both candidate buckets (2 x 2 slots); "
+                              "with independent 32-bit bucket hashes this needs > 4 keys colliding in 64 hash bits");
     default: break;
   }
   return RP_OK;
@@ -284,7 +293,12 @@ static int build_image(const rp_db_desc* d, const uint64_t* keys, const uint64_t
 static void free_device_ctx(DeviceCtx* dc) {
   if (!dc) return;
   if (dc->device >= 0 && cudaSetDevice(dc->device) == cudaSuccess) {
-    StreamCtx* all[3] = {&dc->sc[0], &dc->sc[1], &dc->sc_dev};
+    std::vector<StreamCtx*> all = {&dc->sc[0], &dc->sc[1]};
+    for (auto* ds : dc->dev_slots) {
+      if (ds->user) cudaStreamSynchronize(ds->user);  // (a destroyed caller stream only returns an error here)
+      cudaGetLastError();
+      all.push_back(&ds->sc);
+    }
     for (StreamCtx* sp : all) {
       StreamCtx& s = *sp;
       if (s.stream) cudaStreamSynchronize(s.stream);
@@ -295,6 +309,7 @@ static void free_device_ctx(DeviceCtx* dc) {
       if (s.ev_k1) cudaEventDestroy(s.ev_k1);
       if (s.stream) cudaStreamDestroy(s.stream);
     }
+    for (auto* ds : dc->dev_slots) { if (ds->last) cudaEventDestroy(ds->last); delete ds; }
   }
   delete dc;
 }
@@ -375,6 +390,10 @@ int rp_db_load(const rp_db_desc* desc, const uint64_t* keys, const uint64_t* off
     if (e == cudaSuccess) e = cudaMalloc((void**)&pt.d_blocks, img.block_bytes + 512);
     if (e == cudaSuccess) e = cudaMemcpy(pt.d_table, img.table.data(), img.n_buckets * 32, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && img.block_bytes) e = cudaMemcpy(pt.d_blocks, img.blocks, img.block_bytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && !img.direct.empty()) {
+      e = cudaMalloc((void**)&pt.d_direct, img.direct.size() * 8);
+      if (e == cudaSuccess) e = cudaMemcpy(pt.d_direct, img.direct.data(), img.direct.size() * 8, cudaMemcpyHostToDevice);
+    }
     db->parts.push_back(pt);  // owned (and freed) by the db even on failure
     if (e != cudaSuccess) {
       const int code = (e == cudaErrorMemoryAllocation) ? RP_E_NOMEM : RP_E_CUDA;
@@ -401,7 +420,7 @@ int rp_db_load(const rp_db_desc* desc, const uint64_t* keys, const uint64_t* off
     std::vector<std::vector<uint64_t>> sel(n_parts);
     std::vector<uint8_t> owners(desc->n_keys);
     for (uint64_t i = 0; i < desc->n_keys; i++) {
-      owners[i] = (uint8_t)owner_of(mix_key(planar_from_code(keys[i], bits, desc->k)), n_parts);
+      owners[i] = (uint8_t)owner_of(hash_key(planar_from_code(keys[i], bits, desc->k)), n_parts);
       sel[owners[i]].push_back(i);
     }
     for (int p = 0; p < n_parts; p++) {
@@ -476,7 +495,7 @@ int rp_db_load_partition(const rp_db_desc* desc, const uint64_t* keys, const uin
   std::vector<uint64_t> sel;
   std::vector<uint8_t> owners(desc->n_keys);
   for (uint64_t i = 0; i < desc->n_keys; i++) {
-    owners[i] = (uint8_t)owner_of(mix_key(planar_from_code(keys[i], bits, desc->k)), n_parts);
+    owners[i] = (uint8_t)owner_of(hash_key(planar_from_code(keys[i], bits, desc->k)), n_parts);
     if ((int)owners[i] == part) sel.push_back(i);
   }
   HostImage img;
@@ -559,7 +578,7 @@ int rp_partition_of_keys(int32_t alphabet, int32_t k, const uint64_t* keys, uint
   if ((!keys || !out) && n_keys) return set_error(RP_E_INVALID, "NULL argument");
   if (n_parts < 1 || n_parts > kMaxParts) return set_error(RP_E_INVALID, "n_parts out of range");
   const int bits = alphabet_bits(alphabet);
-  for (uint64_t i = 0; i < n_keys; i++) out[i] = (int32_t)owner_of(mix_key(planar_from_code(keys[i], bits, k)), n_parts);
+  for (uint64_t i = 0; i < n_keys; i++) out[i] = (int32_t)owner_of(hash_key(planar_from_code(keys[i], bits, k)), n_parts);
   return RP_OK;
 }
 
@@ -569,7 +588,7 @@ void rp_db_free(rp_db* db) {
   for (auto& pt : db->parts) {
     if (pt.device < 0 || cudaSetDevice(pt.device) != cudaSuccess) continue;
     if (pt.ipc) { cudaIpcCloseMemHandle(pt.d_table); cudaIpcCloseMemHandle(pt.d_blocks); }
-    else { cudaFree(pt.d_table); cudaFree(pt.d_blocks); }
+    else { cudaFree(pt.d_table); cudaFree(pt.d_blocks); cudaFree(pt.d_direct); }
   }
   delete db;
 }

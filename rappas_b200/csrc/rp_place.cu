@@ -116,7 +116,11 @@ __device__ __forceinline__ void ldg_bucket(const uint4* p, uint4& a, uint4& b) {
                : "l"(p));
 }
 __device__ __forceinline__ bool table_probe(const DbView& db, uint64_t key, uint64_t& meta) {
-  const uint32_t m = mix_key(key);
+  if (db.direct) {  // direct-address table (small nucleotide key spaces)
+    meta = __ldg(reinterpret_cast<const unsigned long long*>(db.direct) + key);
+    return meta != kEmptyKey;
+  }
+  const KeyHash m = hash_key(key);
   const int part = db.table_parts > 1 ? (int)owner_of(m, db.table_parts) : 0;
   const uint4* table = db.table[part];
   const int shift = db.bucket_shift[part];
@@ -302,22 +306,33 @@ __device__ __forceinline__ void top_insert(TopList& t, float cs, int cx, int K, 
   if (lane == pos) { t.s = cs; t.x = cx; }
   if (t.cnt < K) t.cnt++;
 }
-__device__ __forceinline__ TopList select_scan(const CfgView& cfg, float* __restrict__ S, int lo, int hi, bool emit,
-                                               float* dump_row, int n_nodes, int lane) {
+// `S` holds the n nodes (multiple of 128) [node0, node0 + n) of the tree: one slice of a pass, or all of it.
+// The candidates are merged into the running list `t` (top-K over the slices seen so far).  Both sweeps run
+// four float4 loads ahead (one vote per 512 nodes): with few warps per SM the sweep is latency-bound.
+__device__ __forceinline__ void select_scan(const CfgView& cfg, float* __restrict__ S, int n, int node0, bool emit,
+                                            float* dump_row, int n_nodes, int lane, TopList& t) {
   const int K = cfg.K;
-  TopList t;
-  t.s = -INFINITY; t.x = 0xFFFF; t.cnt = 0;
   const float4 sent4 = make_float4(__uint_as_float(kSentinelBits), __uint_as_float(kSentinelBits),
                                    __uint_as_float(kSentinelBits), __uint_as_float(kSentinelBits));
   if (!emit) {
-    for (int i = lo + lane * 4; i < hi; i += 128) *reinterpret_cast<float4*>(S + i) = sent4;
+    for (int i = lane * 4; i < n; i += 128) *reinterpret_cast<float4*>(S + i) = sent4;
     __syncwarp();
-    return t;
+    return;
   }
   float m = -INFINITY;  // fmaxf ignores the NaN sentinel
-  for (int i = lo + lane * 4; i < hi; i += 128) {
-    const float4 q = *reinterpret_cast<const float4*>(S + i);
-    m = fmaxf(m, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
+  {
+    int i = lane * 4;
+    for (; i + 384 < n; i += 512) {
+      const float4 q0 = *reinterpret_cast<const float4*>(S + i), q1 = *reinterpret_cast<const float4*>(S + i + 128);
+      const float4 q2 = *reinterpret_cast<const float4*>(S + i + 256), q3 = *reinterpret_cast<const float4*>(S + i + 384);
+      const float m0 = fmaxf(fmaxf(q0.x, q0.y), fmaxf(q0.z, q0.w)), m1 = fmaxf(fmaxf(q1.x, q1.y), fmaxf(q1.z, q1.w));
+      const float m2 = fmaxf(fmaxf(q2.x, q2.y), fmaxf(q2.z, q2.w)), m3 = fmaxf(fmaxf(q3.x, q3.y), fmaxf(q3.z, q3.w));
+      m = fmaxf(m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+    }
+    for (; i < n; i += 128) {
+      const float4 q = *reinterpret_cast<const float4*>(S + i);
+      m = fmaxf(m, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
+    }
   }
   float tau = -INFINITY;
   {
@@ -330,20 +345,14 @@ __device__ __forceinline__ TopList select_scan(const CfgView& cfg, float* __rest
       const uint32_t holders = __ballot_sync(0xffffffffu, u == mx);
       if (lane == __ffs(holders) - 1) u = floor_u;
     }
+    // a full list from earlier slices raises the bar: only nodes that beat its K-th entry can enter
+    if (t.cnt >= K) tau = fmaxf(tau, __shfl_sync(0xffffffffu, t.s, K - 1));
   }
-  for (int i0 = lo; i0 < hi; i0 += 128) {
-    const int i = i0 + lane * 4;
-    const float4 q = *reinterpret_cast<const float4*>(S + i);
-    *reinterpret_cast<float4*>(S + i) = sent4;
-    if (dump_row) {
-      const float qq[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-      for (int c = 0; c < 4; c++)
-        if (i + c < n_nodes && !is_sentinel(qq[c])) dump_row[i + c] = qq[c];
-    }
+  // one 128-node row: reset, dump, and push the nodes >= tau (a handful per read) into the list
+  auto row = [&](int i0, const float4 q) {
     // NaN >= tau is false: untouched nodes never qualify
     const bool c0 = q.x >= tau, c1 = q.y >= tau, c2 = q.z >= tau, c3 = q.w >= tau;
-    if (!__any_sync(0xffffffffu, c0 | c1 | c2 | c3)) continue;
+    if (!__any_sync(0xffffffffu, c0 | c1 | c2 | c3)) return;
 #pragma unroll
     for (int c = 0; c < 4; c++) {
       const float sc = c == 0 ? q.x : c == 1 ? q.y : c == 2 ? q.z : q.w;
@@ -352,12 +361,39 @@ __device__ __forceinline__ TopList select_scan(const CfgView& cfg, float* __rest
       while (pm) {
         const int src = __ffs(pm) - 1;
         pm &= pm - 1;
-        top_insert(t, __shfl_sync(0xffffffffu, sc, src), i0 + src * 4 + c, K, lane);
+        top_insert(t, __shfl_sync(0xffffffffu, sc, src), node0 + i0 + src * 4 + c, K, lane);
       }
     }
+  };
+  auto dump = [&](int i, const float4 q) {
+    const float qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+      if (node0 + i + c < n_nodes && !is_sentinel(qq[c])) dump_row[node0 + i + c] = qq[c];
+  };
+  int i0 = 0;
+  for (; i0 + 384 < n; i0 += 512) {
+    const int i = i0 + lane * 4;
+    const float4 q0 = *reinterpret_cast<const float4*>(S + i), q1 = *reinterpret_cast<const float4*>(S + i + 128);
+    const float4 q2 = *reinterpret_cast<const float4*>(S + i + 256), q3 = *reinterpret_cast<const float4*>(S + i + 384);
+    *reinterpret_cast<float4*>(S + i) = sent4;
+    *reinterpret_cast<float4*>(S + i + 128) = sent4;
+    *reinterpret_cast<float4*>(S + i + 256) = sent4;
+    *reinterpret_cast<float4*>(S + i + 384) = sent4;
+    if (dump_row) { dump(i, q0); dump(i + 128, q1); dump(i + 256, q2); dump(i + 384, q3); }
+    const float h0 = fmaxf(fmaxf(q0.x, q0.y), fmaxf(q0.z, q0.w)), h1 = fmaxf(fmaxf(q1.x, q1.y), fmaxf(q1.z, q1.w));
+    const float h2 = fmaxf(fmaxf(q2.x, q2.y), fmaxf(q2.z, q2.w)), h3 = fmaxf(fmaxf(q3.x, q3.y), fmaxf(q3.z, q3.w));
+    if (!__any_sync(0xffffffffu, fmaxf(fmaxf(h0, h1), fmaxf(h2, h3)) >= tau)) continue;
+    row(i0, q0); row(i0 + 128, q1); row(i0 + 256, q2); row(i0 + 384, q3);
+  }
+  for (; i0 < n; i0 += 128) {
+    const int i = i0 + lane * 4;
+    const float4 q = *reinterpret_cast<const float4*>(S + i);
+    *reinterpret_cast<float4*>(S + i) = sent4;
+    if (dump_row) dump(i, q);
+    row(i0, q);
   }
   __syncwarp();
-  return t;
 }
 // LWR of the kept nodes and the rows of the read.  Returns rows written, or -1 if no node was touched.
 __device__ __forceinline__ int finalize_rows(const CfgView& cfg, const TopList& t, uint16_t* out_node, float* out_score,
@@ -373,10 +409,22 @@ __device__ __forceinline__ int finalize_rows(const CfgView& cfg, const TopList& 
   // fillBestScoreList `lowest` starts at 0.0f (:413): min(0,lowest) <= -308  <=>  lowest <= -308.
   const float shift = (-308.0f >= lowest) ? best : 0.0f;
   // computeWeightRatio: Math.pow(10.0,(double)(s.score-weightRatioShift))/sum with a double shift (:392-393)
+  // One f64 exp10 per read instead of two (it is ~150 instructions on 7 of 32 lanes; 9.5 % of the stall samples of
+  // the round-1 kernel sat behind the pair of calls): lanes 0..15 take the numerators, lanes 16..31 the shifted
+  // terms of the sum for the same nodes.  K > 16 keeps the two calls.
   double num = 0.0, e = 0.0;
-  if (lane < nb) {
-    num = exp10((double)top_s - (double)shift);
+  if (K <= 16) {
+    const float ts = __shfl_sync(0xffffffffu, top_s, lane & 15);
+    const bool valid = (lane & 15) < nb;
     // the sum's terms subtract in f32 when shifted (:446), else they are the plain powers (:418)
+    const double arg = (lane >= 16) ? (double)__fsub_rn(ts, shift) : (double)ts - (double)shift;
+    const double ex = (valid && (lane < 16 || shift != 0.0f)) ? exp10(arg) : 0.0;
+    const double ex_hi = __shfl_sync(0xffffffffu, ex, (lane & 15) + 16);
+    num = ex;
+    e = (shift != 0.0f) ? ex_hi : ex;
+    if (lane >= nb) { num = 0.0; e = 0.0; }
+  } else if (lane < nb) {
+    num = exp10((double)top_s - (double)shift);
     e = (shift != 0.0f) ? exp10((double)__fsub_rn(top_s, shift)) : num;
   }
   double sum = 0.0;  // ascending score order, as the rebuilt sum of :445-447
@@ -404,8 +452,11 @@ __device__ __forceinline__ int finalize_rows(const CfgView& cfg, const TopList& 
 // alternative order, and the rest of the stage is the consumer's S_amb/C_amb table.  kGrpAmbGlobal: same
 // window, but its alternatives did not fit a stage: the consumer walks them in global memory.
 // Their flags also carry W_size (bits 8-12) and log2 of the table entries per consumer (bits 16-19).
-enum : int { kGrpLast = 1, kGrpBad = 2, kGrpTooLong = 4, kGrpStop = 8, kGrpAmb = 16, kGrpAmbGlobal = 32 };
-constexpr int kGrpWsizeShift = 8, kGrpTabShift = 16;
+// kGrpPassEnd: last group of a node-range pass that is not the read's last (the consumer selects over the slice
+// and resets it); the pass index travels in bits 24-27.
+enum : int { kGrpLast = 1, kGrpBad = 2, kGrpTooLong = 4, kGrpStop = 8, kGrpAmb = 16, kGrpAmbGlobal = 32, kGrpPassEnd = 64 };
+constexpr int kGrpWsizeShift = 8, kGrpTabShift = 16, kGrpPassShift = 24;
+constexpr int kMaxPasses = 16;  // slices are routed by sixteenths of the node range
 struct __align__(16) StageHdr {
   long long r;           // read index in the batch
   const uint8_t* seq;    // character g0 of the read: first window of this group
@@ -413,8 +464,8 @@ struct __align__(16) StageHdr {
   float QT;              // (float)Q * T
   int flags;             // kGrp*
   int n_match, n_amb, n_skip;       // totals of the read, valid on its last group
-  int n_chunks;                     // chunk descriptors of the staged windows
-  uint32_t hitm, staged_bytes, stagedm;  // windows (bit l = window g0+l) matched / bytes staged / windows staged
+  int n_chunks;                     // step descriptors (two chunks each) of the staged windows
+  uint32_t hitm, staged_bytes, stagedm;  // windows (bit l = window g0+l) matched and routed to this pass / bytes staged / windows staged
   int pad[2];
 };
 static_assert(sizeof(StageHdr) == 64, "StageHdr is one 64 B slot");
@@ -423,7 +474,7 @@ static_assert(sizeof(StageHdr) == 64, "StageHdr is one 64 B slot");
 //   [0,32)    full[kStages], empty[kStages] mbarriers
 //   [64, ..)  kStages x { StageHdr (64 B) | pk u32[32] | meta u64[32] }  = 448 B each
 //   stage     kStages x stage_bytes        posting blocks as they lie in HBM
-//   desc      kStages x C x max_chunks x 8 B   chunk descriptors {shared address of the scores, m}, one list per consumer
+//   desc      kStages x max_chunks x 16 B  step descriptors: 2 x {shared address of a chunk's scores, m}
 //   S         f32[n_pad + 32]              (+32: per-lane dummies for the idle lanes of a short chunk)
 constexpr int kStageMetaBytes = 64 + 128 + 256;
 static_assert((kStages * kStageMetaBytes) % 64 == 0, "stages start 16 B aligned");
@@ -449,50 +500,57 @@ __device__ __forceinline__ void rmw_store(uint32_t a, float s, float d, float QT
       : "memory");
 }
 
-// Adds the staged posting blocks of a whole group into S, chunk by chunk, in window order.  Four register
-// slots (m, score, node) rotate through the descriptor list and the descriptors themselves are fetched
-// earlier still, so no instruction of a step waits on a load issued in the same step: the loads of
-// chunk j+4 are issued between the S[x] load of chunk j and its dependent tail.  The list is padded with
-// idle descriptors (m = 0) for the rounds of four + look-ahead.  Every shared-memory instruction counts
-// here (the load/store pipe is shared with the producers' probes): descriptors are read two per LDS.128.
-// SLICED: this warp is one of several consumers of the read and owns the nodes [lo, lo+width) only.
-#define RP_CHUNK_STEP(M_, V_, X_, DX_, DY_, FETCH_)                                                    \
+// Adds the staged posting blocks of a whole group into S, in window order, TWO CHUNKS PER STEP.  A step descriptor
+// (16 B) names two chunks {scores address, m} that cannot touch the same node -- two chunks of one window (a
+// posting list never repeats a node), or the chunks of two neighbouring windows whose node ranges (the
+// sixteenths kept in the table entry) do not intersect; the producer pairs them and leaves slot B idle (m = 0)
+// where it cannot.  Both S[x] loads of a step are issued before both stores, so one shared-memory round trip
+// retires up to 64 postings: with the few warps a big tree leaves per SM the loop is bound by exactly that
+// dependent round trip (round 1: one chunk per trip).  Per-node order is untouched: chunks that share a node
+// are never in one step, and steps are taken in order.  Two register slots rotate through the list and the
+// descriptors are fetched two steps ahead, so no instruction waits on a load issued in the same step; the
+// list is padded with idle steps for the look-ahead.
+// SLICED: S holds the nodes [lo, lo + width) only (one pass of a big tree); other nodes are predicated off.
+#define RP_STEP2(MA_, VA_, XA_, MB_, VB_, XB_, D_, FETCH_)                                             \
   {                                                                                                    \
-    const uint32_t a_ = s_base + 4 * X_;                                                               \
-    const uint32_t p_ = SLICED ? (uint32_t)(lane < M_ && X_ - lo < width) : (uint32_t)(lane < M_);     \
-    const float s_ = rmw_load(a_, p_);                                                                 \
-    const float d_ = __fsub_rn(V_, T);                                                                 \
-    M_ = DY_;                                                                                          \
-    V_ = lds_f32(DX_ + lane4);                                                                         \
-    X_ = lds_u16(DX_ + 4 * DY_ + lane2);                                                               \
+    const uint32_t xa_ = SLICED ? XA_ - lo : XA_, xb_ = SLICED ? XB_ - lo : XB_;                       \
+    const uint32_t aa_ = s_base + 4 * xa_, ab_ = s_base + 4 * xb_;                                     \
+    const uint32_t pa_ = SLICED ? (uint32_t)(lane < MA_ && xa_ < width) : (uint32_t)(lane < MA_);      \
+    const uint32_t pb_ = SLICED ? (uint32_t)(lane < MB_ && xb_ < width) : (uint32_t)(lane < MB_);      \
+    const float sa_ = rmw_load(aa_, pa_);                                                              \
+    const float sb_ = rmw_load(ab_, pb_);                                                              \
+    const float da_ = __fsub_rn(VA_, T), db_ = __fsub_rn(VB_, T);                                      \
+    MA_ = D_.y;                                                                                        \
+    VA_ = lds_f32(D_.x + lane4);                                                                       \
+    XA_ = lds_u16(D_.x + 4 * D_.y + lane2);                                                            \
+    MB_ = D_.w;                                                                                        \
+    VB_ = lds_f32(D_.z + lane4);                                                                       \
+    XB_ = lds_u16(D_.z + 4 * D_.w + lane2);                                                            \
     FETCH_                                                                                             \
-    rmw_store(a_, s_, d_, QT0, p_);                                                                    \
+    rmw_store(aa_, sa_, da_, QT0, pa_);                                                                \
+    rmw_store(ab_, sb_, db_, QT0, pb_);                                                                \
   }
 template <bool SLICED>
-__device__ __forceinline__ void accumulate_chunks(float* __restrict__ S, uint32_t dl, int n_chunks, float QT0, float T,
+__device__ __forceinline__ void accumulate_chunks(float* __restrict__ S, uint32_t dl, int n_steps, float QT0, float T,
                                                   int lane, uint32_t lo, uint32_t width) {
   const uint32_t lane4 = lane * 4, lane2 = lane * 2;
   const uint32_t s_base = smem_u32(S);
-  // descriptors travel in pairs (one LDS.128 per two chunks; the lists are 16 B aligned): e = chunks j+4, j+5
-  // of the round, f = chunks j+6, j+7, each fetched two steps before its first use
-  const uint4 d01 = lds_u128(dl), d23 = lds_u128(dl + 16);
-  uint4 e = lds_u128(dl + 32), f;
-  float v0 = lds_f32(d01.x + lane4), v1 = lds_f32(d01.z + lane4), v2 = lds_f32(d23.x + lane4), v3 = lds_f32(d23.z + lane4);
-  uint32_t x0 = lds_u16(d01.x + 4 * d01.y + lane2), x1 = lds_u16(d01.z + 4 * d01.w + lane2);
-  uint32_t x2 = lds_u16(d23.x + 4 * d23.y + lane2), x3 = lds_u16(d23.z + 4 * d23.w + lane2);
-  uint32_t m0 = d01.y, m1 = d01.w, m2 = d23.y, m3 = d23.w;
-  uint32_t dp = dl + 48;  // descriptors j+6, j+7 of the round's first chunk
-  const uint32_t dend = dl + 48 + 8 * n_chunks;
+  const uint4 d0 = lds_u128(dl), d1 = lds_u128(dl + 16);
+  uint4 e = lds_u128(dl + 32), f = lds_u128(dl + 48);
+  uint32_t ma0 = d0.y, mb0 = d0.w, ma1 = d1.y, mb1 = d1.w;
+  float va0 = lds_f32(d0.x + lane4), vb0 = lds_f32(d0.z + lane4), va1 = lds_f32(d1.x + lane4), vb1 = lds_f32(d1.z + lane4);
+  uint32_t xa0 = lds_u16(d0.x + 4 * d0.y + lane2), xb0 = lds_u16(d0.z + 4 * d0.w + lane2);
+  uint32_t xa1 = lds_u16(d1.x + 4 * d1.y + lane2), xb1 = lds_u16(d1.z + 4 * d1.w + lane2);
+  uint32_t dp = dl + 64;  // descriptor of step j+4 of the round's first step
+  const uint32_t dend = dl + 64 + 16 * n_steps;
 #pragma unroll 1
   for (; dp < dend; dp += 32) {
-    RP_CHUNK_STEP(m0, v0, x0, e.x, e.y, f = lds_u128(dp);)
-    RP_CHUNK_STEP(m1, v1, x1, e.z, e.w, )
-    RP_CHUNK_STEP(m2, v2, x2, f.x, f.y, e = lds_u128(dp + 16);)
-    RP_CHUNK_STEP(m3, v3, x3, f.z, f.w, )
+    RP_STEP2(ma0, va0, xa0, mb0, vb0, xb0, e, e = lds_u128(dp);)
+    RP_STEP2(ma1, va1, xa1, mb1, vb1, xb1, f, f = lds_u128(dp + 16);)
   }
   __syncwarp();
 }
-#undef RP_CHUNK_STEP
+#undef RP_STEP2
 
 // Same for one posting block, staged (p = shared address) -- slow path of a group with special windows
 __device__ __forceinline__ void accumulate_staged(float* __restrict__ S, uint32_t p, int len, float QT0, float T, int lane,
@@ -590,25 +648,38 @@ struct PairSmem {
 // while the descriptors and bulk copies of group i are written: the characters of the next group are
 // already in registers (the class bytes of 96 characters are kept, shifted by the number of windows the
 // group consumed, and the following 32 are prefetched), so its keys need no memory access.
+// DIRECT: nucleotide DBs with 4^k <= 2^24 possible keys carry a direct-address table (one u64 meta per planar
+// key, kEmptyKey = absent) beside the cuckoo table: one 8 B load per window instead of two 32 B buckets, no
+// hashing and no key compare (the cuckoo table stays the general form).
 struct ProbeIO {
-  uint4 s0, s1, s2, s3;   // the four candidate slots (in flight after issue)
+  uint4 s0, s1, s2, s3;   // the four candidate slots (in flight after issue); DIRECT: s0.x/y = the meta
   uint32_t klo, khi;
 };
+template <bool DIRECT>
 __device__ __forceinline__ void probe_issue(const DbView& db, uint64_t key, bool active, ProbeIO& io) {
   io.klo = (uint32_t)key; io.khi = (uint32_t)(key >> 32);
   io.s0 = io.s1 = io.s2 = io.s3 = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u);  // the empty key never matches
   if (active) {
-    const uint32_t m = mix_key(key);
-    const int part = db.table_parts > 1 ? (int)owner_of(m, db.table_parts) : 0;
-    const uint4* table = db.table[part];
-    const int shift = db.bucket_shift[part];
-    const uint4* p1 = table + (size_t)bucket1(m, shift) * kBucketSlots;
-    const uint4* p2 = table + (size_t)bucket2(m, shift) * kBucketSlots;
-    ldg_bucket(p1, io.s0, io.s1);
-    ldg_bucket(p2, io.s2, io.s3);
+    if (DIRECT) {
+      asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(io.s0.x), "=r"(io.s0.y) : "l"(db.direct + key));
+    } else {
+      const KeyHash m = hash_key(key);
+      const int part = db.table_parts > 1 ? (int)owner_of(m, db.table_parts) : 0;
+      const uint4* table = db.table[part];
+      const int shift = db.bucket_shift[part];
+      const uint4* p1 = table + (size_t)bucket1(m, shift) * kBucketSlots;
+      const uint4* p2 = table + (size_t)bucket2(m, shift) * kBucketSlots;
+      ldg_bucket(p1, io.s0, io.s1);
+      ldg_bucket(p2, io.s2, io.s3);
+    }
   }
 }
+template <bool DIRECT>
 __device__ __forceinline__ bool probe_resolve(const ProbeIO& io, uint64_t& meta) {
+  if (DIRECT) {
+    meta = (uint64_t)io.s0.x | ((uint64_t)io.s0.y << 32);
+    return (io.s0.x & io.s0.y) != 0xffffffffu;
+  }
   const bool h0 = io.s0.x == io.klo && io.s0.y == io.khi, h1 = io.s1.x == io.klo && io.s1.y == io.khi;
   const bool h2 = io.s2.x == io.klo && io.s2.y == io.khi, h3 = io.s3.x == io.klo && io.s3.y == io.khi;
   const uint32_t z = h0 ? io.s0.z : h1 ? io.s1.z : h2 ? io.s2.z : io.s3.z;
@@ -617,26 +688,19 @@ __device__ __forceinline__ bool probe_resolve(const ProbeIO& io, uint64_t& meta)
   return h0 | h1 | h2 | h3;
 }
 
-template <int C>
+// SLICED: the tree is too big for all of S[] to stay in shared memory with enough reads per SM, so a read is
+// walked n_pass times; pass p accumulates the nodes [p * slice, (p + 1) * slice) only.  A window is staged in
+// the passes whose slice its (node-sorted) posting list can touch: the table entry carries the first and the
+// last sixteenth of the padded node range the list spans.  Every node belongs to exactly one pass and the
+// windows of a pass are visited in order, so each S[x] still sees the reference's f32 addition sequence.
+template <bool SLICED, bool DIRECT>
 __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const DbView& db, const CfgView& cfg,
                                          const BatchView& bt, unsigned long long* work_counter, const PairSmem& w,
-                                         uint32_t cls_tab, int lane, int n_pad) {
-  constexpr uint32_t n_cons = C;
-  // C > 1: consumer c owns the node slice [c*per, (c+1)*per); qb holds, per consumer, the first and the last
-  // sixteenth of the padded node range that its slice overlaps (4 + 4 bits each) -- a window whose list
-  // spans the sixteenths [qmin, qmax] (kept in its table entry) is routed to consumer c iff they intersect
-  uint32_t qb = 0;
-  if (C > 1) {
-    const int per = ((n_pad / 128 + C - 1) / C) * 128, u = n_pad / 16;
-    for (int c = 0; c < C; c++) {
-      const int lo_c = min(c * per, n_pad), hi_c = min(lo_c + per, n_pad);
-      const int qlo = lo_c / u, qhi = hi_c > lo_c ? (hi_c - 1) / u : 0;
-      qb |= (uint32_t)((hi_c > lo_c ? qlo : 15) | (qhi << 4)) << (8 * c);  // empty slice: qlo 15 > qhi 0, never hit
-    }
-  }
+                                         uint32_t cls_tab, int lane, int n_pad, int slice, int n_pass) {
   const int k = db.k;
   const uint32_t kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
   const int stage_bytes = w.stage_bytes;
+  const uint32_t lt_mask = (1u << lane) - 1u;
   // (read indices are 32-bit here: rp_place_batch_device refuses batches of 2^31 reads or more)
   uint32_t rn_raw = 0;  // lane 0: result of the atomicAdd that fetched the read after the next
   if (lane == 0) rn_raw = (uint32_t)atomicAdd(work_counter, 1ull);
@@ -646,6 +710,9 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
   int len = 0, Ql = 0, g0 = 0, n_match = 0, n_amb = 0, n_skip = 0;
   bool too_long = false;
   float QT = 0.f;
+  // the node-range pass of the read, and the sixteenths of the padded node range its slice overlaps
+  int pass = 0;
+  uint32_t pqlo = 0, pqhi = 15;
   // group about to be published: class bytes of characters [g0, g0+64), raw characters [g0+64, g0+96)
   uint32_t cA = kClsPad, cB = kClsPad, rawC = 0;
   // its window classification and its probe in flight
@@ -684,7 +751,7 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
         key |= (uint64_t)(__funnelshift_r(b0, b1, lane) & kmask) << (p * k);
       }
     }
-    probe_issue(db, key, g_plain, io);
+    probe_issue<DIRECT>(db, key, g_plain, io);
   };
   // The alternatives of the ambiguous window g0 (class bytes in cA): lane t < W_size probes alternative t,
   // in which position o_m takes A_m[t mod |A_m|]  (AmbigSequenceKnife.java:249-256).  Returns W_size.
@@ -720,6 +787,19 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       nx_o1 = bt.seq_off[nx_r + 1];
     }
   };
+  // first 96 characters of the read (a pass starts here again)
+  auto load_chars = [&]() {
+    g0 = 0;
+    n_match = n_amb = n_skip = 0;
+    cA = lane < len ? lds_u8(cls_tab + s[lane]) : (uint32_t)kClsPad;
+    cB = lane + 32 < len ? lds_u8(cls_tab + s[lane + 32]) : (uint32_t)kClsPad;
+    rawC = lane + 64 < len ? s[lane + 64] : 0u;
+    if (SLICED) {
+      const int u = n_pad >> 4, lo = pass * slice, hi = min(lo + slice, n_pad);
+      pqlo = (uint32_t)(lo / u);
+      pqhi = (uint32_t)((hi - 1) / u);
+    }
+  };
   // next read of this pair: false when the batch is exhausted
   auto start_read = [&]() -> bool {
     if (!nx_have) return false;
@@ -729,11 +809,8 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
     len = too_long ? 0 : (int)(nx_o1 - nx_o0);
     Ql = len - k + 1;  // sk.getMerCount()
     QT = __fmul_rn((float)Ql, db.T);  // Q*PPStarThresholdAsLog10 (int*float)
-    g0 = 0;
-    n_match = n_amb = n_skip = 0;
-    cA = lane < len ? lds_u8(cls_tab + s[lane]) : (uint32_t)kClsPad;
-    cB = lane + 32 < len ? lds_u8(cls_tab + s[lane + 32]) : (uint32_t)kClsPad;
-    rawC = lane + 64 < len ? s[lane + 64] : 0u;
+    pass = 0;
+    load_chars();
     fetch_next_offsets();
     front();
     return true;
@@ -762,15 +839,15 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       }
       return;
     }
-    int flags = too_long ? kGrpTooLong : 0;
-    int n_chunks = 0;
+    int flags = (too_long ? kGrpTooLong : 0) | (SLICED ? pass << kGrpPassShift : 0);
+    int n_steps = 0;
     uint32_t hitm = 0, stagedm = 0, total = 0;
     const uint8_t* seq_g0 = s + g0;
     // per-lane results of this group that the publication below needs
     uint64_t meta = 0;
     uint32_t n_post = 0, bytes = 0, my_chunks = 0, incl_chunks = 0, off = 0, incl = 0;
     int cons = 0, last = 0;
-    bool more = false;  // another group of this read follows (its probe is issued below)
+    bool more = false;  // another group of this pass follows (its probe is issued below)
     if (RP_UNLIKELY(g_bad)) {
       // an unsupported character aborts the reference whatever the length (AmbigSequenceKnife.java:124-128)
       flags |= kGrpBad | kGrpLast;
@@ -780,13 +857,19 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       bool found;
       int wsize = 0;
       if (RP_UNLIKELY(g_nv == 0)) wsize = probe_alternatives(found, meta);
-      else found = probe_resolve(io, meta);
+      else found = probe_resolve<DIRECT>(io, meta);
+      // node-range pass: only the windows whose list can touch this pass's slice are staged
+      bool routed = found;
+      if (SLICED) {
+        const uint32_t q8 = (uint32_t)(meta >> kMetaQminShift) & 0xFFu;  // qmin | qmax << 4
+        routed = found && (q8 & 15u) <= pqhi && (q8 >> 4) >= pqlo;
+      }
       // stage assignment: windows are taken in order while their posting blocks fit into the stage;
       // a block larger than a whole stage is read from global memory by the consumer instead
-      n_post = found ? (uint32_t)(meta & 0xFFFF) : 0u;
+      n_post = routed ? (uint32_t)(meta & 0xFFFF) : 0u;
       bytes = (n_post * 6 + 31) & ~31u;
       const bool giant = bytes > (uint32_t)stage_bytes;
-      const uint32_t sb = (found && !giant) ? bytes : 0u;
+      const uint32_t sb = (routed && !giant) ? bytes : 0u;
       // one scan for both prefix sums: bytes in 32 B units (<= 2^15 over the warp) above the chunk count (< 2^13)
       my_chunks = sb ? (n_post + 31) >> 5 : 0u;
       incl = (sb >> 5 << 13) | my_chunks;
@@ -799,12 +882,12 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       incl_chunks = incl & 0x1FFFu;
       const uint32_t nofit = __ballot_sync(0xffffffffu, incl_bytes > (uint32_t)stage_bytes);
       if (RP_UNLIKELY(wsize != 0)) {
-        // all the alternatives found, plus a table of >= as many entries as they have postings (per
-        // consumer), in one stage -- or nothing is staged and the consumer reads them from global memory
+        // all the alternatives found, plus a table of >= as many entries as they have postings, in one
+        // stage -- or nothing is staged and the consumer reads them from global memory
         const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
         const uint32_t tot_bytes = tot >> 13 << 5, tot_chunks = tot & 0x1FFFu;
-        const uint32_t foundm = __ballot_sync(0xffffffffu, found), giantm = __ballot_sync(0xffffffffu, found && giant);
-        const uint32_t room = (tot_bytes <= (uint32_t)stage_bytes ? (uint32_t)stage_bytes - tot_bytes : 0u) / (8u * n_cons);
+        const uint32_t foundm = __ballot_sync(0xffffffffu, routed), giantm = __ballot_sync(0xffffffffu, routed && giant);
+        const uint32_t room = (tot_bytes <= (uint32_t)stage_bytes ? (uint32_t)stage_bytes - tot_bytes : 0u) / 8u;
         uint32_t lg = room ? 31 - __clz(room) : 0;                         // the largest table that fits ...
         if (tot_chunks) lg = min(lg, 32u - __clz(64u * tot_chunks - 1u));  // ... up to twice the postings
         const bool staged = !nofit && !giantm && (1u << lg) >= 32u * tot_chunks && lg >= 5;
@@ -818,15 +901,15 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
         cons = min(cons, g_nv);
         last = cons - 1;
         const uint32_t lanes = cons >= 32 ? 0xffffffffu : ((1u << cons) - 1u);
-        hitm = __ballot_sync(0xffffffffu, found) & lanes;
+        hitm = __ballot_sync(0xffffffffu, routed) & lanes;
         stagedm = __ballot_sync(0xffffffffu, sb != 0u) & lanes;
-        n_match += __popc(hitm);
+        n_match += __popc((SLICED ? __ballot_sync(0xffffffffu, found) : hitm) & lanes);
         n_skip += __popc(__ballot_sync(0xffffffffu, g_skip) & lanes);
       }
       off = incl_bytes - sb;
       if (!((stagedm >> lane) & 1u)) bytes = 0;  // only staged windows are copied
       if (g0 + cons >= Ql) {
-        flags |= kGrpLast;
+        flags |= (!SLICED || pass == n_pass - 1) ? kGrpLast : kGrpPassEnd;
       } else {
         // ---- next group of the read: shift the 96 known class bytes by `cons`, prefetch 32 more characters,
         // and put its probes in flight before this group's descriptors and copies are written
@@ -845,30 +928,6 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
     const uint32_t n_post_c = n_post, bytes_c = bytes, my_chunks_c = my_chunks, incl_chunks_c = incl_chunks, off_c = off;
     const uint64_t meta_c = meta;
     const uint32_t last_incl = (stagedm && cons > 0) ? __shfl_sync(0xffffffffu, incl, last) : 0u;
-    // C > 1: the chunks of a window go to the lists of the consumers whose slice the window's nodes can touch
-    // (all of them for the alternatives of an ambiguous window: every consumer needs the whole W_size picture
-    // of its own nodes only, but the table pass is cheap and the case rare)
-    uint32_t route = 0;          // this lane's consumers
-    uint64_t rincl = 0, rtot = 0;  // per consumer (13 bits each): inclusive prefix of the routed chunks, totals
-    if (C > 1 && stagedm) {
-      if (bytes_c) {
-        const uint32_t qmin = (uint32_t)(meta_c >> kMetaQminShift) & 15u, qmax = (uint32_t)(meta_c >> kMetaQmaxShift) & 15u;
-#pragma unroll
-        for (int c = 0; c < C; c++) {
-          const uint32_t b = qb >> (8 * c);
-          if ((flags & kGrpAmb) || (qmin <= ((b >> 4) & 15u) && qmax >= (b & 15u))) route |= 1u << c;
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < C; c++)
-        if ((route >> c) & 1u) rincl |= (uint64_t)my_chunks_c << (13 * c);
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint64_t t = __shfl_up_sync(0xffffffffu, rincl, d);
-        if (lane >= d) rincl += t;
-      }
-      rtot = __shfl_sync(0xffffffffu, rincl, last);
-    }
     if (more) front();
     acquire();
     if (hitm & ~stagedm) {  // the consumer's per-window path needs these
@@ -877,48 +936,49 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
     }
     if (stagedm) {
       total = last_incl >> 13 << 5;
-      n_chunks = (int)(last_incl & 0x1FFFu);
+      const uint32_t n_chunks = last_incl & 0x1FFFu;
       const uint32_t stages = w.bar + 64 + kStages * kStageMetaBytes;
       const uint32_t stage0 = stages + slot * stage_bytes;
-      const uint32_t dl0 = stages + kStages * stage_bytes + slot * (C * w.max_chunks * 8);  // C lists per stage
-      if (C == 1) {
-        if (bytes_c) {
-          // chunk descriptors of this window, in window order
-          uint32_t dl = dl0 + 8 * (incl_chunks_c - my_chunks_c);
-          uint32_t a = stage0 + off_c;
-          for (uint32_t left = n_post_c; left; a += kSubBlockBytes, dl += 8) {
-            const uint32_t m = min(left, 32u);
-            sts_u64(dl, make_uint2(a, m));
-            left -= m;
+      const uint32_t dl0 = stages + kStages * stage_bytes + slot * (w.max_chunks * 16);
+      // ---- step descriptors: chunk c of the group (windows in order, a window's chunks in order) goes to slot
+      // c & 1 of step c >> 1, unless the pair (c - 1, c) straddles two windows whose node ranges intersect: then
+      // the pair is SPLIT into two steps with idle B slots, and every later step moves down by one.  A split is
+      // owned by the lane of the odd chunk (the first chunk of its window).
+      const uint32_t c0 = incl_chunks_c - my_chunks_c;
+      const uint32_t q8 = (uint32_t)(meta_c >> kMetaQminShift) & 0xFFu;
+      const uint32_t prevm = stagedm & lt_mask;
+      const uint32_t pq = __shfl_sync(0xffffffffu, q8, prevm ? 31 - __clz(prevm) : 0);
+      const bool disjoint = (q8 >> 4) < (pq & 15u) || (pq >> 4) < (q8 & 15u);
+      const bool split = bytes_c && (c0 & 1u) && !disjoint && !(flags & kGrpAmb);
+      const uint32_t splitm = __ballot_sync(0xffffffffu, split);
+      const uint32_t sbef = __popc(splitm & lt_mask) + (split ? 1u : 0u);
+      n_steps = (int)(((n_chunks + 1) >> 1) + __popc(splitm));
+      const uint2 idle = make_uint2(stage0, 0u);
+      if (bytes_c) {
+        uint32_t a = stage0 + off_c, c = c0;
+        bool first = split;
+        for (uint32_t left = n_post_c; left; a += kSubBlockBytes, c++) {
+          const uint32_t m = min(left, 32u);
+          const uint32_t d = dl0 + 16 * ((c >> 1) + sbef);
+          sts_u64(d + (first ? 0u : 8u * (c & 1u)), make_uint2(a, m));
+          if (first) {  // the B slots of the two halves of the split pair
+            sts_u64(d + 8, idle);
+            sts_u64(d - 8, idle);
+            first = false;
           }
-        }
-        if (lane < 12)  // idle descriptors behind the list: the consumer works in rounds of 4 and looks 8 ahead
-          sts_u64(dl0 + 8 * (n_chunks + lane), make_uint2(stage0, 0u));
-      } else {
-#pragma unroll
-        for (int c = 0; c < C; c++) {
-          const uint32_t dlc = dl0 + c * (w.max_chunks * 8);
-          if ((route >> c) & 1u) {
-            uint32_t dl = dlc + 8 * ((uint32_t)(rincl >> (13 * c)) & 0x1FFFu) - 8 * my_chunks_c;
-            uint32_t a = stage0 + off_c;
-            for (uint32_t left = n_post_c; left; a += kSubBlockBytes, dl += 8) {
-              const uint32_t m = min(left, 32u);
-              sts_u64(dl, make_uint2(a, m));
-              left -= m;
-            }
-          }
-          if (lane < 12) sts_u64(dlc + 8 * (((uint32_t)(rtot >> (13 * c)) & 0x1FFFu) + lane), make_uint2(stage0, 0u));
+          left -= m;
         }
       }
+      if (lane < 6)  // idle steps behind the list: the consumer works in rounds of 2 steps and looks 4 ahead
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%1,%2};" ::"r"(dl0 + 16 * (n_steps + lane)), "r"(stage0), "r"(0u) : "memory");
+      if (lane == 6 && (n_chunks & 1u)) sts_u64(dl0 + 16 * (n_steps - 1) + 8, idle);  // the last chunk has no partner
     }
     if (lane == 0) {
       StageHdr h;
       h.r = r; h.seq = seq_g0; h.Q = Ql; h.QT = QT; h.flags = flags;
       h.n_match = n_match; h.n_amb = n_amb; h.n_skip = n_skip;
-      h.n_chunks = n_chunks; h.hitm = hitm; h.staged_bytes = total; h.stagedm = stagedm;
-      // C > 1: the length of each consumer's list, 16 bits each
-      h.pad[0] = (int)(((uint32_t)rtot & 0x1FFFu) | (((uint32_t)(rtot >> 13) & 0x1FFFu) << 16));
-      h.pad[1] = (int)(((uint32_t)(rtot >> 26) & 0x1FFFu) | (((uint32_t)(rtot >> 39) & 0x1FFFu) << 16));
+      h.n_chunks = n_steps; h.hitm = hitm; h.staged_bytes = total; h.stagedm = stagedm;
+      h.pad[0] = h.pad[1] = 0;
       const uint4* q = reinterpret_cast<const uint4*>(&h);
 #pragma unroll
       for (int i = 0; i < 4; i++)
@@ -934,28 +994,27 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
     // this lane's bulk copy (bytes_c != 0 only for the staged windows of the group)
     if (bytes_c)
       bulk_g2s(w.bar + 64 + kStages * kStageMetaBytes + slot * stage_bytes + off_c, block_ptr(db, meta_c), bytes_c, full);
-    if (flags & kGrpLast) have = start_read();
+    if (flags & kGrpLast) {
+      have = start_read();
+    } else if (SLICED && (flags & kGrpPassEnd)) {
+      pass++;
+      load_chars();
+      front();
+    }
   }
 }
 
-// ---- K3 + K4: the consumer warps ------------------------------------------------------------------
-// C consumers share one read: consumer c owns the nodes [lo, lo+width) of S -- it adds only the postings
-// of its nodes (it walks, in window order, the chunks of the windows routed to its slice, so the per-node
-// order is kept), selects the top-K of its slice, and consumer 0 merges the C lists and writes the rows.  C = 1 for small trees
-// (the pair of DESIGN.md); big trees, whose S[] leaves room for only a few reads per SM, get more warps
-// per read this way.  Candidate hand-over: cand[c][K] in shared memory, guarded by two mbarriers.
-template <int C>
+// ---- K3 + K4: the consumer warp -------------------------------------------------------------------
+// SLICED: S holds one node slice of the tree at a time; at the end of a pass the slice is searched for
+// candidates (merged into the running top-K list), reset, and reused by the next slice.
+template <bool SLICED>
 __device__ __forceinline__ void consumer(const AlphabetTables& c_alpha, const DbView& db, const CfgView& cfg,
-                                         const BatchView& bt, const PairSmem& w, float* Sa, int* Ca, int n_pad, int lane,
-                                         int c, uint32_t cand) {
+                                         const BatchView& bt, const PairSmem& w, float* Sa, int* Ca, int n_pad, int slice,
+                                         int lane) {
   const int K = cfg.K;
   float* S = w.S;
-  // slice of this consumer, in multiples of 128 nodes (the selection works on float4 x 32 lanes)
-  const int per = ((n_pad / 128 + C - 1) / C) * 128;
-  const int lo_i = min(c * per, n_pad), hi_i = min(lo_i + per, n_pad);
-  const uint32_t lo = C > 1 ? (uint32_t)lo_i : 0u, width = C > 1 ? (uint32_t)(hi_i - lo_i) : 0xFFFFFFFFu;
-  const uint32_t cand_full = w.bar + 8 * (2 * kStages), cand_free = w.bar + 8 * (2 * kStages + 1);
-  uint32_t n_done = 0;  // reads finished (phase of the candidate hand-over)
+  TopList t;
+  t.s = -INFINITY; t.x = 0xFFFF; t.cnt = 0;
   for (uint32_t batch = 0;; batch++) {
     const int slot = batch % kStages;
     const uint32_t use = batch / kStages;
@@ -963,24 +1022,28 @@ __device__ __forceinline__ void consumer(const AlphabetTables& c_alpha, const Db
     const StageHdr g = *reinterpret_cast<const StageHdr*>(w.meta + slot * kStageMetaBytes);
     if (g.flags & kGrpStop) return;
     const float QT0 = __fadd_rn(0.0f, g.QT);  // S[x]+=Q*T on a zeroed S[x]
-    // this consumer's chunk list of the stage and its length (C > 1: only the windows routed to its slice)
-    const uint32_t my_list = w.desc + (slot * C + c) * (w.max_chunks * 8);
-    const int my_chunks = C > 1 ? (int)(((uint32_t)((c >> 1) ? g.pad[1] : g.pad[0]) >> (16 * (c & 1))) & 0xFFFFu) : g.n_chunks;
+    // the node slice of this group's pass
+    const int pass = SLICED ? (g.flags >> kGrpPassShift) & 0xF : 0;
+    const int lo_i = SLICED ? pass * slice : 0, n_slice = SLICED ? min(slice, n_pad - lo_i) : n_pad;
+    const uint32_t lo = (uint32_t)lo_i, width = SLICED ? (uint32_t)n_slice : 0xFFFFFFFFu;
+    float* Sv = S - lo_i;  // Sv[x] = the slot of node x, for the x of this slice
+    const uint32_t my_list = w.desc + slot * (w.max_chunks * 16);
+    const int n_steps = g.n_chunks;
     const bool bad = g.flags & kGrpBad;
     if (!bad && !((g.flags & (kGrpAmb | kGrpAmbGlobal)) | (g.hitm & ~g.stagedm))) {
       // common case: every matched window of the group is staged
-      if (my_chunks) accumulate_chunks<(C > 1)>(S, my_list, my_chunks, QT0, db.T, lane, lo, width);
+      if (n_steps) accumulate_chunks<SLICED>(S, my_list, n_steps, QT0, db.T, lane, lo, width);
     } else if (!bad) {
       if (g.flags & kGrpAmb) {
-        // one ambiguous window, its alternatives staged; the table of consumer c follows the blocks
+        // one ambiguous window, its alternatives staged (the list holds their chunks in alternative order: slot A
+        // then slot B of every step); the S_amb / C_amb table follows the blocks
         const int tab_log2 = (g.flags >> kGrpTabShift) & 0xF;
-        if (my_chunks)
-          ambiguous_staged(db, cfg, S, my_list, my_chunks,
-                           w.stage + slot * w.stage_bytes + g.staged_bytes + ((uint32_t)c << (tab_log2 + 3)), tab_log2,
+        if (n_steps)
+          ambiguous_staged(db, cfg, Sv, my_list, 2 * n_steps, w.stage + slot * w.stage_bytes + g.staged_bytes, tab_log2,
                            (g.flags >> kGrpWsizeShift) & 0x1F, g.QT, lane, lo, width);
       } else if (g.flags & kGrpAmbGlobal) {
         // one ambiguous window whose alternatives did not fit a stage
-        ambiguous_window(c_alpha, db, cfg, S, g.seq, g.QT, Sa, Ca, lane, lo, width);
+        ambiguous_window(c_alpha, db, cfg, Sv, g.seq, g.QT, Sa, Ca, lane, lo, width);
       } else {
         // a posting block larger than a stage: windows one by one, in order (a node's S[x] must see its
         // contributions in window order)
@@ -992,48 +1055,24 @@ __device__ __forceinline__ void consumer(const AlphabetTables& c_alpha, const Db
           todo &= todo - 1;
           const uint32_t pk = pk_arr[l];
           if ((g.stagedm >> l) & 1u) {
-            accumulate_staged(S, stage + (pk >> 16), (int)(pk & 0xFFFF), QT0, db.T, lane, lo, width);
+            accumulate_staged(Sv, stage + (pk >> 16), (int)(pk & 0xFFFF), QT0, db.T, lane, lo, width);
           } else {
-            accumulate_global(S, block_ptr(db, meta_arr[l]), (int)(pk & 0xFFFF), QT0, db.T, lane, lo, width);
+            accumulate_global(Sv, block_ptr(db, meta_arr[l]), (int)(pk & 0xFFFF), QT0, db.T, lane, lo, width);
           }
         }
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(w.bar + 8 * (kStages + slot));  // the stage may be refilled (all C consumers arrive)
-    if (!(g.flags & kGrpLast)) continue;
-    // ---- selection / outputs
+    if (lane == 0) mbar_arrive(w.bar + 8 * (kStages + slot));  // the stage may be refilled
+    if (!(g.flags & (kGrpLast | kGrpPassEnd))) continue;
+    // ---- selection over the slice (merged into the running list) / outputs after the last pass
     const long long r = g.r;
     const bool no_select = (g.flags & kGrpTooLong) || (g.Q < 0 && !bad);  // nothing was accumulated
-    TopList t;
-    t.s = -INFINITY; t.x = 0xFFFF; t.cnt = 0;
     if (!no_select) {  // a bad read only resets S
       float* dump_row = (bt.dump_scores && !bad) ? bt.dump_scores + r * (size_t)db.n_nodes : nullptr;
-      t = select_scan(cfg, S, C > 1 ? lo_i : 0, C > 1 ? hi_i : n_pad, !bad, dump_row, db.n_nodes, lane);
+      select_scan(cfg, S, n_slice, lo_i, !bad, dump_row, db.n_nodes, lane, t);
     }
-    if (C > 1) {
-      if (c > 0) {
-        // hand the slice's list to consumer 0 (once it has finished with the previous read's lists)
-        if (n_done) mbar_wait(cand_free, (n_done - 1) & 1u);
-        if (lane < K) sts_u64(cand + 8 * (c * 32 + lane), make_uint2(__float_as_uint(t.s), (uint32_t)t.x));
-        if (lane == 0) sts_u32(cand + 8 * 32 * C + 4 * c, (uint32_t)t.cnt);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(cand_full);
-        n_done++;
-        continue;
-      }
-      mbar_wait(cand_full, n_done & 1u);
-      for (int cc = 1; cc < C; cc++) {
-        const uint32_t cnt_c = lds_u32(cand + 8 * 32 * C + 4 * cc);
-        for (uint32_t i = 0; i < cnt_c; i++) {
-          const uint2 e = lds_u64(cand + 8 * (cc * 32 + i));
-          top_insert(t, __uint_as_float(e.x), (int)e.y, K, lane);
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(cand_free);
-      n_done++;
-    }
+    if (!(g.flags & kGrpLast)) continue;
     uint16_t* o_node = bt.node + r * K;
     float* o_score = bt.score + r * K;
     double* o_lwr = bt.lwr + r * K;
@@ -1046,6 +1085,7 @@ __device__ __forceinline__ void consumer(const AlphabetTables& c_alpha, const Db
       rows = bad ? 0 : finalize_rows(cfg, t, o_node, o_score, o_lwr, lane);
       status = bad ? RP_STATUS_BAD_CHAR : rows < 0 ? RP_STATUS_UNPLACED : RP_STATUS_PLACED;  // L empty -> not placed (:797-806)
     }
+    t.s = -INFINITY; t.x = 0xFFFF; t.cnt = 0;
     if (rows <= 0 && status != RP_STATUS_PLACED) {
       rows = 0;
       if (lane < K) { o_node[lane] = 0xFFFF; o_score[lane] = -INFINITY; o_lwr[lane] = 0.0; }
@@ -1063,27 +1103,27 @@ __device__ __forceinline__ void consumer(const AlphabetTables& c_alpha, const Db
 }
 
 // --------------------------------------------------------------------------------- main kernel
-// Warps 0..teams-1 are the producers, then C consumers per team; blockDim = teams * (1 + C) * 32.
+// Warps 0..pairs-1 are the producers, warps pairs..2*pairs-1 the consumers; blockDim = pairs * 64.
 constexpr int kMaxThreads = kMaxPairsPerCta * 64;
-// teams of several consumers only run where S[] leaves room for a few reads per SM: fewer threads, more registers
-constexpr int max_threads_for(int C) { return C == 1 ? kMaxThreads : 640; }
-template <int C>
-__global__ void __launch_bounds__(max_threads_for(C), 1)
+// a sliced tree runs at most kWantPairs pairs per SM (that is what the number of passes is chosen for), so its
+// kernel may use the 128 registers a 512-thread CTA gets: the slice arithmetic spilt at 80
+constexpr int kWantPairs = 8;
+constexpr int max_threads_for(bool sliced) { return sliced ? kWantPairs * 64 : kMaxThreads; }
+template <bool SLICED, bool DIRECT>
+__global__ void __launch_bounds__(max_threads_for(SLICED), 1)
 place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_constant__ DbView db,
              const __grid_constant__ CfgView cfg, const __grid_constant__ BatchView bt,
              unsigned long long* work_counter, float* amb_S, int* amb_C, int n_pad, int per_pair_bytes,
-             int stage_bytes, int max_chunks) {
+             int stage_bytes, int max_chunks, int slice, int n_pass) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  const int teams = (blockDim.x >> 5) / (1 + C);
-  const bool is_producer = warp < teams;
-  const int pair = is_producer ? warp : (warp - teams) / C;
-  const int cidx = is_producer ? 0 : (warp - teams) % C;
+  const int pairs = blockDim.x >> 6;
+  const bool is_producer = warp < pairs;
+  const int pair = is_producer ? warp : warp - pairs;
   // CTA-wide: character class table
   for (int i = threadIdx.x; i < 256; i += blockDim.x) smem[i] = c_alpha.cls[i];
   PairSmem w;
-  uint32_t cand;
   {
     uint8_t* base = smem + 256 + (size_t)pair * per_pair_bytes;
     w.bar = smem_u32(base);
@@ -1092,22 +1132,18 @@ place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_consta
     w.stage = smem_u32(p);  // idle lanes of a short chunk read (and ignore) up to 160 B past it: keep the stages inside
     p += (size_t)kStages * stage_bytes;
     w.desc = smem_u32(p);
-    p += (size_t)kStages * C * max_chunks * 8;
+    p += (size_t)kStages * max_chunks * 16;
     w.S = reinterpret_cast<float*>(p);
-    p += 4 * (size_t)(n_pad + 32);
-    cand = smem_u32(p);  // C > 1: cand[C][32] x 8 B
     w.stage_bytes = stage_bytes;
     w.max_chunks = max_chunks;
   }
-  if (!is_producer && cidx == 0) {
-    for (int i = lane; i < n_pad + 32; i += 32) w.S[i] = __uint_as_float(kSentinelBits);
+  if (!is_producer) {
+    for (int i = lane; i < slice + 32; i += 32) w.S[i] = __uint_as_float(kSentinelBits);
     if (lane == 0) {
       for (int i = 0; i < kStages; i++) {
-        mbar_init(w.bar + 8 * i, 1);                // full: the producer's arrival (+ the staged bytes)
-        mbar_init(w.bar + 8 * (kStages + i), C);    // empty: every consumer of the team
+        mbar_init(w.bar + 8 * i, 1);              // full: the producer's arrival (+ the staged bytes)
+        mbar_init(w.bar + 8 * (kStages + i), 1);  // empty: the consumer
       }
-      mbar_init(w.bar + 8 * (2 * kStages), C > 1 ? C - 1 : 1);  // cand_full
-      mbar_init(w.bar + 8 * (2 * kStages + 1), 1);              // cand_free
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1117,10 +1153,10 @@ place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_consta
   // local memory around them, and with ~227 KB of shared memory carved out there is no L1 left, so every
   // such spill was an L2 round trip: 20 % of the kernel time, profiles/r01_v5_spill_stalls.txt.)
   if (is_producer) {
-    producer<C>(c_alpha, db, cfg, bt, work_counter, w, smem_u32(smem), lane, n_pad);
+    producer<SLICED, DIRECT>(c_alpha, db, cfg, bt, work_counter, w, smem_u32(smem), lane, n_pad, slice, n_pass);
   } else {
-    const size_t gp = (size_t)blockIdx.x * teams + pair;
-    consumer<C>(c_alpha, db, cfg, bt, w, amb_S + gp * n_pad, amb_C + gp * n_pad, n_pad, lane, cidx, cand);
+    const size_t gp = (size_t)blockIdx.x * pairs + pair;
+    consumer<SLICED>(c_alpha, db, cfg, bt, w, amb_S + gp * n_pad, amb_C + gp * n_pad, n_pad, slice, lane);
   }
 }
 
@@ -1196,22 +1232,19 @@ __global__ void fill_f32_kernel(float* p, size_t n, float v) {
 }
 
 // ------------------------------------------------------------------------------ host plumbing
-// Shared memory per team (one producer + C consumers sharing one read) = S[n_pad + 32] + kStages posting
-// stages (+ descriptor lists, stage headers, mbarriers, candidate lists); teams per CTA x CTAs per SM
-// maximise the resident teams under the 227 KB budget and 768 threads.  A stage holds about a group's
-// worth of posting blocks; RP_STAGE_BYTES / RP_CONSUMERS override for tuning.
-template <int C>
-static int geometry_for(const rp_db* db, DeviceCtx* dc, LaunchGeom& g) {
-  auto kern = place_kernel<C>;
-  RP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
-  // what the hardware really keeps resident (registers may bind before shared memory does)
-  int resident = 0;
-  RP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, g.warps_per_cta * 32, g.smem_bytes));
-  if (resident < 1) return set_error(RP_E_CUDA, "placement kernel does not fit on an SM (smem %zu B)", g.smem_bytes);
-  g.ctas_per_sm = resident;
-  g.grid = dc->sm_count * g.ctas_per_sm;
-  (void)db;
-  return RP_OK;
+// Shared memory per pair (one producer + one consumer sharing one read) = S[slice + 32] + kStages posting
+// stages (+ step descriptor lists, stage headers, mbarriers); pairs per CTA x CTAs per SM maximise the
+// resident pairs under the 227 KB budget, 768 threads and the register file.  A stage holds about a group's
+// worth of posting blocks.  Trees whose S[] would leave fewer than kWantPairs reads per SM are walked in
+// node-range passes (S = one slice).  RP_STAGE_BYTES / RP_PASSES / RP_PAIRS_PER_SM override for tuning.
+typedef void (*place_kernel_t)(const AlphabetTables, const DbView, const CfgView, const BatchView, unsigned long long*,
+                               float*, int*, int, int, int, int, int, int);
+static place_kernel_t kernel_for(bool sliced, bool direct) {
+  return sliced ? (direct ? place_kernel<true, true> : place_kernel<true, false>)
+                : (direct ? place_kernel<false, true> : place_kernel<false, false>);
+}
+static bool db_is_direct(const rp_db* db, const DeviceCtx* dc) {
+  return !db->partitioned && !dc->parts.empty() && db->parts[dc->parts[0]].d_direct != nullptr;
 }
 
 int compute_geometry(const rp_db* db, DeviceCtx* dc) {
@@ -1221,74 +1254,80 @@ int compute_geometry(const rp_db* db, DeviceCtx* dc) {
   const size_t optin = dc->smem_optin;         // 227 KB on sm_100
   const size_t sm_total = optin + 1024;        // 228 KB per SM, 1 KB reserved per resident CTA
   const double mean_block = db->desc.n_keys ? (double)db->block_bytes / (double)db->desc.n_keys : 32.0;
-  long stage = (long)(32.0 * mean_block * 0.81);  // tools/sweep_stage.sh: flat optimum 0.8-0.9
-  if (const char* e = getenv("RP_STAGE_BYTES")) stage = atol(e);
-  stage = std::max(1024L, std::min(stage, 32768L - 128));
-  stage = (stage + 127) & ~127L;
-  auto team_bytes = [&](long st, int C) {
-    const size_t chunks = (32 + st / kSubBlockBytes + 13 + 1) & ~(size_t)1;  // per window + per extra sub-block + 12 idle
-    return (64 + kStages * (size_t)kStageMetaBytes + kStages * 8 * chunks * C + 4 * (size_t)(g.n_pad + 32) +
-            kStages * (size_t)st + (C > 1 ? (size_t)C * 264 : 0) + 127) & ~(size_t)127;
+  auto chunks_for = [&](long st) { return (size_t)((32 + st / kSubBlockBytes + 13 + 1) & ~1); };  // per window + per extra sub-block + idle
+  auto pair_bytes = [&](long st, int slice) {
+    return (64 + kStages * (size_t)kStageMetaBytes + kStages * 16 * chunks_for(st) + 4 * (size_t)(slice + 32) +
+            kStages * (size_t)st + 127) & ~(size_t)127;
   };
-  // big trees: give the stages up before giving the accumulator up
-  while (stage > 1024 && cta_fixed + 2 * team_bytes(stage, 1) > optin) stage = std::max(1024L, (stage / 2 + 127) & ~127L);
-  // a slightly smaller stage that lets one more team fit is the better trade (cfg2: 4992 B -> 11 pairs)
+  auto slice_for = [&](int np) { return std::min(g.n_pad, ((g.n_pad + np - 1) / np + 127) & ~127); };
+  // a pass stages the windows whose list can touch its slice: 1/n_pass of them plus the lists that straddle a border
+  auto stage_for = [&](int np) {
+    const double share = np == 1 ? 1.0 : std::min(1.0, 1.0 / np + 0.15);
+    long st = (long)(32.0 * mean_block * 0.81 * share);  // tools/sweep_stage.sh: flat optimum 0.8-0.9 of a group's blocks
+    st = std::max(1024L, std::min(st, 32768L - 128));
+    return (st + 127) & ~127L;
+  };
+  int n_pass = 1;
+  for (; n_pass < kMaxPasses; n_pass++)
+    if ((optin - cta_fixed) / pair_bytes(stage_for(n_pass), slice_for(n_pass)) >= (size_t)kWantPairs) break;
+  if (const char* e = getenv("RP_PASSES")) n_pass = std::max(1, std::min(kMaxPasses, atoi(e)));
+  while (n_pass > 1 && slice_for(n_pass) == slice_for(n_pass - 1)) n_pass--;  // no empty slices
+  g.n_pass = n_pass;
+  g.slice = slice_for(n_pass);
+  long stage = stage_for(n_pass);
+  if (const char* e = getenv("RP_STAGE_BYTES")) stage = (std::max(1024L, std::min(atol(e), 32768L - 128)) + 127) & ~127L;
+  // a slightly smaller stage that lets one more pair fit is the better trade (cfg2: 4992 B -> 11 pairs)
   if (!getenv("RP_STAGE_BYTES")) {
-    const size_t t0 = (optin - cta_fixed) / team_bytes(stage, 1);
+    const size_t t0 = (optin - cta_fixed) / pair_bytes(stage, g.slice);
     for (long st = stage - 128; st >= stage - stage / 16 && st >= 1024; st -= 128)
-      if ((optin - cta_fixed) / team_bytes(st, 1) > t0) { stage = st; break; }
+      if ((optin - cta_fixed) / pair_bytes(st, g.slice) > t0) { stage = st; break; }
   }
-  // consumers per team: 1.  2 or 4 warps sharing a read's S[] (RP_CONSUMERS) are correct but not faster,
-  // even on big trees and even though every window is routed to the consumers whose node slice its list
-  // can touch (cfg3, N = 9 999, 4 teams per SM: 30.5 / 31.6 / 43.7 ms for C = 1 / 2 / 4,
-  // tools/sweep_teams_stage.sh): what bounds a big tree is the producer, which pays one table round trip
-  // per group.  Kept as a tested knob.
-  int C = 1;
-  if (const char* e = getenv("RP_CONSUMERS")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) C = v; }
-  g.consumers = C;
   g.stage_bytes = (int)stage;
-  g.max_chunks = (32 + g.stage_bytes / kSubBlockBytes + 13 + 1) & ~1;  // even: S stays 16 B aligned behind the lists
-  g.per_warp_bytes = team_bytes(stage, C);
+  g.max_chunks = (int)chunks_for(stage);
+  g.per_warp_bytes = pair_bytes(stage, g.slice);
   if (cta_fixed + g.per_warp_bytes > optin)
-    return set_error(RP_E_UNSUPPORTED,
-                     "n_nodes=%d needs %zu B of shared memory per read (> %zu B per CTA); trees beyond ~54k nodes "
-                     "are not supported by the shared-memory accumulator",
-                     db->desc.n_nodes, g.per_warp_bytes, optin);
-  const int max_teams_cta = max_threads_for(C) / (32 * (1 + C));
-  int max_teams_sm = 16;
-  if (const char* e = getenv("RP_PAIRS_PER_SM")) max_teams_sm = std::max(1, std::min(16, atoi(e)));
+    return set_error(RP_E_UNSUPPORTED, "n_nodes=%d: one pair needs %zu B of shared memory (> %zu B per CTA) even with %d passes",
+                     db->desc.n_nodes, g.per_warp_bytes, optin, n_pass);
+  const int max_pairs_cta = max_threads_for(n_pass > 1) / 64;
+  int max_pairs_sm = 16;
+  if (const char* e = getenv("RP_PAIRS_PER_SM")) max_pairs_sm = std::max(1, std::min(16, atoi(e)));
   // registers bind before shared memory does on small trees (768 threads x 80 registers fill the file):
   // a split into several CTAs only counts for what the register file keeps resident
   RP_CUDA_TRY(cudaSetDevice(dc->device));
+  place_kernel_t kern = kernel_for(n_pass > 1, db_is_direct(db, dc));
   cudaFuncAttributes fa;
-  RP_CUDA_TRY(C == 1 ? cudaFuncGetAttributes(&fa, place_kernel<1>)
-                     : C == 2 ? cudaFuncGetAttributes(&fa, place_kernel<2>) : cudaFuncGetAttributes(&fa, place_kernel<4>));
+  RP_CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
   const int regs_sm = 65536;
-  int best_total = 0, teams_cta = 1;
+  int best_total = 0, pairs_cta = 1;
   for (int c = 1; c <= 8; c++) {
     const size_t budget = std::min(optin, sm_total / c - 1024);
     if (budget < cta_fixed + g.per_warp_bytes) break;
-    int tpc = (int)std::min<size_t>(max_teams_cta, (budget - cta_fixed) / g.per_warp_bytes);
-    if (c * tpc > max_teams_sm) tpc = max_teams_sm / c;
-    if (c * tpc * (1 + C) * 32 > 2048 / 1) tpc = 2048 / (32 * (1 + C) * c);
-    while (tpc >= 1 && (long)c * (((long)tpc * (1 + C) * 32 * fa.numRegs + 511) & ~511L) > regs_sm) tpc--;
+    int tpc = (int)std::min<size_t>(max_pairs_cta, (budget - cta_fixed) / g.per_warp_bytes);
+    if (c * tpc > max_pairs_sm) tpc = max_pairs_sm / c;
+    if (c * tpc * 64 > 2048) tpc = 2048 / (64 * c);
+    while (tpc >= 1 && (long)c * (((long)tpc * 64 * fa.numRegs + 511) & ~511L) > regs_sm) tpc--;
     if (tpc < 1) break;
     if (c * tpc > best_total) {
       best_total = c * tpc;
       g.ctas_per_sm = c;
-      teams_cta = tpc;
+      pairs_cta = tpc;
     }
   }
-  g.warps_per_cta = teams_cta * (1 + C);
-  g.smem_bytes = cta_fixed + teams_cta * g.per_warp_bytes;
-  RP_CUDA_TRY(cudaSetDevice(dc->device));
-  int rc = C == 1 ? geometry_for<1>(db, dc, g) : C == 2 ? geometry_for<2>(db, dc, g) : geometry_for<4>(db, dc, g);
-  if (rc) return rc;
+  g.warps_per_cta = pairs_cta * 2;
+  g.smem_bytes = cta_fixed + pairs_cta * g.per_warp_bytes;
+  RP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+  // what the hardware really keeps resident (registers may bind before shared memory does)
+  int resident = 0;
+  RP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, g.warps_per_cta * 32, g.smem_bytes));
+  if (resident < 1) return set_error(RP_E_CUDA, "placement kernel does not fit on an SM (smem %zu B)", g.smem_bytes);
+  g.ctas_per_sm = resident;
+  g.grid = dc->sm_count * g.ctas_per_sm;
+  if (const char* e = getenv("RP_GRID_SMS")) g.grid = std::max(1, std::min(dc->sm_count, atoi(e))) * g.ctas_per_sm;
   dc->geom = g;
   if (getenv("RP_DEBUG_GEOM"))
-    fprintf(stderr, "rappas_b200 geometry: n_pad=%d consumers=%d teams/CTA=%d CTAs/SM=%d stage=%d B team=%zu B smem/CTA=%zu B\n",
-            g.n_pad, g.consumers, g.warps_per_cta / (1 + g.consumers), g.ctas_per_sm, g.stage_bytes, g.per_warp_bytes,
-            g.smem_bytes);
+    fprintf(stderr, "rappas_b200 geometry: n_pad=%d passes=%d slice=%d pairs/CTA=%d CTAs/SM=%d stage=%d B pair=%zu B smem/CTA=%zu B regs=%d direct=%d\n",
+            g.n_pad, g.n_pass, g.slice, g.warps_per_cta / 2, g.ctas_per_sm, g.stage_bytes, g.per_warp_bytes, g.smem_bytes,
+            fa.numRegs, (int)db_is_direct(db, dc));
   return RP_OK;
 }
 
@@ -1299,7 +1338,7 @@ int ensure_stream_ctx(const rp_db* db, DeviceCtx* dc, StreamCtx* sc) {
   if (!sc->stream) RP_CUDA_TRY(cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking));
   RP_CUDA_TRY(cudaEventCreate(&sc->ev_k0));
   RP_CUDA_TRY(cudaEventCreate(&sc->ev_k1));
-  const size_t n = (size_t)dc->geom.grid * (dc->geom.warps_per_cta / (1 + dc->geom.consumers)) * dc->geom.n_pad;
+  const size_t n = (size_t)dc->sm_count * dc->geom.ctas_per_sm * (dc->geom.warps_per_cta / 2) * dc->geom.n_pad;
   RP_CUDA_TRY(cudaMalloc((void**)&sc->d_amb_S, n * sizeof(float)));
   RP_CUDA_TRY(cudaMalloc((void**)&sc->d_amb_C, n * sizeof(int)));
   RP_CUDA_TRY(cudaMemset(sc->d_amb_S, 0, n * sizeof(float)));
@@ -1328,10 +1367,10 @@ static int launch_place(const rp_db* db, DeviceCtx* dc, StreamCtx* sc, const rp_
   const LaunchGeom& g = dc->geom;
   RP_CUDA_TRY(cudaMemsetAsync(sc->d_counter, 0, sizeof(unsigned long long), stream));
   if (time_it) RP_CUDA_TRY(cudaEventRecord(sc->ev_k0, stream));
-  auto kern = g.consumers == 1 ? place_kernel<1> : g.consumers == 2 ? place_kernel<2> : place_kernel<4>;
+  place_kernel_t kern = kernel_for(g.n_pass > 1, db_is_direct(db, dc));
   kern<<<g.grid, g.warps_per_cta * 32, g.smem_bytes, stream>>>(
       db->alpha, make_db_view(db, dc), make_cfg_view(cfg), bt, sc->d_counter, sc->d_amb_S, sc->d_amb_C, g.n_pad,
-      (int)g.per_warp_bytes, g.stage_bytes, g.max_chunks);
+      (int)g.per_warp_bytes, g.stage_bytes, g.max_chunks, g.slice, g.n_pass);
   RP_CUDA_TRY(cudaGetLastError());
   g_kernel_launches.fetch_add(1);
   if (time_it) RP_CUDA_TRY(cudaEventRecord(sc->ev_k1, stream));
@@ -1369,6 +1408,16 @@ static int ensure_io(StreamCtx* sc, size_t seq_bytes, size_t n_reads, int K, boo
 }
 
 // Places reads [r0, r1) of the host batch on one device, in double-buffered chunks.
+// Inside the loop a CUDA error must not return at once: the other stream may still be copying into the
+// caller's out_* buffers, so errors break out and both streams are drained (and d_dump freed) first.
+#define RP_CUDA_BRK(expr)                                                                                   \
+  {                                                                                                         \
+    cudaError_t _e = (expr);                                                                                \
+    if (_e != cudaSuccess) {                                                                                \
+      rc = rp::set_error(RP_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      break;                                                                                                \
+    }                                                                                                       \
+  }
 static int place_on_device(rp_db* db, DeviceCtx* dc, const rp_place_cfg* cfg, const uint8_t* seq,
                            const uint64_t* seq_off, int64_t r0, int64_t r1, int32_t* out_n_rows, uint16_t* out_node,
                            float* out_score, double* out_lwr, int32_t* out_counts, int32_t* out_status,
@@ -1402,29 +1451,29 @@ static int place_on_device(rp_db* db, DeviceCtx* dc, const rp_place_cfg* cfg, co
     const uint64_t b0 = seq_off[c0], nbytes = seq_off[c1] - b0;
     if ((rc = ensure_io(sc, nbytes, (size_t)n, K, out_counts != nullptr))) break;
     cudaStream_t st = sc->stream;
-    if (nbytes) RP_CUDA_TRY(cudaMemcpyAsync(sc->d_seq, seq + b0, nbytes, cudaMemcpyHostToDevice, st));
-    RP_CUDA_TRY(cudaMemcpyAsync(sc->d_off, seq_off + c0, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    if (nbytes) RP_CUDA_BRK(cudaMemcpyAsync(sc->d_seq, seq + b0, nbytes, cudaMemcpyHostToDevice, st));
+    RP_CUDA_BRK(cudaMemcpyAsync(sc->d_off, seq_off + c0, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     BatchView bt;
     bt.seq = sc->d_seq; bt.seq_off = sc->d_off; bt.seq_base = b0; bt.n_reads = n;
     bt.n_rows = sc->d_n_rows; bt.node = sc->d_node; bt.score = sc->d_score; bt.lwr = sc->d_lwr;
     bt.counts = out_counts ? sc->d_counts : nullptr; bt.status = sc->d_status; bt.dump_scores = nullptr;
     if (out_dump) {
       const size_t nd = (size_t)n * db->desc.n_nodes;
-      if (!d_dump[b]) RP_CUDA_TRY(cudaMalloc((void**)&d_dump[b], (size_t)kChunk * db->desc.n_nodes * sizeof(float)));
+      if (!d_dump[b]) RP_CUDA_BRK(cudaMalloc((void**)&d_dump[b], (size_t)kChunk * db->desc.n_nodes * sizeof(float)));
       fill_f32_kernel<<<256, 256, 0, st>>>(d_dump[b], nd, nanf(""));
       g_kernel_launches.fetch_add(1);
       bt.dump_scores = d_dump[b];
     }
     if ((rc = launch_place(db, dc, sc, cfg, bt, st, true))) break;
-    RP_CUDA_TRY(cudaMemcpyAsync(out_n_rows + c0, sc->d_n_rows, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    RP_CUDA_TRY(cudaMemcpyAsync(out_status + c0, sc->d_status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    RP_CUDA_TRY(cudaMemcpyAsync(out_node + c0 * K, sc->d_node, n * K * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
-    RP_CUDA_TRY(cudaMemcpyAsync(out_score + c0 * K, sc->d_score, n * K * sizeof(float), cudaMemcpyDeviceToHost, st));
-    RP_CUDA_TRY(cudaMemcpyAsync(out_lwr + c0 * K, sc->d_lwr, n * K * sizeof(double), cudaMemcpyDeviceToHost, st));
+    RP_CUDA_BRK(cudaMemcpyAsync(out_n_rows + c0, sc->d_n_rows, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    RP_CUDA_BRK(cudaMemcpyAsync(out_status + c0, sc->d_status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    RP_CUDA_BRK(cudaMemcpyAsync(out_node + c0 * K, sc->d_node, n * K * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+    RP_CUDA_BRK(cudaMemcpyAsync(out_score + c0 * K, sc->d_score, n * K * sizeof(float), cudaMemcpyDeviceToHost, st));
+    RP_CUDA_BRK(cudaMemcpyAsync(out_lwr + c0 * K, sc->d_lwr, n * K * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (out_counts)
-      RP_CUDA_TRY(cudaMemcpyAsync(out_counts + c0 * 4, sc->d_counts, n * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      RP_CUDA_BRK(cudaMemcpyAsync(out_counts + c0 * 4, sc->d_counts, n * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (out_dump)
-      RP_CUDA_TRY(cudaMemcpyAsync(out_dump + (size_t)c0 * db->desc.n_nodes, d_dump[b],
+      RP_CUDA_BRK(cudaMemcpyAsync(out_dump + (size_t)c0 * db->desc.n_nodes, d_dump[b],
                                   (size_t)n * db->desc.n_nodes * sizeof(float), cudaMemcpyDeviceToHost, st));
     pending_lo[b] = c0;
   }
@@ -1491,7 +1540,10 @@ int rp_node_scores(rp_db* db, const rp_place_cfg* cfg, const uint8_t* seq, const
                    float* out_scores, int32_t* out_hitcount) {
   if (out_hitcount) return set_error(RP_E_UNSUPPORTED, "the CUDA path keeps no C[] vector; pass out_hitcount=NULL");
   if (!out_scores) return set_error(RP_E_INVALID, "out_scores is NULL");
-  if (!cfg) return set_error(RP_E_INVALID, "cfg is NULL");
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  if (n_reads < 0) return set_error(RP_E_INVALID, "n_reads < 0");
+  if (n_reads == 0) return RP_OK;
   const int K = cfg->keep_at_most;
   std::vector<int32_t> n_rows(n_reads), status(n_reads);
   std::vector<uint16_t> node((size_t)n_reads * K);
@@ -1514,13 +1566,31 @@ int rp_place_batch_device(rp_db* db, int32_t device_index, const rp_place_cfg* c
   DeviceCtx* dc = db->dev[device_index];
   std::lock_guard<std::mutex> lock(dc->mu);
   RP_CUDA_TRY(cudaSetDevice(dc->device));
-  StreamCtx* sc = &dc->sc_dev;
+  // the scheduler counter and the ambiguity scratch of THIS caller stream (see DeviceCtx::DevSlot)
+  cudaStream_t us = (cudaStream_t)stream;
+  DeviceCtx::DevSlot* slot = nullptr;
+  for (auto* ds : dc->dev_slots) if (ds->user == us) { slot = ds; break; }
+  if (!slot) {
+    if ((int)dc->dev_slots.size() < DeviceCtx::kMaxDevSlots) {
+      slot = new DeviceCtx::DevSlot();
+      slot->user = us;
+      dc->dev_slots.push_back(slot);
+    } else {
+      slot = dc->dev_slots[dc->dev_slot_rr++ % DeviceCtx::kMaxDevSlots];
+      slot->shared = true;
+    }
+  }
+  if (!slot->last) RP_CUDA_TRY(cudaEventCreateWithFlags(&slot->last, cudaEventDisableTiming));
+  StreamCtx* sc = &slot->sc;
   if ((rc = ensure_stream_ctx(db, dc, sc))) return rc;
+  if (slot->shared) RP_CUDA_TRY(cudaStreamWaitEvent(us, slot->last, 0));  // another stream may still be using the slot
   BatchView bt;
   bt.seq = d_seq; bt.seq_off = d_seq_off; bt.seq_base = 0; bt.n_reads = n_reads;
   bt.n_rows = d_out_n_rows; bt.node = d_out_node; bt.score = d_out_score; bt.lwr = d_out_lwr;
   bt.counts = d_out_counts; bt.status = d_out_status; bt.dump_scores = nullptr;
-  return launch_place(db, dc, sc, cfg, bt, (cudaStream_t)stream, false);
+  rc = launch_place(db, dc, sc, cfg, bt, us, false);
+  if (rc == RP_OK) RP_CUDA_TRY(cudaEventRecord(slot->last, us));
+  return rc;
 }
 
 int rp_extract_kmers(rp_db* db, const uint8_t* seq, const uint64_t* seq_off, int64_t n_reads, const uint64_t* win_off,

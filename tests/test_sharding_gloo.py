@@ -61,7 +61,7 @@ def test_two_rank_sharded_placement_equals_single_process(tmp_path):
 
 
 def _owner_restatement(alphabet, k, keys, n_parts):
-    """numpy restatement of rp_common.h planar_from_code -> mix_key -> owner_of (uint32 arithmetic)."""
+    """numpy restatement of rp_common.h planar_from_code -> hash_key -> owner_of (uint32 arithmetic)."""
     bits = 2 if alphabet == 0 else 5
     keys = keys.astype(np.uint64)
     planar = np.zeros_like(keys)
@@ -70,11 +70,19 @@ def _owner_restatement(alphabet, k, keys, n_parts):
         for p in range(bits):
             planar |= ((st >> np.uint64(p)) & np.uint64(1)) << np.uint64(p * k + i)
     M = np.uint64(0xFFFFFFFF)
-    x = (planar & M) ^ (((planar >> np.uint64(32)) * np.uint64(0x9E3779B1)) & M)
-    x ^= x >> np.uint64(16); x = (x * np.uint64(0x7FEB352D)) & M
-    x ^= x >> np.uint64(15); x = (x * np.uint64(0x846CA68B)) & M
-    x ^= x >> np.uint64(16)
-    return (((((x * np.uint64(0x85EBCA6B)) & M) >> np.uint64(16)) * np.uint64(n_parts)) >> np.uint64(16)).astype(np.int32)
+    u = np.uint64
+    lo, hi = planar & M, planar >> u(32)
+    a = lo ^ ((hi * u(0x9E3779B1)) & M)                                   # hash_key().a : lowbias32
+    a ^= a >> u(16); a = (a * u(0x7FEB352D)) & M
+    a ^= a >> u(15); a = (a * u(0x846CA68B)) & M
+    a ^= a >> u(16)
+    b = ((hi ^ ((lo * u(0x85EBCA6B)) & M)) + u(0x7F4A7C15)) & M           # hash_key().b : triple32
+    b ^= b >> u(17); b = (b * u(0xED5AD4BB)) & M
+    b ^= b >> u(11); b = (b * u(0xAC4C1B51)) & M
+    b ^= b >> u(15); b = (b * u(0x31848BAB)) & M
+    b ^= b >> u(14)
+    m = ((a ^ (((b << u(16)) | (b >> u(16))) & M)) * u(0x85EBCA6B)) & M   # owner_of
+    return (((m >> u(16)) * u(n_parts)) >> u(16)).astype(np.int32)
 
 
 @pytest.mark.parametrize("alphabet,k", [(0, 10), (0, 15), (0, 20), (1, 6)])
