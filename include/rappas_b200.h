@@ -51,7 +51,7 @@ extern "C" {
 #define RP_STATUS_UNPLACED  1 /* no k-mer hit: PlacementProcess.java:797-806            */
 #define RP_STATUS_TOO_SHORT 2 /* len < k-1; the reference throws NegativeArraySizeException (AmbigSequenceKnife.java:145) */
 #define RP_STATUS_BAD_CHAR  3 /* unsupported character; the reference exits(1) (AmbigSequenceKnife.java:124-128) */
-#define RP_STATUS_TOO_LONG  4 /* read longer than 2^26-64 characters: not placed (CUDA library limit)    */
+#define RP_STATUS_TOO_LONG  4 /* read longer than 2^30 characters: not placed (CUDA library limit)       */
 
 /* per-window kind (rp_extract_kmers) */
 #define RP_WIN_PLAIN   0     /* no ambiguity: one k-mer                                */
@@ -141,6 +141,48 @@ void rp_db_free(rp_db* db);
 int  rp_db_describe(const rp_db* db, rp_db_desc* out);
 /* bytes of HBM the DB occupies on one device (table + posting blocks) */
 int  rp_db_device_bytes(const rp_db* db, uint64_t* table_bytes, uint64_t* block_bytes);
+
+/* ---- synthetic DB generated ON THE DEVICE, one partition per call ("a synthetic DB too large
+ * for one GPU ... each GPU generates its own partition on device from the seed with a counter-based RNG keyed by
+ * code").  Every property of a key is a pure function of (seed, code) -- rappas_b200/csrc/rp_synth.h, restated
+ * on the host in rappas_b200/synth_hash.py -- so the keys a read sample probes can be regenerated for the CPU
+ * oracle while the whole DB exists nowhere but in the HBM of its owners.  Nucleotide, k <= 16.
+ *   occupancy        fraction of the 4^k codes that are keys (CustomHash_v4_FastUtil81.java:49: ">= 75 %")
+ *   plen_table       [65536] inverse CDF of the posting-list length, values in [1, n_nodes]
+ * n_parts == 1: a whole DB, ready for rp_place_batch.  n_parts > 1: partition `part` of the keys
+ * (owner = rp_partition_of_keys); complete it with rp_db_partition_blob + rp_db_attach_partitions (peer-memory
+ * form) or hand it to rp_xchg_create (exchange form).  desc->n_keys / n_postings are outputs (rp_db_describe). */
+int  rp_db_synth_partition(const rp_db_desc* desc, uint64_t seed, double occupancy, const uint16_t* plen_table,
+                           int32_t device, int32_t part, int32_t n_parts, rp_db** out);
+/* CUDA-IPC blob of the partition this handle holds (what rp_db_load_partition returns in blob_out) */
+int  rp_db_partition_blob(rp_db* db, uint8_t* blob_out);
+
+/* ---- EXCHANGE FORM of a hash-partitioned DB (north_star: "NCCL all-to-all of k-mer probes over NVLink, only for
+ * DBs exceeding one GPU's HBM").  One rank per GPU (one process each); rank p holds partition p and
+ * places its own reads: the keys of their windows travel to the owners (all-to-all), the owners answer with the
+ * posting lists of the hits (all-to-all back, pipelined over sub-batches), and the home GPU runs the same fused
+ * placement kernel over what it received -- rows are bit-identical to the replicated DB.  rp_xchg_place is a
+ * COLLECTIVE: every rank calls it, with its own reads (possibly none).
+ *   rp_xchg_unique_id   rank 0 creates the NCCL id; the host program hands it to the other ranks (any transport)
+ *   rp_xchg_create      `partition` = this rank's rp_db_load_partition / rp_db_synth_partition handle (kept by the
+ *                       caller, must outlive the rp_xchg); NCCL is loaded with dlopen("libnccl.so.2") (RP_NCCL_LIB)
+ *   rp_xchg_create_local  all `world` ranks inside ONE process on one GPU (collectives = device copies): how a
+ *                       1-GPU box tests the form; rp_xchg_place then takes `world` batches at once
+ *   rp_xchg_place       n_local = 1 (NCCL) or world (local); arrays of n_local pointers, each as in rp_place_batch
+ *                       (seq_off[l][0] == 0; out_counts may be NULL or hold NULL entries) */
+#define RP_XCHG_ID_BYTES 128
+typedef struct rp_xchg rp_xchg;
+int  rp_xchg_unique_id(uint8_t* id_out);
+int  rp_xchg_create(rp_db* partition, int32_t rank, int32_t world, const uint8_t* id, rp_xchg** out);
+int  rp_xchg_create_local(rp_db** partitions, int32_t world, rp_xchg** out);
+int  rp_xchg_place(rp_xchg* x, const rp_place_cfg* cfg, int32_t n_local, const uint8_t* const* seq,
+                   const uint64_t* const* seq_off, const int64_t* n_reads, int32_t* const* out_n_rows,
+                   uint16_t* const* out_node, float* const* out_score, double* const* out_lwr,
+                   int32_t* const* out_counts, int32_t* const* out_status);
+/* of the last rp_xchg_place: device time from "reads resident" to "rows ready" (max over local ranks), probes sent,
+ * posting bytes received */
+int  rp_xchg_stats(const rp_xchg* x, double* device_ms, uint64_t* probes, uint64_t* payload_bytes);
+void rp_xchg_free(rp_xchg* x);
 
 /* ---- placement of one batch of reads: replaces the per-read body of
  * PlacementProcess.processQueries (PlacementProcess.java:645-838) and the LWR / keep-factor

@@ -13,7 +13,8 @@ import numpy as np
 RP_OK = 0
 RP_MAX_KEEP = 32
 RP_PART_BLOB_BYTES = 152
-STATUS_PLACED, STATUS_UNPLACED, STATUS_TOO_SHORT, STATUS_BAD_CHAR = 0, 1, 2, 3
+STATUS_PLACED, STATUS_UNPLACED, STATUS_TOO_SHORT, STATUS_BAD_CHAR, STATUS_TOO_LONG = 0, 1, 2, 3, 4
+RP_XCHG_ID_BYTES = 128
 WIN_PLAIN, WIN_AMBIG, WIN_SKIPPED = 0, 1, 2
 CNT_WINDOWS, CNT_MATCHED, CNT_AMBIG, CNT_SKIPPED = 0, 1, 2, 3
 
@@ -58,6 +59,14 @@ PROTOTYPES = {
     "db_load_partition": (C.c_int, [C.POINTER(RpDbDesc), _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.POINTER(_P)]),
     "db_attach_partitions": (C.c_int, [_P, _P, C.c_int32]),
     "partition_of_keys": (C.c_int, [C.c_int32, C.c_int32, _P, C.c_uint64, C.c_int32, _P]),
+    "db_synth_partition": (C.c_int, [C.POINTER(RpDbDesc), C.c_uint64, C.c_double, _P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "db_partition_blob": (C.c_int, [_P, _P]),
+    "xchg_unique_id": (C.c_int, [_P]),
+    "xchg_create": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.POINTER(_P)]),
+    "xchg_create_local": (C.c_int, [_P, C.c_int32, C.POINTER(_P)]),
+    "xchg_place": (C.c_int, [_P, C.POINTER(RpPlaceCfg), C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "xchg_stats": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "xchg_free": (None, [_P]),
     "db_free": (None, [_P]),
     "gap_intervals": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "pp_prepare": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, _P, _P]),

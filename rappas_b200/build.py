@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "librappas_b200.so")
-SOURCES = ["rp_db.cu", "rp_place.cu", "rp_dbbuild.cu", "rp_ingest.cpp"]
-HEADERS = ["rp_common.h", "rp_dbbuild_core.h", "rp_dbbuild_merge.h", os.path.join("..", "..", "include", "rappas_b200.h")]
+SOURCES = ["rp_db.cu", "rp_place.cu", "rp_dbbuild.cu", "rp_synthdb.cu", "rp_xchg.cu", "rp_ingest.cpp"]
+HEADERS = ["rp_common.h", "rp_device.cuh", "rp_synth.h", "rp_dbbuild_core.h", "rp_dbbuild_merge.h", os.path.join("..", "..", "include", "rappas_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2,-Wall,-fvisibility=hidden", "--expt-relaxed-constexpr",
@@ -38,7 +38,7 @@ def stale():
 def build(force=False, verbose=False, extra=()):
     if not force and not stale():
         return OUT
-    cmd = [nvcc(), *NVCC_FLAGS, *extra, "-shared", "-o", OUT, *[os.path.join(CSRC, s) for s in SOURCES], "-lcudart"]
+    cmd = [nvcc(), *NVCC_FLAGS, *extra, "-shared", "-o", OUT, *[os.path.join(CSRC, s) for s in SOURCES], "-lcudart", "-ldl"]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)

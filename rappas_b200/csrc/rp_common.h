@@ -50,6 +50,14 @@ __host__ __device__ inline uint64_t block_bytes_for(uint64_t n_postings) {
 struct KeyHash { uint32_t a, b; };
 __host__ __device__ inline KeyHash hash_key(uint64_t key) {
   const uint32_t lo = (uint32_t)key, hi = (uint32_t)(key >> 32);
+#ifdef RP_HASH_OLD  /* bisect only: the round-1 single mix */
+  {
+    uint32_t x = lo ^ (hi * 0x9E3779B1u);
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    KeyHash o; o.a = x; o.b = x * 0x9E3779B1u + 0x7F4A7C15u;
+    return o;
+  }
+#endif
   uint32_t a = lo ^ (hi * 0x9E3779B1u);
   a ^= a >> 16; a *= 0x7feb352dU; a ^= a >> 15; a *= 0x846ca68bU; a ^= a >> 16;     // lowbias32
   uint32_t b = (hi ^ (lo * 0x85EBCA6Bu)) + 0x7F4A7C15u;
@@ -127,6 +135,17 @@ constexpr int kMetaQminShift = 53, kMetaQmaxShift = 57;
 constexpr uint64_t kMetaOffMask = (1ull << 37) - 1;  // 2^37 x 32 B = 4 TB of posting blocks per partition
 __host__ __device__ inline int padded_nodes(int n_nodes) { return (n_nodes + 127) & ~127; }
 
+// Exchange form of a hash-partitioned DB (rp_xchg.cu): the table lives with its owner, so the home GPU's kernel
+// does not probe anything -- the owners' answers to this batch's probes are already here, one stream per owner
+// in the order the home enumerated the probes.  rmeta[o][i] = the usual table meta of the i-th probe sent to
+// owner o (block offset = where the owner's posting block landed in the receive buffer, which is
+// DbView.blocks[o]), or kEmptyKey for a miss; base[r * n_parts + o] = index of read r's first probe in stream o.
+struct XchgView {
+  const uint64_t* rmeta[kMaxParts];
+  const uint32_t* base;
+  int n_parts;
+};
+
 struct CfgView {
   int K;
   float keep_factor;
@@ -200,7 +219,7 @@ struct Partition {   // one table + posting-block image resident on one device
   uint4* d_table = nullptr;
   uint64_t* d_direct = nullptr;  // direct-address table (replicated nucleotide DBs with 4^k <= 2^24 keys), else null
   uint8_t* d_blocks = nullptr;
-  uint64_t n_buckets = 0, block_bytes = 0;
+  uint64_t n_buckets = 0, block_bytes = 0, n_keys = 0;
   bool ipc = false;  // opened from another process' handle (cudaIpcCloseMemHandle instead of cudaFree)
 };
 }  // namespace rp
@@ -213,6 +232,7 @@ struct rp_db {
   uint64_t max_block_bytes = 0;
   int partitioned = 0;
   bool table_replicated = false;  // partitioned postings, but the whole table on every partition's device
+  bool xchg = false;              // one partition behind the exchange form (rp_xchg.cu): kernels read owners' answers
   rp::AlphabetTables alpha{};
   std::vector<rp::DeviceCtx*> dev;
   std::atomic<double> last_kernel_ms{0.0};
@@ -232,6 +252,11 @@ extern std::atomic<uint64_t> g_kernel_launches;
 
 DbView make_db_view(const rp_db* db, const DeviceCtx* dc);
 int compute_geometry(const rp_db* db, DeviceCtx* dc);  // rp_place.cu
+// enqueue the placement kernel in its exchange form (rp_place.cu; used by rp_xchg.cu): `view` names the receive
+// buffers as the posting-block bases, `xv` the owners' answers
+int launch_place_xchg(const rp_db* db, DeviceCtx* dc, const rp_place_cfg* cfg, const DbView& view, const BatchView& bt,
+                      const XchgView& xv, unsigned long long* d_counter, float* d_amb_S, int* d_amb_C, int grid_sms,
+                      cudaStream_t stream);
 int ensure_stream_ctx(const rp_db* db, DeviceCtx* dc, StreamCtx* sc);  // rp_place.cu
 
 }  // namespace rp

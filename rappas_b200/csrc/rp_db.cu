@@ -512,6 +512,7 @@ int rp_db_load_partition(const rp_db_desc* desc, const uint64_t* keys, const uin
   pt.device = device;
   pt.n_buckets = img.n_buckets;
   pt.block_bytes = img.block_bytes;
+  pt.n_keys = replicate_table ? desc->n_keys : sel.size();
   db->max_block_bytes = img.max_block_bytes;
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaMalloc((void**)&pt.d_table, img.n_buckets * 32);
@@ -538,6 +539,25 @@ int rp_db_load_partition(const rp_db_desc* desc, const uint64_t* keys, const uin
   dc->local_part = part;
   db->dev.push_back(dc);
   *out = db;
+  return RP_OK;
+}
+
+int rp_db_partition_blob(rp_db* db, uint8_t* blob_out) {
+  if (!db || !blob_out) return set_error(RP_E_INVALID, "NULL argument");
+  if (db->dev.size() != 1) return set_error(RP_E_INVALID, "not a single-partition handle");
+  const int part = db->dev[0]->local_part;
+  if (part < 0 || part >= (int)db->parts.size() || !db->parts[part].d_table || db->parts[part].ipc)
+    return set_error(RP_E_INVALID, "the handle holds no partition of its own");
+  Partition& pt = db->parts[part];
+  RP_CUDA_TRY(cudaSetDevice(pt.device));
+  PartBlob blob;
+  memset(&blob, 0, sizeof blob);
+  RP_CUDA_TRY(cudaIpcGetMemHandle(&blob.table, pt.d_table));
+  RP_CUDA_TRY(cudaIpcGetMemHandle(&blob.blocks, pt.d_blocks));
+  blob.n_buckets = pt.n_buckets;
+  blob.block_bytes = pt.block_bytes;
+  blob.n_keys = db->desc.n_keys;
+  memcpy(blob_out, &blob, sizeof blob);
   return RP_OK;
 }
 

@@ -40,6 +40,7 @@
 #include <thread>
 
 #include "rp_common.h"
+#include "rp_device.cuh"
 
 namespace rp {
 
@@ -106,43 +107,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 
 // ------------------------------------------------------------------------------------ helpers
-// Cuckoo lookup: both candidate buckets (2 x 2 slots of 16 B) are loaded unconditionally.
-// In partitioned mode the owner partition's table is probed (peer memory over NVLink if it is remote).
-// one bucket = 2 slots = one 32 B sector: a single 256-bit load (LDG.E.256) instead of two 128-bit ones halves
-// the load-pipe work of a probe (32 lanes, 32 different sectors per instruction)
-__device__ __forceinline__ void ldg_bucket(const uint4* p, uint4& a, uint4& b) {
-  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
-               : "l"(p));
-}
-__device__ __forceinline__ bool table_probe(const DbView& db, uint64_t key, uint64_t& meta) {
-  if (db.direct) {  // direct-address table (small nucleotide key spaces)
-    meta = __ldg(reinterpret_cast<const unsigned long long*>(db.direct) + key);
-    return meta != kEmptyKey;
-  }
-  const KeyHash m = hash_key(key);
-  const int part = db.table_parts > 1 ? (int)owner_of(m, db.table_parts) : 0;
-  const uint4* table = db.table[part];
-  const int shift = db.bucket_shift[part];
-  const uint4* p1 = table + (size_t)bucket1(m, shift) * kBucketSlots;
-  const uint4* p2 = table + (size_t)bucket2(m, shift) * kBucketSlots;
-  uint4 s0, s1, s2, s3;
-  ldg_bucket(p1, s0, s1);
-  ldg_bucket(p2, s2, s3);
-  const uint32_t klo = (uint32_t)key, khi = (uint32_t)(key >> 32);
-  const bool h0 = s0.x == klo && s0.y == khi, h1 = s1.x == klo && s1.y == khi;
-  const bool h2 = s2.x == klo && s2.y == khi, h3 = s3.x == klo && s3.y == khi;
-  const uint32_t z = h0 ? s0.z : h1 ? s1.z : h2 ? s2.z : s3.z;
-  const uint32_t w = h0 ? s0.w : h1 ? s1.w : h2 ? s2.w : s3.w;
-  meta = (uint64_t)z | ((uint64_t)w << 32);
-  return h0 | h1 | h2 | h3;
-}
-
-// posting block a table meta points to (its partition is in the top bits)
-__device__ __forceinline__ const uint8_t* block_ptr(const DbView& db, uint64_t meta) {
-  return db.blocks[meta >> kMetaPartShift] + ((meta >> 16) & kMetaOffMask) * kBlockAlign;
-}
-
+// (table_probe / block_ptr / ldg_bucket: rp_device.cuh)
 __device__ __forceinline__ bool is_sentinel(float s) { return __float_as_uint(s) == kSentinelBits; }
 
 // total order used for selection: higher score first, lower node id on exact ties
@@ -183,34 +148,14 @@ __device__ __forceinline__ void accumulate_global(float* __restrict__ S, const u
 }
 
 // One ambiguous window (<= max_amb ambiguous residues): treatAmbiguitiesWithMean / WithMax,
-// PlacementProcess.java:1129-1174 / 1185-1236.  Rare path; S_amb/C_amb live in a per-warp global
-// scratch that is all-zero between calls.  `seq` = the window's first character.
-__device__ __forceinline__ void ambiguous_window(const AlphabetTables& c_alpha, const DbView& db, const CfgView& cfg,
-                                              float* __restrict__ S, const uint8_t* seq, float QT, float* Sa, int* Ca,
-                                              int lane, uint32_t lo, uint32_t width) {
-  // class bytes of the window (k <= 31), and the ambiguous offsets inside it (ascending)
-  uint8_t cls[32];
-  uint32_t wbits = 0;
-  for (int i = 0; i < db.k; i++) {
-    cls[i] = c_alpha.cls[seq[i]];
-    if ((cls[i] & 0xC0) == kClsAmb) wbits |= 1u << i;
-  }
-  const int o1 = __ffs(wbits) - 1;
-  const uint32_t rest = wbits & (wbits - 1);
-  const int o2 = rest ? __ffs(rest) - 1 : -1;
-  const int id1 = cls[o1] & 0x3F;
-  const int n1 = c_alpha.alt_n[id1];
-  const int id2 = o2 >= 0 ? (cls[o2] & 0x3F) : 0;
-  const int n2 = o2 >= 0 ? c_alpha.alt_n[id2] : 1;
-  const int n = n1 * n2;  // W_size ; <= 20 (amino) / 16 (nucl, 2 ambiguities)
-  // alternative t (lane t): position o_m takes A_m[t mod |A_m|]  (AmbigSequenceKnife.java:249-256)
-  uint64_t meta = 0;
-  bool found = false;
-  if (lane < n) {
-    const uint64_t key = planar_from_states(cls, db.k, db.bits, o1, c_alpha.alt_states[id1][lane % n1], o2,
-                                            c_alpha.alt_states[id2][lane % n2], nullptr);
-    found = table_probe(db, key, meta);
-  }
+// PlacementProcess.java:1129-1174 / 1185-1236.  Rare path (the alternatives did not fit a stage); S_amb/C_amb
+// live in a per-warp global scratch that is all-zero between calls.  `metas` = the table entries of the n
+// alternatives as the producer resolved them (kEmptyKey = not in the DB), in alternative order.
+__device__ __forceinline__ void ambiguous_window(const DbView& db, const CfgView& cfg, float* __restrict__ S,
+                                              const uint64_t* metas, int n, float QT, float* Sa, int* Ca, int lane,
+                                              uint32_t lo, uint32_t width) {
+  const uint64_t meta = lane < n ? metas[lane] : kEmptyKey;
+  const bool found = meta != kEmptyKey;
   const uint32_t fm = __ballot_sync(0xffffffffu, found);
   if (!fm) return;
   // pass 1: S_amb / C_amb over the alternatives in order (:1137-1157 / :1196-1219)
@@ -348,50 +293,35 @@ __device__ __forceinline__ void select_scan(const CfgView& cfg, float* __restric
     // a full list from earlier slices raises the bar: only nodes that beat its K-th entry can enter
     if (t.cnt >= K) tau = fmaxf(tau, __shfl_sync(0xffffffffu, t.s, K - 1));
   }
-  // one 128-node row: reset, dump, and push the nodes >= tau (a handful per read) into the list
-  auto row = [&](int i0, const float4 q) {
-    // NaN >= tau is false: untouched nodes never qualify
-    const bool c0 = q.x >= tau, c1 = q.y >= tau, c2 = q.z >= tau, c3 = q.w >= tau;
-    if (!__any_sync(0xffffffffu, c0 | c1 | c2 | c3)) return;
+  // The sweep: reset, dump, and push the nodes >= tau (a handful per read) into the list.  One row of 128 nodes
+  // per step with the next row's load in flight, and ONE insertion site (the component loop is not unrolled):
+  // the unrolled form with its 20 inlined insertions pushed the kernel's hot code past the instruction cache
+  // (no_inst = 33 % of the stall samples, profiles/r02_icache_*): code size is a first-order cost here.
+  float4 q = *reinterpret_cast<const float4*>(S + lane * 4);
+#pragma unroll 1
+  for (int i0 = 0; i0 < n; i0 += 128) {
+    const int i = i0 + lane * 4;
+    const float4 cur = q;
+    if (i0 + 128 < n) q = *reinterpret_cast<const float4*>(S + i + 128);
+    *reinterpret_cast<float4*>(S + i) = sent4;
+    if (dump_row) {
+      const float qq[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
+      for (int c = 0; c < 4; c++)
+        if (node0 + i + c < n_nodes && !is_sentinel(qq[c])) dump_row[node0 + i + c] = qq[c];
+    }
+    // NaN >= tau is false: untouched nodes never qualify
+    if (!__any_sync(0xffffffffu, fmaxf(fmaxf(cur.x, cur.y), fmaxf(cur.z, cur.w)) >= tau)) continue;
+#pragma unroll 1
     for (int c = 0; c < 4; c++) {
-      const float sc = c == 0 ? q.x : c == 1 ? q.y : c == 2 ? q.z : q.w;
-      const bool cand = c == 0 ? c0 : c == 1 ? c1 : c == 2 ? c2 : c3;
-      uint32_t pm = __ballot_sync(0xffffffffu, cand);
+      const float sc = c == 0 ? cur.x : c == 1 ? cur.y : c == 2 ? cur.z : cur.w;
+      uint32_t pm = __ballot_sync(0xffffffffu, sc >= tau);
       while (pm) {
         const int src = __ffs(pm) - 1;
         pm &= pm - 1;
         top_insert(t, __shfl_sync(0xffffffffu, sc, src), node0 + i0 + src * 4 + c, K, lane);
       }
     }
-  };
-  auto dump = [&](int i, const float4 q) {
-    const float qq[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-    for (int c = 0; c < 4; c++)
-      if (node0 + i + c < n_nodes && !is_sentinel(qq[c])) dump_row[node0 + i + c] = qq[c];
-  };
-  int i0 = 0;
-  for (; i0 + 384 < n; i0 += 512) {
-    const int i = i0 + lane * 4;
-    const float4 q0 = *reinterpret_cast<const float4*>(S + i), q1 = *reinterpret_cast<const float4*>(S + i + 128);
-    const float4 q2 = *reinterpret_cast<const float4*>(S + i + 256), q3 = *reinterpret_cast<const float4*>(S + i + 384);
-    *reinterpret_cast<float4*>(S + i) = sent4;
-    *reinterpret_cast<float4*>(S + i + 128) = sent4;
-    *reinterpret_cast<float4*>(S + i + 256) = sent4;
-    *reinterpret_cast<float4*>(S + i + 384) = sent4;
-    if (dump_row) { dump(i, q0); dump(i + 128, q1); dump(i + 256, q2); dump(i + 384, q3); }
-    const float h0 = fmaxf(fmaxf(q0.x, q0.y), fmaxf(q0.z, q0.w)), h1 = fmaxf(fmaxf(q1.x, q1.y), fmaxf(q1.z, q1.w));
-    const float h2 = fmaxf(fmaxf(q2.x, q2.y), fmaxf(q2.z, q2.w)), h3 = fmaxf(fmaxf(q3.x, q3.y), fmaxf(q3.z, q3.w));
-    if (!__any_sync(0xffffffffu, fmaxf(fmaxf(h0, h1), fmaxf(h2, h3)) >= tau)) continue;
-    row(i0, q0); row(i0 + 128, q1); row(i0 + 256, q2); row(i0 + 384, q3);
-  }
-  for (; i0 < n; i0 += 128) {
-    const int i = i0 + lane * 4;
-    const float4 q = *reinterpret_cast<const float4*>(S + i);
-    *reinterpret_cast<float4*>(S + i) = sent4;
-    if (dump_row) dump(i, q);
-    row(i0, q);
   }
   __syncwarp();
 }
@@ -411,22 +341,28 @@ __device__ __forceinline__ int finalize_rows(const CfgView& cfg, const TopList& 
   // computeWeightRatio: Math.pow(10.0,(double)(s.score-weightRatioShift))/sum with a double shift (:392-393)
   // One f64 exp10 per read instead of two (it is ~150 instructions on 7 of 32 lanes; 9.5 % of the stall samples of
   // the round-1 kernel sat behind the pair of calls): lanes 0..15 take the numerators, lanes 16..31 the shifted
-  // terms of the sum for the same nodes.  K > 16 keeps the two calls.
+  // terms of the sum for the same nodes.  K > 16 runs the same call site twice (one site: code size, see above).
   double num = 0.0, e = 0.0;
-  if (K <= 16) {
-    const float ts = __shfl_sync(0xffffffffu, top_s, lane & 15);
-    const bool valid = (lane & 15) < nb;
+  const bool halves = K <= 16;
+#pragma unroll 1
+  for (int rep = 0; rep < (halves ? 1 : 2); rep++) {
+    const int li = halves ? (lane & 15) : lane;
+    const bool second = halves ? lane >= 16 : rep == 1;
+    const float ts = __shfl_sync(0xffffffffu, top_s, li);
     // the sum's terms subtract in f32 when shifted (:446), else they are the plain powers (:418)
-    const double arg = (lane >= 16) ? (double)__fsub_rn(ts, shift) : (double)ts - (double)shift;
-    const double ex = (valid && (lane < 16 || shift != 0.0f)) ? exp10(arg) : 0.0;
-    const double ex_hi = __shfl_sync(0xffffffffu, ex, (lane & 15) + 16);
-    num = ex;
-    e = (shift != 0.0f) ? ex_hi : ex;
-    if (lane >= nb) { num = 0.0; e = 0.0; }
-  } else if (lane < nb) {
-    num = exp10((double)top_s - (double)shift);
-    e = (shift != 0.0f) ? exp10((double)__fsub_rn(top_s, shift)) : num;
+    const double arg = second ? (double)__fsub_rn(ts, shift) : (double)ts - (double)shift;
+    const double ex = (li < nb && (!second || shift != 0.0f)) ? exp10(arg) : 0.0;
+    if (halves) {
+      const double ex_hi = __shfl_sync(0xffffffffu, ex, (lane & 15) + 16);
+      num = ex;
+      e = (shift != 0.0f) ? ex_hi : ex;
+    } else if (rep == 0) {
+      num = e = ex;
+    } else if (shift != 0.0f) {
+      e = ex;
+    }
   }
+  if (lane >= nb) { num = 0.0; e = 0.0; }
   double sum = 0.0;  // ascending score order, as the rebuilt sum of :445-447
   for (int i = nb - 1; i >= 0; i--) sum += __shfl_sync(0xffffffffu, e, i);
   double lwr = 0.0;
@@ -651,17 +587,22 @@ struct PairSmem {
 // DIRECT: nucleotide DBs with 4^k <= 2^24 possible keys carry a direct-address table (one u64 meta per planar
 // key, kEmptyKey = absent) beside the cuckoo table: one 8 B load per window instead of two 32 B buckets, no
 // hashing and no key compare (the cuckoo table stays the general form).
+// kXchg: exchange form of a partitioned DB -- the "probe" reads the owner's answer (see XchgView).
+enum : int { kCuckoo = 0, kDirect = 1, kXchg = 2 };
 struct ProbeIO {
-  uint4 s0, s1, s2, s3;   // the four candidate slots (in flight after issue); DIRECT: s0.x/y = the meta
+  uint4 s0, s1, s2, s3;   // the four candidate slots (in flight after issue); kDirect / kXchg: s0.x/y = the meta
   uint32_t klo, khi;
 };
-template <bool DIRECT>
-__device__ __forceinline__ void probe_issue(const DbView& db, uint64_t key, bool active, ProbeIO& io) {
+template <int MODE>
+__device__ __forceinline__ void probe_issue(const DbView& db, uint64_t key, bool active, ProbeIO& io,
+                                            const uint64_t* answer = nullptr) {
   io.klo = (uint32_t)key; io.khi = (uint32_t)(key >> 32);
   io.s0 = io.s1 = io.s2 = io.s3 = make_uint4(0xffffffffu, 0xffffffffu, 0u, 0u);  // the empty key never matches
   if (active) {
-    if (DIRECT) {
+    if (MODE == kDirect) {
       asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(io.s0.x), "=r"(io.s0.y) : "l"(db.direct + key));
+    } else if (MODE == kXchg) {
+      asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(io.s0.x), "=r"(io.s0.y) : "l"(answer));
     } else {
       const KeyHash m = hash_key(key);
       const int part = db.table_parts > 1 ? (int)owner_of(m, db.table_parts) : 0;
@@ -674,9 +615,9 @@ __device__ __forceinline__ void probe_issue(const DbView& db, uint64_t key, bool
     }
   }
 }
-template <bool DIRECT>
+template <int MODE>
 __device__ __forceinline__ bool probe_resolve(const ProbeIO& io, uint64_t& meta) {
-  if (DIRECT) {
+  if (MODE != kCuckoo) {
     meta = (uint64_t)io.s0.x | ((uint64_t)io.s0.y << 32);
     return (io.s0.x & io.s0.y) != 0xffffffffu;
   }
@@ -693,10 +634,10 @@ __device__ __forceinline__ bool probe_resolve(const ProbeIO& io, uint64_t& meta)
 // the passes whose slice its (node-sorted) posting list can touch: the table entry carries the first and the
 // last sixteenth of the padded node range the list spans.  Every node belongs to exactly one pass and the
 // windows of a pass are visited in order, so each S[x] still sees the reference's f32 addition sequence.
-template <bool SLICED, bool DIRECT>
+template <bool SLICED, int MODE>
 __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const DbView& db, const CfgView& cfg,
-                                         const BatchView& bt, unsigned long long* work_counter, const PairSmem& w,
-                                         uint32_t cls_tab, int lane, int n_pad, int slice, int n_pass) {
+                                         const BatchView& bt, const XchgView& xv, unsigned long long* work_counter,
+                                         const PairSmem& w, uint32_t cls_tab, int lane, int n_pad, int slice, int n_pass) {
   const int k = db.k;
   const uint32_t kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
   const int stage_bytes = w.stage_bytes;
@@ -720,6 +661,19 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
   int g_nv = 0;
   ProbeIO io;
   io.klo = io.khi = 0; io.s0 = io.s1 = io.s2 = io.s3 = make_uint4(0, 0, 0, 0);
+  // kXchg: lane o < n_parts keeps the index of the read's next answer in owner o's stream, and the lanes of the
+  // group in flight whose key belongs to owner o (its counter moves by the windows the group consumes)
+  uint32_t x_run = 0, x_base = 0, x_mask = 0;
+  // index of this lane's answer: the owner's counter + the lanes before this one with the same owner
+  auto answer_of = [&](uint64_t key, bool active) -> const uint64_t* {
+    const uint32_t own = active ? owner_of(hash_key(key), xv.n_parts) : 0xFFu;
+    for (int o = 0; o < xv.n_parts; o++) {
+      const uint32_t m = __ballot_sync(0xffffffffu, own == (uint32_t)o);
+      if (lane == o) x_mask = m;
+    }
+    const uint32_t mine = __shfl_sync(0xffffffffu, x_mask, own & 7u), cur = __shfl_sync(0xffffffffu, x_run, own & 7u);
+    return xv.rmeta[own & 7u] + (cur + __popc(mine & lt_mask));
+  };
 
   auto cls_of = [&](uint32_t raw, int i) -> uint32_t { return i < len ? lds_u8(cls_tab + raw) : (uint32_t)kClsPad; };
   // K1 of the group whose class bytes are in cA/cB, and issue of its probes (K2).  A group is a run of plain
@@ -751,7 +705,8 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
         key |= (uint64_t)(__funnelshift_r(b0, b1, lane) & kmask) << (p * k);
       }
     }
-    probe_issue<DIRECT>(db, key, g_plain, io);
+    if (MODE == kXchg) probe_issue<MODE>(db, key, g_plain, io, answer_of(key, g_plain));
+    else probe_issue<MODE>(db, key, g_plain, io);
   };
   // The alternatives of the ambiguous window g0 (class bytes in cA): lane t < W_size probes alternative t,
   // in which position o_m takes A_m[t mod |A_m|]  (AmbigSequenceKnife.java:249-256).  Returns W_size.
@@ -769,13 +724,20 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       plane |= (uint64_t)((st1 >> p) & 1u) << o1;
       key |= plane << (p * k);
     }
-    found = lane < wsize && table_probe(db, key, meta);
+    if (MODE == kXchg) {  // the alternatives' answers, in alternative order; all of them are consumed
+      const uint64_t* a = answer_of(key, lane < wsize);
+      meta = lane < wsize ? __ldg(reinterpret_cast<const unsigned long long*>(a)) : kEmptyKey;
+      found = meta != kEmptyKey;
+      if (lane < xv.n_parts) x_run += __popc(x_mask);
+    } else {
+      found = lane < wsize && table_probe(db, key, meta);
+    }
     return wsize;
   };
   // The NEXT read of the pair: its index comes from the atomic issued one read earlier and its two
   // offsets are requested when the current read starts, so a read start waits for its characters only.
   // (Prefetching those too costs the producer more registers than it has: it spills.)
-  uint32_t nx_r = 0;
+  uint32_t nx_r = 0, nx_base = 0;
   uint64_t nx_o0 = 0, nx_o1 = 0;
   bool nx_have = false;
   auto fetch_next_offsets = [&]() {
@@ -785,6 +747,7 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       if (lane == 0) rn_raw = (uint32_t)atomicAdd(work_counter, 1ull);  // consumed when that read starts
       nx_o0 = bt.seq_off[nx_r];
       nx_o1 = bt.seq_off[nx_r + 1];
+      if (MODE == kXchg && lane < xv.n_parts) nx_base = xv.base[(size_t)nx_r * xv.n_parts + lane];
     }
   };
   // first 96 characters of the read (a pass starts here again)
@@ -794,6 +757,7 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
     cA = lane < len ? lds_u8(cls_tab + s[lane]) : (uint32_t)kClsPad;
     cB = lane + 32 < len ? lds_u8(cls_tab + s[lane + 32]) : (uint32_t)kClsPad;
     rawC = lane + 64 < len ? s[lane + 64] : 0u;
+    if (MODE == kXchg) x_run = x_base;  // every pass walks the read's answers from the start
     if (SLICED) {
       const int u = n_pad >> 4, lo = pass * slice, hi = min(lo + slice, n_pad);
       pqlo = (uint32_t)(lo / u);
@@ -810,6 +774,7 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
     Ql = len - k + 1;  // sk.getMerCount()
     QT = __fmul_rn((float)Ql, db.T);  // Q*PPStarThresholdAsLog10 (int*float)
     pass = 0;
+    if (MODE == kXchg) x_base = nx_base;
     load_chars();
     fetch_next_offsets();
     front();
@@ -857,7 +822,7 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       bool found;
       int wsize = 0;
       if (RP_UNLIKELY(g_nv == 0)) wsize = probe_alternatives(found, meta);
-      else found = probe_resolve<DIRECT>(io, meta);
+      else found = probe_resolve<MODE>(io, meta);
       // node-range pass: only the windows whose list can touch this pass's slice are staged
       bool routed = found;
       if (SLICED) {
@@ -892,6 +857,7 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
         if (tot_chunks) lg = min(lg, 32u - __clz(64u * tot_chunks - 1u));  // ... up to twice the postings
         const bool staged = !nofit && !giantm && (1u << lg) >= 32u * tot_chunks && lg >= 5;
         flags |= (staged ? kGrpAmb : kGrpAmbGlobal) | (wsize << kGrpWsizeShift) | (lg << kGrpTabShift);
+        if (!found) meta = kEmptyKey;  // (the consumer's global-memory walk takes the alternatives' entries as they are)
         hitm = stagedm = staged ? foundm : 0u;
         cons = 1;
         last = 31;
@@ -905,6 +871,7 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
         stagedm = __ballot_sync(0xffffffffu, sb != 0u) & lanes;
         n_match += __popc((SLICED ? __ballot_sync(0xffffffffu, found) : hitm) & lanes);
         n_skip += __popc(__ballot_sync(0xffffffffu, g_skip) & lanes);
+        if (MODE == kXchg && lane < xv.n_parts) x_run += __popc(x_mask & lanes);  // the answers of the windows taken
       }
       off = incl_bytes - sb;
       if (!((stagedm >> lane) & 1u)) bytes = 0;  // only staged windows are copied
@@ -930,7 +897,7 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
     const uint32_t last_incl = (stagedm && cons > 0) ? __shfl_sync(0xffffffffu, incl, last) : 0u;
     if (more) front();
     acquire();
-    if (hitm & ~stagedm) {  // the consumer's per-window path needs these
+    if ((hitm & ~stagedm) | (uint32_t)(flags & kGrpAmbGlobal)) {  // the consumer's per-window path needs these
       sts_u32(hdr + 64 + 4 * lane, (off_c << 16) | n_post_c);
       sts_u64(hdr + 192 + 8 * lane, make_uint2((uint32_t)meta_c, (uint32_t)(meta_c >> 32)));
     }
@@ -949,7 +916,11 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       const uint32_t prevm = stagedm & lt_mask;
       const uint32_t pq = __shfl_sync(0xffffffffu, q8, prevm ? 31 - __clz(prevm) : 0);
       const bool disjoint = (q8 >> 4) < (pq & 15u) || (pq >> 4) < (q8 & 15u);
+#ifdef RP_NOPAIR  /* bisect only: never pair the chunks of two windows */
+      const bool split = bytes_c && (c0 & 1u) && !(flags & kGrpAmb);
+#else
       const bool split = bytes_c && (c0 & 1u) && !disjoint && !(flags & kGrpAmb);
+#endif
       const uint32_t splitm = __ballot_sync(0xffffffffu, split);
       const uint32_t sbef = __popc(splitm & lt_mask) + (split ? 1u : 0u);
       n_steps = (int)(((n_chunks + 1) >> 1) + __popc(splitm));
@@ -1043,7 +1014,8 @@ __device__ __forceinline__ void consumer(const AlphabetTables& c_alpha, const Db
                            (g.flags >> kGrpWsizeShift) & 0x1F, g.QT, lane, lo, width);
       } else if (g.flags & kGrpAmbGlobal) {
         // one ambiguous window whose alternatives did not fit a stage
-        ambiguous_window(c_alpha, db, cfg, Sv, g.seq, g.QT, Sa, Ca, lane, lo, width);
+        ambiguous_window(db, cfg, Sv, reinterpret_cast<const uint64_t*>(w.meta + slot * kStageMetaBytes + 192),
+                         (g.flags >> kGrpWsizeShift) & 0x1F, g.QT, Sa, Ca, lane, lo, width);
       } else {
         // a posting block larger than a stage: windows one by one, in order (a node's S[x] must see its
         // contributions in window order)
@@ -1109,11 +1081,11 @@ constexpr int kMaxThreads = kMaxPairsPerCta * 64;
 // kernel may use the 128 registers a 512-thread CTA gets: the slice arithmetic spilt at 80
 constexpr int kWantPairs = 8;
 constexpr int max_threads_for(bool sliced) { return sliced ? kWantPairs * 64 : kMaxThreads; }
-template <bool SLICED, bool DIRECT>
+template <bool SLICED, int MODE>
 __global__ void __launch_bounds__(max_threads_for(SLICED), 1)
 place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_constant__ DbView db,
              const __grid_constant__ CfgView cfg, const __grid_constant__ BatchView bt,
-             unsigned long long* work_counter, float* amb_S, int* amb_C, int n_pad, int per_pair_bytes,
+             const __grid_constant__ XchgView xv, unsigned long long* work_counter, float* amb_S, int* amb_C, int n_pad, int per_pair_bytes,
              int stage_bytes, int max_chunks, int slice, int n_pass) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int lane = threadIdx.x & 31;
@@ -1153,7 +1125,7 @@ place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_consta
   // local memory around them, and with ~227 KB of shared memory carved out there is no L1 left, so every
   // such spill was an L2 round trip: 20 % of the kernel time, profiles/r01_v5_spill_stalls.txt.)
   if (is_producer) {
-    producer<SLICED, DIRECT>(c_alpha, db, cfg, bt, work_counter, w, smem_u32(smem), lane, n_pad, slice, n_pass);
+    producer<SLICED, MODE>(c_alpha, db, cfg, bt, xv, work_counter, w, smem_u32(smem), lane, n_pad, slice, n_pass);
   } else {
     const size_t gp = (size_t)blockIdx.x * pairs + pair;
     consumer<SLICED>(c_alpha, db, cfg, bt, w, amb_S + gp * n_pad, amb_C + gp * n_pad, n_pad, slice, lane);
@@ -1237,11 +1209,12 @@ __global__ void fill_f32_kernel(float* p, size_t n, float v) {
 // resident pairs under the 227 KB budget, 768 threads and the register file.  A stage holds about a group's
 // worth of posting blocks.  Trees whose S[] would leave fewer than kWantPairs reads per SM are walked in
 // node-range passes (S = one slice).  RP_STAGE_BYTES / RP_PASSES / RP_PAIRS_PER_SM override for tuning.
-typedef void (*place_kernel_t)(const AlphabetTables, const DbView, const CfgView, const BatchView, unsigned long long*,
-                               float*, int*, int, int, int, int, int, int);
-static place_kernel_t kernel_for(bool sliced, bool direct) {
-  return sliced ? (direct ? place_kernel<true, true> : place_kernel<true, false>)
-                : (direct ? place_kernel<false, true> : place_kernel<false, false>);
+typedef void (*place_kernel_t)(const AlphabetTables, const DbView, const CfgView, const BatchView, const XchgView,
+                               unsigned long long*, float*, int*, int, int, int, int, int, int);
+static place_kernel_t kernel_for(bool sliced, int mode) {
+  if (mode == kXchg) return sliced ? place_kernel<true, kXchg> : place_kernel<false, kXchg>;
+  if (mode == kDirect) return sliced ? place_kernel<true, kDirect> : place_kernel<false, kDirect>;
+  return sliced ? place_kernel<true, kCuckoo> : place_kernel<false, kCuckoo>;
 }
 static bool db_is_direct(const rp_db* db, const DeviceCtx* dc) {
   return !db->partitioned && !dc->parts.empty() && db->parts[dc->parts[0]].d_direct != nullptr;
@@ -1253,8 +1226,11 @@ int compute_geometry(const rp_db* db, DeviceCtx* dc) {
   const size_t cta_fixed = 256;
   const size_t optin = dc->smem_optin;         // 227 KB on sm_100
   const size_t sm_total = optin + 1024;        // 228 KB per SM, 1 KB reserved per resident CTA
-  const double mean_block = db->desc.n_keys ? (double)db->block_bytes / (double)db->desc.n_keys : 32.0;
-  auto chunks_for = [&](long st) { return (size_t)((32 + st / kSubBlockBytes + 13 + 1) & ~1); };  // per window + per extra sub-block + idle
+  // (exchange form: the handle holds one partition, and the kernel gathers what the owners sent -- same mean)
+  const uint64_t keys_here = db->xchg ? db->parts[dc->local_part].n_keys : db->desc.n_keys;
+  const uint64_t bytes_here = db->xchg ? db->parts[dc->local_part].block_bytes : db->block_bytes;
+  const double mean_block = keys_here ? (double)bytes_here / (double)keys_here : 32.0;
+  auto chunks_for = [&](long st) { return (size_t)((32 + st / kSubBlockBytes + 7 + 1) & ~1); };  // steps <= chunks: per window + per extra sub-block; + 6 idle
   auto pair_bytes = [&](long st, int slice) {
     return (64 + kStages * (size_t)kStageMetaBytes + kStages * 16 * chunks_for(st) + 4 * (size_t)(slice + 32) +
             kStages * (size_t)st + 127) & ~(size_t)127;
@@ -1279,7 +1255,7 @@ int compute_geometry(const rp_db* db, DeviceCtx* dc) {
   // a slightly smaller stage that lets one more pair fit is the better trade (cfg2: 4992 B -> 11 pairs)
   if (!getenv("RP_STAGE_BYTES")) {
     const size_t t0 = (optin - cta_fixed) / pair_bytes(stage, g.slice);
-    for (long st = stage - 128; st >= stage - stage / 16 && st >= 1024; st -= 128)
+    for (long st = stage - 128; st >= stage - stage / 4 && st >= 1024; st -= 128)
       if ((optin - cta_fixed) / pair_bytes(st, g.slice) > t0) { stage = st; break; }
   }
   g.stage_bytes = (int)stage;
@@ -1294,7 +1270,8 @@ int compute_geometry(const rp_db* db, DeviceCtx* dc) {
   // registers bind before shared memory does on small trees (768 threads x 80 registers fill the file):
   // a split into several CTAs only counts for what the register file keeps resident
   RP_CUDA_TRY(cudaSetDevice(dc->device));
-  place_kernel_t kern = kernel_for(n_pass > 1, db_is_direct(db, dc));
+  const int mode = db->xchg ? kXchg : db_is_direct(db, dc) ? kDirect : kCuckoo;
+  place_kernel_t kern = kernel_for(n_pass > 1, mode);
   cudaFuncAttributes fa;
   RP_CUDA_TRY(cudaFuncGetAttributes(&fa, kern));
   const int regs_sm = 65536;
@@ -1367,13 +1344,31 @@ static int launch_place(const rp_db* db, DeviceCtx* dc, StreamCtx* sc, const rp_
   const LaunchGeom& g = dc->geom;
   RP_CUDA_TRY(cudaMemsetAsync(sc->d_counter, 0, sizeof(unsigned long long), stream));
   if (time_it) RP_CUDA_TRY(cudaEventRecord(sc->ev_k0, stream));
-  place_kernel_t kern = kernel_for(g.n_pass > 1, db_is_direct(db, dc));
+  place_kernel_t kern = kernel_for(g.n_pass > 1, db_is_direct(db, dc) ? kDirect : kCuckoo);
+  XchgView xv;
+  memset(&xv, 0, sizeof xv);
   kern<<<g.grid, g.warps_per_cta * 32, g.smem_bytes, stream>>>(
-      db->alpha, make_db_view(db, dc), make_cfg_view(cfg), bt, sc->d_counter, sc->d_amb_S, sc->d_amb_C, g.n_pad,
+      db->alpha, make_db_view(db, dc), make_cfg_view(cfg), bt, xv, sc->d_counter, sc->d_amb_S, sc->d_amb_C, g.n_pad,
       (int)g.per_warp_bytes, g.stage_bytes, g.max_chunks, g.slice, g.n_pass);
   RP_CUDA_TRY(cudaGetLastError());
   g_kernel_launches.fetch_add(1);
   if (time_it) RP_CUDA_TRY(cudaEventRecord(sc->ev_k1, stream));
+  return RP_OK;
+}
+
+int launch_place_xchg(const rp_db* db, DeviceCtx* dc, const rp_place_cfg* cfg, const DbView& view, const BatchView& bt,
+                      const XchgView& xv, unsigned long long* d_counter, float* d_amb_S, int* d_amb_C, int grid_sms,
+                      cudaStream_t stream) {
+  const LaunchGeom& g = dc->geom;
+  RP_CUDA_TRY(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream));
+  place_kernel_t kern = kernel_for(g.n_pass > 1, kXchg);
+  int grid = g.grid;
+  if (grid_sms > 0) grid = std::min(grid, grid_sms * g.ctas_per_sm);
+  kern<<<grid, g.warps_per_cta * 32, g.smem_bytes, stream>>>(db->alpha, view, make_cfg_view(cfg), bt, xv, d_counter, d_amb_S,
+                                                               d_amb_C, g.n_pad, (int)g.per_warp_bytes, g.stage_bytes,
+                                                               g.max_chunks, g.slice, g.n_pass);
+  RP_CUDA_TRY(cudaGetLastError());
+  g_kernel_launches.fetch_add(1);
   return RP_OK;
 }
 

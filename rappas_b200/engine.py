@@ -77,6 +77,54 @@ class Database:
         return self
 
     @classmethod
+    def partition_of_synth(cls, db, device, part, n_parts):
+        """Only hash partition `part` of `db`, on `device` (host-built): a rank of the exchange form
+        (rappas_b200.exchange) or, after attach, of the peer-memory form."""
+        fn = load()
+        keys = np.ascontiguousarray(db.keys, dtype=np.uint64)
+        offsets = np.ascontiguousarray(db.offsets, dtype=np.uint64)
+        post_node = np.ascontiguousarray(db.post_node, dtype=np.uint16)
+        post_score = np.ascontiguousarray(db.post_score, dtype=np.float32)
+        desc = _abi.RpDbDesc(int(db.alphabet), int(db.k), int(db.n_nodes), float(db.thr_log10), float(db.thr_lin), 0,
+                             keys.shape[0], post_node.shape[0])
+        blob = np.zeros(_abi.RP_PART_BLOB_BYTES, np.uint8)
+        h = C.c_void_p()
+        check(fn["db_load_partition"](C.byref(desc), _abi.ptr(keys), _abi.ptr(offsets), _abi.ptr(post_node),
+                                      _abi.ptr(post_score), int(device), int(part), int(n_parts), 0, _abi.ptr(blob), C.byref(h)))
+        return cls(h, desc)
+
+    @classmethod
+    def from_hash_db(cls, hdb, device=0, part=0, n_parts=1):
+        """The hash-defined synthetic DB (rappas_b200.synth_hash.HashDB) generated ON THE DEVICE: the whole DB
+        (n_parts == 1, ready for place()) or one partition of it."""
+        fn = load()
+        desc = _abi.RpDbDesc(int(hdb.alphabet), int(hdb.k), int(hdb.n_nodes), float(hdb.thr_log10), float(hdb.thr_lin), 0, 0, 0)
+        plen = np.ascontiguousarray(hdb.plen, dtype=np.uint16)
+        h = C.c_void_p()
+        check(fn["db_synth_partition"](C.byref(desc), int(hdb.seed), float(hdb.occupancy), _abi.ptr(plen), int(device),
+                                       int(part), int(n_parts), C.byref(h)))
+        out = _abi.RpDbDesc()
+        check(fn["db_describe"](h, C.byref(out)))
+        return cls(h, out)
+
+    def attach_partitions_dist(self, device, group=None):
+        """Peer-memory form: all_gather the CUDA-IPC blobs of the ranks' partitions and map the others'."""
+        import torch
+        import torch.distributed as dist
+        fn = load()
+        world = dist.get_world_size(group)
+        blob = np.zeros(_abi.RP_PART_BLOB_BYTES, np.uint8)
+        check(fn["db_partition_blob"](self._h, _abi.ptr(blob)))
+        mine = torch.from_numpy(blob)
+        if dist.get_backend(group) == "nccl":
+            mine = mine.to(torch.device("cuda", int(device)))
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine, group=group)
+        blobs = np.ascontiguousarray(torch.stack(gathered).cpu().numpy())
+        check(fn["db_attach_partitions"](self._h, _abi.ptr(blobs), world))
+        return self
+
+    @classmethod
     def from_file(cls, path, devices=(0,), partitioned=False):
         fn = load()
         dev = np.ascontiguousarray(devices, dtype=np.int32)
