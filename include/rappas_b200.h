@@ -179,9 +179,10 @@ int  rp_xchg_place(rp_xchg* x, const rp_place_cfg* cfg, int32_t n_local, const u
                    const uint64_t* const* seq_off, const int64_t* n_reads, int32_t* const* out_n_rows,
                    uint16_t* const* out_node, float* const* out_score, double* const* out_lwr,
                    int32_t* const* out_counts, int32_t* const* out_status);
-/* of the last rp_xchg_place: device time from "reads resident" to "rows ready" (max over local ranks), probes sent,
- * posting bytes received */
-int  rp_xchg_stats(const rp_xchg* x, double* device_ms, uint64_t* probes, uint64_t* payload_bytes);
+/* of the last rp_xchg_place: device time from "reads resident" to "rows ready" (max over local ranks), probes sent by
+ * the local ranks, posting bytes they received, and -- as OWNERS -- the probes that hit and the postings they listed */
+int  rp_xchg_stats(const rp_xchg* x, double* device_ms, uint64_t* probes, uint64_t* payload_bytes, uint64_t* hits,
+                   uint64_t* postings);
 void rp_xchg_free(rp_xchg* x);
 
 /* ---- placement of one batch of reads: replaces the per-read body of
@@ -201,6 +202,16 @@ int  rp_place_batch(rp_db* db, const rp_place_cfg* cfg,
                     const uint8_t* seq, const uint64_t* seq_off, int64_t n_reads,
                     int32_t* out_n_rows, uint16_t* out_node, float* out_score, double* out_lwr,
                     int32_t* out_counts, int32_t* out_status);
+
+/* Host memory for rp_place_batch.  The call pipelines H2D / kernel / D2H over chunks of the batch; that needs
+ * page-locked host memory.  Buffers from rp_host_alloc (or registered with rp_host_register: e.g. the address of a
+ * direct ByteBuffer / a MemorySegment) are copied from and to directly.  Any other (pageable) buffer is detected
+ * (cudaPointerGetAttributes) and staged through the library's own pinned ring by the calling thread and a few
+ * helpers -- correct, and overlapped with the GPU, but it costs the host one extra pass over the bytes. */
+int  rp_host_alloc(void** out, uint64_t bytes);
+void rp_host_free(void* p);
+int  rp_host_register(void* p, uint64_t bytes);
+int  rp_host_unregister(void* p);
 
 /* Same work with every buffer already resident on devices[device_index] and the kernels
  * enqueued on `stream` (a cudaStream_t; NULL = default stream).  Asynchronous: returns

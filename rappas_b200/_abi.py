@@ -65,7 +65,8 @@ PROTOTYPES = {
     "xchg_create": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.POINTER(_P)]),
     "xchg_create_local": (C.c_int, [_P, C.c_int32, C.POINTER(_P)]),
     "xchg_place": (C.c_int, [_P, C.POINTER(RpPlaceCfg), C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
-    "xchg_stats": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "xchg_stats": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                         C.POINTER(C.c_uint64)]),
     "xchg_free": (None, [_P]),
     "db_free": (None, [_P]),
     "gap_intervals": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
@@ -76,6 +77,10 @@ PROTOTYPES = {
     "dbbuild_free": (None, [_P]),
     "db_describe": (C.c_int, [_P, C.POINTER(RpDbDesc)]),
     "db_device_bytes": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "host_alloc": (C.c_int, [C.POINTER(_P), C.c_uint64]),
+    "host_free": (None, [_P]),
+    "host_register": (C.c_int, [_P, C.c_uint64]),
+    "host_unregister": (C.c_int, [_P]),
     "place_batch": (C.c_int, [_P, C.POINTER(RpPlaceCfg), _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P]),
     "place_batch_device": (C.c_int, [_P, C.c_int32, C.POINTER(RpPlaceCfg), _P, _P, C.c_int64,
                                      _P, _P, _P, _P, _P, _P, _P]),

@@ -179,6 +179,10 @@ struct StreamCtx {
   uint64_t* d_off = nullptr; size_t cap_reads = 0;
   int32_t* d_n_rows = nullptr; uint16_t* d_node = nullptr; float* d_score = nullptr; double* d_lwr = nullptr;
   int32_t* d_counts = nullptr; int32_t* d_status = nullptr; int cap_K = 0;
+  // pinned host staging for callers whose buffers are ordinary pageable memory (a JVM heap array, a numpy array):
+  // one block for the chunk's inputs, one for its outputs (grown on demand)
+  uint8_t* h_in = nullptr; size_t cap_h_in = 0;
+  uint8_t* h_out = nullptr; size_t cap_h_out = 0;
   float kernel_ms = 0.f;
 };
 

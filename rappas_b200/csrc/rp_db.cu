@@ -305,6 +305,8 @@ static void free_device_ctx(DeviceCtx* dc) {
       cudaFree(s.d_counter); cudaFree(s.d_amb_S); cudaFree(s.d_amb_C);
       cudaFree(s.d_seq); cudaFree(s.d_off); cudaFree(s.d_n_rows); cudaFree(s.d_node); cudaFree(s.d_score);
       cudaFree(s.d_lwr); cudaFree(s.d_counts); cudaFree(s.d_status);
+      if (s.h_in) cudaFreeHost(s.h_in);
+      if (s.h_out) cudaFreeHost(s.h_out);
       if (s.ev_k0) cudaEventDestroy(s.ev_k0);
       if (s.ev_k1) cudaEventDestroy(s.ev_k1);
       if (s.stream) cudaStreamDestroy(s.stream);

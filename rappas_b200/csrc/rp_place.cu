@@ -1402,6 +1402,37 @@ static int ensure_io(StreamCtx* sc, size_t seq_bytes, size_t n_reads, int K, boo
   return RP_OK;
 }
 
+// ---- host memory of the caller: pinned (rp_host_alloc / rp_host_register / cudaHostAlloc) or pageable ----------
+// cudaMemcpyAsync from pageable memory is staged by the driver and blocks the calling thread, which serialises the
+// two-stream pipeline.  A pageable caller buffer is therefore copied through the library's own pinned ring: the
+// calling thread (plus helpers for large pieces) fills the ring for chunk i+1 while the GPU works on chunk i.
+static bool is_pinned(const void* p) {
+  if (!p) return true;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+static void par_memcpy(void* dst, const void* src, size_t n) {
+  constexpr size_t kPiece = 2u << 20;
+  if (n < 2 * kPiece) { memcpy(dst, src, n); return; }
+  const unsigned nt = (unsigned)std::min<size_t>(4, n / kPiece);
+  std::vector<std::thread> th;
+  for (unsigned t = 1; t < nt; t++)
+    th.emplace_back([=] { memcpy((char*)dst + n * t / nt, (const char*)src + n * t / nt, n * (t + 1) / nt - n * t / nt); });
+  memcpy(dst, src, n / nt);
+  for (auto& x : th) x.join();
+}
+static int ensure_pinned(uint8_t** p, size_t* cap, size_t n) {
+  if (n <= *cap) return RP_OK;
+  if (*p) cudaFreeHost(*p);
+  *p = nullptr;
+  *cap = 0;
+  const size_t want = n + n / 8 + 4096;
+  RP_CUDA_TRY(cudaHostAlloc((void**)p, want, cudaHostAllocPortable));
+  *cap = want;
+  return RP_OK;
+}
+
 // Places reads [r0, r1) of the host batch on one device, in double-buffered chunks.
 // Inside the loop a CUDA error must not return at once: the other stream may still be copying into the
 // caller's out_* buffers, so errors break out and both streams are drained (and d_dump freed) first.
@@ -1423,16 +1454,41 @@ static int place_on_device(rp_db* db, DeviceCtx* dc, const rp_place_cfg* cfg, co
   // reads per H2D / kernel / D2H pipeline step (two streams alternate); RP_CHUNK_READS overrides for tuning
   int64_t kChunk = out_dump ? 4096 : (1 << 16);  // tools/sweep_chunk.sh: 32k-128k reads are equivalent, 256k+ exposes the first H2D
   if (const char* e = getenv("RP_CHUNK_READS")) if (!out_dump && atoll(e) > 0) kChunk = atoll(e);
+  const bool stage_in = !is_pinned(seq) || !is_pinned(seq_off);
+  const bool stage_out = !out_dump && (!is_pinned(out_n_rows) || !is_pinned(out_node) || !is_pinned(out_score) ||
+                                       !is_pinned(out_lwr) || !is_pinned(out_status) || !is_pinned(out_counts));
   double ms_total = 0.0;
-  int64_t pending_lo[2] = {-1, -1};
+  int64_t pending_lo[2] = {-1, -1}, pending_n[2] = {0, 0};
+  bool in_flight[2] = {false, false};
   float* d_dump[2] = {nullptr, nullptr};
+  // layout of a chunk's outputs inside the pinned block (every array 16 B aligned)
+  auto out_layout = [&](int64_t n, size_t off[7]) {
+    size_t o = 0;
+    auto put = [&](int i, size_t bytes) { off[i] = o; o += (bytes + 15) & ~(size_t)15; };
+    put(0, n * 4); put(1, n * 4); put(2, (size_t)n * K * 2); put(3, (size_t)n * K * 4); put(4, (size_t)n * K * 8);
+    put(5, out_counts ? n * 16 : 0);
+    off[6] = o;
+  };
   auto finish = [&](int b) -> int {
-    if (pending_lo[b] < 0) return RP_OK;
+    if (!in_flight[b]) return RP_OK;
     StreamCtx* sc = &dc->sc[b];
+    in_flight[b] = false;
     RP_CUDA_TRY(cudaStreamSynchronize(sc->stream));
+    if (pending_lo[b] < 0) return RP_OK;  // the chunk was abandoned half-way (error path): only drained
     float ms = 0.f;
     RP_CUDA_TRY(cudaEventElapsedTime(&ms, sc->ev_k0, sc->ev_k1));
     ms_total += ms;
+    if (stage_out) {  // pinned block -> the caller's arrays
+      const int64_t c0 = pending_lo[b], n = pending_n[b];
+      size_t off[7];
+      out_layout(n, off);
+      par_memcpy(out_n_rows + c0, sc->h_out + off[0], n * 4);
+      par_memcpy(out_status + c0, sc->h_out + off[1], n * 4);
+      par_memcpy(out_node + c0 * K, sc->h_out + off[2], (size_t)n * K * 2);
+      par_memcpy(out_score + c0 * K, sc->h_out + off[3], (size_t)n * K * 4);
+      par_memcpy(out_lwr + c0 * K, sc->h_out + off[4], (size_t)n * K * 8);
+      if (out_counts) par_memcpy(out_counts + c0 * 4, sc->h_out + off[5], n * 16);
+    }
     pending_lo[b] = -1;
     return RP_OK;
   };
@@ -1446,8 +1502,22 @@ static int place_on_device(rp_db* db, DeviceCtx* dc, const rp_place_cfg* cfg, co
     const uint64_t b0 = seq_off[c0], nbytes = seq_off[c1] - b0;
     if ((rc = ensure_io(sc, nbytes, (size_t)n, K, out_counts != nullptr))) break;
     cudaStream_t st = sc->stream;
-    if (nbytes) RP_CUDA_BRK(cudaMemcpyAsync(sc->d_seq, seq + b0, nbytes, cudaMemcpyHostToDevice, st));
-    RP_CUDA_BRK(cudaMemcpyAsync(sc->d_off, seq_off + c0, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    in_flight[b] = true;
+    const uint8_t* src_seq = seq + b0;
+    const uint64_t* src_off = seq_off + c0;
+    if (stage_in) {
+      const size_t off_bytes = (size_t)(n + 1) * sizeof(uint64_t), seq_at = (off_bytes + 63) & ~(size_t)63;
+      if ((rc = ensure_pinned(&sc->h_in, &sc->cap_h_in, seq_at + nbytes))) break;
+      par_memcpy(sc->h_in, src_off, off_bytes);
+      par_memcpy(sc->h_in + seq_at, src_seq, nbytes);
+      src_off = reinterpret_cast<const uint64_t*>(sc->h_in);
+      src_seq = sc->h_in + seq_at;
+    }
+    size_t ooff[7];
+    out_layout(n, ooff);
+    if (stage_out && (rc = ensure_pinned(&sc->h_out, &sc->cap_h_out, ooff[6]))) break;
+    if (nbytes) RP_CUDA_BRK(cudaMemcpyAsync(sc->d_seq, src_seq, nbytes, cudaMemcpyHostToDevice, st));
+    RP_CUDA_BRK(cudaMemcpyAsync(sc->d_off, src_off, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     BatchView bt;
     bt.seq = sc->d_seq; bt.seq_off = sc->d_off; bt.seq_base = b0; bt.n_reads = n;
     bt.n_rows = sc->d_n_rows; bt.node = sc->d_node; bt.score = sc->d_score; bt.lwr = sc->d_lwr;
@@ -1460,17 +1530,19 @@ static int place_on_device(rp_db* db, DeviceCtx* dc, const rp_place_cfg* cfg, co
       bt.dump_scores = d_dump[b];
     }
     if ((rc = launch_place(db, dc, sc, cfg, bt, st, true))) break;
-    RP_CUDA_BRK(cudaMemcpyAsync(out_n_rows + c0, sc->d_n_rows, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    RP_CUDA_BRK(cudaMemcpyAsync(out_status + c0, sc->d_status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    RP_CUDA_BRK(cudaMemcpyAsync(out_node + c0 * K, sc->d_node, n * K * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
-    RP_CUDA_BRK(cudaMemcpyAsync(out_score + c0 * K, sc->d_score, n * K * sizeof(float), cudaMemcpyDeviceToHost, st));
-    RP_CUDA_BRK(cudaMemcpyAsync(out_lwr + c0 * K, sc->d_lwr, n * K * sizeof(double), cudaMemcpyDeviceToHost, st));
+    uint8_t* ho = sc->h_out;
+    RP_CUDA_BRK(cudaMemcpyAsync(stage_out ? (void*)(ho + ooff[0]) : (void*)(out_n_rows + c0), sc->d_n_rows, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    RP_CUDA_BRK(cudaMemcpyAsync(stage_out ? (void*)(ho + ooff[1]) : (void*)(out_status + c0), sc->d_status, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    RP_CUDA_BRK(cudaMemcpyAsync(stage_out ? (void*)(ho + ooff[2]) : (void*)(out_node + c0 * K), sc->d_node, n * K * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+    RP_CUDA_BRK(cudaMemcpyAsync(stage_out ? (void*)(ho + ooff[3]) : (void*)(out_score + c0 * K), sc->d_score, n * K * sizeof(float), cudaMemcpyDeviceToHost, st));
+    RP_CUDA_BRK(cudaMemcpyAsync(stage_out ? (void*)(ho + ooff[4]) : (void*)(out_lwr + c0 * K), sc->d_lwr, n * K * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (out_counts)
-      RP_CUDA_BRK(cudaMemcpyAsync(out_counts + c0 * 4, sc->d_counts, n * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      RP_CUDA_BRK(cudaMemcpyAsync(stage_out ? (void*)(ho + ooff[5]) : (void*)(out_counts + c0 * 4), sc->d_counts, n * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (out_dump)
       RP_CUDA_BRK(cudaMemcpyAsync(out_dump + (size_t)c0 * db->desc.n_nodes, d_dump[b],
                                   (size_t)n * db->desc.n_nodes * sizeof(float), cudaMemcpyDeviceToHost, st));
     pending_lo[b] = c0;
+    pending_n[b] = n;
   }
   for (int i = 0; i < 2; i++) {
     int rc2 = finish(i);
@@ -1523,6 +1595,28 @@ static int place_host(rp_db* db, const rp_place_cfg* cfg, const uint8_t* seq, co
 using namespace rp;
 
 extern "C" {
+
+int rp_host_alloc(void** out, uint64_t bytes) {
+  if (!out) return set_error(RP_E_INVALID, "out is NULL");
+  *out = nullptr;
+  cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_error(e == cudaErrorMemoryAllocation ? RP_E_NOMEM : RP_E_CUDA, "cudaHostAlloc(%llu): %s", (unsigned long long)bytes, cudaGetErrorString(e));
+  }
+  return RP_OK;
+}
+void rp_host_free(void* p) { if (p) cudaFreeHost(p); }
+int rp_host_register(void* p, uint64_t bytes) {
+  if (!p) return set_error(RP_E_INVALID, "p is NULL");
+  RP_CUDA_TRY(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+  return RP_OK;
+}
+int rp_host_unregister(void* p) {
+  if (!p) return set_error(RP_E_INVALID, "p is NULL");
+  RP_CUDA_TRY(cudaHostUnregister(p));
+  return RP_OK;
+}
 
 int rp_place_batch(rp_db* db, const rp_place_cfg* cfg, const uint8_t* seq, const uint64_t* seq_off, int64_t n_reads,
                    int32_t* out_n_rows, uint16_t* out_node, float* out_score, double* out_lwr, int32_t* out_counts,

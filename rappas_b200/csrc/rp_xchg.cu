@@ -241,7 +241,8 @@ __global__ void xk_segtot(const uint32_t* base, const uint32_t* tot, long long n
 // Step 3.  One thread per received key: the owner's table entry, the answer for the home, the 32 B units of the block.
 // answer = found << 31 | qmax << 20 | qmin << 16 | list length  (0 = not in the DB)
 __global__ void __launch_bounds__(256) xk_lookup(const __grid_constant__ DbView db, const uint64_t* keys, size_t n, uint64_t* ometa,
-                                                 uint32_t* answer, uint32_t* units) {
+                                                 uint32_t* answer, uint32_t* units, unsigned long long* stat /*[2]: hits, postings*/) {
+  unsigned long long hits = 0, posts = 0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     uint64_t meta;
     const bool found = table_probe(db, keys[i], meta);
@@ -249,7 +250,13 @@ __global__ void __launch_bounds__(256) xk_lookup(const __grid_constant__ DbView 
     ometa[i] = found ? meta : kEmptyKey;
     answer[i] = found ? (0x80000000u | ((uint32_t)((meta >> kMetaQminShift) & 0xFF) << 16) | len) : 0u;
     units[i] = found ? (len * 6 + 31) >> 5 : 0u;
+    if (found) { hits++; posts += len; }
   }
+  for (int d = 16; d; d >>= 1) {
+    hits += __shfl_down_sync(0xffffffffu, hits, d);
+    posts += __shfl_down_sync(0xffffffffu, posts, d);
+  }
+  if ((threadIdx.x & 31) == 0 && hits) { atomicAdd(stat, hits); atomicAdd(stat + 1, posts); }
 }
 __global__ void xk_answer_units(const uint32_t* answer, size_t n, uint32_t* units) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -391,6 +398,7 @@ struct XRank {
   DBuf<uint64_t> sendkeys, recvkeys, ometa, rmeta;
   DBuf<uint32_t> answer_out, units, uoff, answer_in, aunits, ascan, sums, bnd_vals;
   DBuf<size_t> bnd_idx;
+  DBuf<unsigned long long> stat;
   DBuf<HomeSeg> hsegs;
   DBuf<uint8_t> sendpay[2], recvpay[2];
   // outputs (device)
@@ -419,7 +427,7 @@ struct rp_xchg {
   DBuf<uint64_t> gather_dev;   // NCCL: staging of the small host all-gathers
   int reserve_sms = 0;
   double last_ms = 0.0;
-  uint64_t last_probes = 0, last_payload = 0;
+  uint64_t last_probes = 0, last_payload = 0, last_hits = 0, last_postings = 0;
 };
 
 namespace rp {
@@ -511,7 +519,7 @@ static void free_rank(XRank* R) {
     R->seq.release(); R->off.release(); R->cnt.release(); R->base.release(); R->tot.release(); R->seg.release();
     R->sendkeys.release(); R->recvkeys.release(); R->ometa.release(); R->rmeta.release(); R->answer_out.release();
     R->units.release(); R->uoff.release(); R->answer_in.release(); R->aunits.release(); R->ascan.release(); R->sums.release();
-    R->bnd_vals.release(); R->bnd_idx.release(); R->hsegs.release();
+    R->bnd_vals.release(); R->bnd_idx.release(); R->hsegs.release(); R->stat.release();
     for (int i = 0; i < 2; i++) { R->sendpay[i].release(); R->recvpay[i].release(); }
     R->o_n_rows.release(); R->o_status.release(); R->o_counts.release(); R->o_node.release(); R->o_score.release(); R->o_lwr.release();
     cudaFree(R->sc.d_counter); cudaFree(R->sc.d_amb_S); cudaFree(R->sc.d_amb_C);
@@ -580,8 +588,9 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
     r->n = io[l].n;
     const size_t n = (size_t)r->n, bytes = n ? (size_t)(io[l].seq_off[n] - io[l].seq_off[0]) : 0;
     if ((rc = r->seq.ensure(bytes + 64)) || (rc = r->off.ensure(n + 1)) || (rc = r->cnt.ensure(n * W + 1)) ||
-        (rc = r->base.ensure(n * W + 1)) || (rc = r->tot.ensure(W)))
+        (rc = r->base.ensure(n * W + 1)) || (rc = r->tot.ensure(W)) || (rc = r->stat.ensure(2)))
       return rc;
+    RP_CUDA_TRY(cudaMemsetAsync(r->stat.p, 0, 16, r->sC));
     if (n && io[l].seq_off[0] != 0) return set_error(RP_E_INVALID, "seq_off[0] must be 0");
     if (bytes) RP_CUDA_TRY(cudaMemcpyAsync(r->seq.p, io[l].seq, bytes, cudaMemcpyHostToDevice, r->sC));
     RP_CUDA_TRY(cudaMemcpyAsync(r->off.p, io[l].seq_off, (n + 1) * 8, cudaMemcpyHostToDevice, r->sC));
@@ -696,7 +705,8 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
     view.table_parts = 1;
     view.direct = nullptr;
     if (nr) {
-      xk_lookup<<<grid_for(nr, 256, r->dc->sm_count), 256, 0, r->sC>>>(view, r->recvkeys.p, nr, r->ometa.p, r->answer_out.p, r->units.p);
+      xk_lookup<<<grid_for(nr, 256, r->dc->sm_count), 256, 0, r->sC>>>(view, r->recvkeys.p, nr, r->ometa.p, r->answer_out.p, r->units.p,
+                                                                          r->stat.p);
       g_kernel_launches.fetch_add(1);
       if ((rc = scan_u32(r, r->units.p, nr, r->uoff.p, r->sC))) return rc;
     }
@@ -895,9 +905,14 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
     if (io[l].counts) RP_CUDA_TRY(cudaMemcpyAsync(io[l].counts, r->o_counts.p, n * 16, cudaMemcpyDeviceToHost, r->sC));
   }
   double ms_max = 0;
+  x->last_hits = x->last_postings = 0;
   for (int l = 0; l < L; l++) {
     RP_CUDA_TRY(dev(l));
+    unsigned long long st[2] = {0, 0};
+    RP_CUDA_TRY(cudaMemcpyAsync(st, R(l)->stat.p, 16, cudaMemcpyDeviceToHost, R(l)->sC));
     RP_CUDA_TRY(cudaStreamSynchronize(R(l)->sC));
+    x->last_hits += st[0];
+    x->last_postings += st[1];
     RP_CUDA_TRY(cudaStreamSynchronize(R(l)->sN));
     RP_CUDA_TRY(cudaStreamSynchronize(R(l)->sP));
     float ms = 0;
@@ -994,11 +1009,14 @@ int rp_xchg_place(rp_xchg* x, const rp_place_cfg* cfg, int32_t n_local, const ui
   return xchg_place(x, cfg, io);
 }
 
-int rp_xchg_stats(const rp_xchg* x, double* device_ms, uint64_t* probes, uint64_t* payload_bytes) {
+int rp_xchg_stats(const rp_xchg* x, double* device_ms, uint64_t* probes, uint64_t* payload_bytes, uint64_t* hits,
+                  uint64_t* postings) {
   if (!x) return set_error(RP_E_INVALID, "NULL argument");
   if (device_ms) *device_ms = x->last_ms;
   if (probes) *probes = x->last_probes;
   if (payload_bytes) *payload_bytes = x->last_payload;
+  if (hits) *hits = x->last_hits;
+  if (postings) *postings = x->last_postings;
   return RP_OK;
 }
 

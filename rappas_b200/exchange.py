@@ -79,6 +79,7 @@ class Exchange:
         return outs
 
     def stats(self):
-        ms, pr, pb = C.c_double(), C.c_uint64(), C.c_uint64()
-        check(load()["xchg_stats"](self._h, C.byref(ms), C.byref(pr), C.byref(pb)))
-        return {"device_ms": ms.value, "probes": pr.value, "payload_bytes": pb.value}
+        ms, pr, pb, hi, po = C.c_double(), C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        check(load()["xchg_stats"](self._h, C.byref(ms), C.byref(pr), C.byref(pb), C.byref(hi), C.byref(po)))
+        return {"device_ms": ms.value, "probes": pr.value, "payload_bytes": pb.value, "owner_hits": hi.value,
+                "owner_postings": po.value}
