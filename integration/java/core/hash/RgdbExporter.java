@@ -48,7 +48,13 @@ public final class RgdbExporter {
                                                StandardOpenOption.TRUNCATE_EXISTING)) {
             ByteBuffer h = ByteBuffer.allocate(80).order(ByteOrder.LITTLE_ENDIAN);
             h.put(new byte[]{'R', 'G', 'D', 'B', 0, 0, 0, 1});
-            h.putInt(nucl ? 0 : 1).putInt(s.k).putInt(s.originalTree.getNodeCount());
+            // alphabet: 0 nucleotides, 1 amino acids, 2 amino acids of a DB built with --convertUO (AAStates.java:118-123:
+            // U and O are then states -- C and L -- and queries may contain them; RP_ALPHA_AMINO_UO)
+            int alphabet = nucl ? 0 : 1;
+            if (!nucl) {
+                try { s.states.stateToByte('U'); alphabet = 2; } catch (Exception notConverted) { /* plain AAStates(false) */ }
+            }
+            h.putInt(alphabet).putInt(s.k).putInt(s.originalTree.getNodeCount());
             h.putFloat(s.PPStarThresholdAsLog10).putFloat(s.PPStarThreshold).putInt(0);
             h.putLong(nKeys).putLong(nPost).putLong(offKeys).putLong(offOffsets).putLong(offNodes).putLong(offScores);
             h.flip();
