@@ -137,12 +137,8 @@ def pin_to_gpu_numa_node(local_rank):
     """CPU affinity = the cores of the NUMA node the GPU hangs off, so that the pinned staging buffers are
     first-touched there and the copy threads run there.  Best effort; returns what it did."""
     try:
-        import torch
-        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id if hasattr(torch.cuda.get_device_properties(local_rank), "pci_bus_id") else None
-        if bus is None:
-            out = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
-                                 capture_output=True, text=True).stdout.strip()
-            bus = out
+        bus = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True).stdout.strip()
         bus = bus.lower()
         if len(bus.split(":")[0]) == 8:
             bus = bus[4:]
@@ -289,35 +285,14 @@ def main():
         dist.destroy_process_group()
 
 
-# ------------------------------------------------------------------------------------------- configs 1-4
-def run_replicated(ctx):
+def device_leg(ctx, gdb, rb, cfg):
+    """value leg: reads resident in HBM, rp_place_batch_device on the current stream, CUDA events around `steps`
+    launches (max over ranks), clocks sampled during the timed region.  -> (ms per step, outputs, launches, clocks)"""
     import torch
-    import torch.distributed as dist
     import rappas_b200 as R
-    from rappas_b200 import _abi, synth
-    args, rank, local_rank, world, dev = ctx["args"], ctx["rank"], ctx["local_rank"], ctx["world"], ctx["dev"]
+    args, local_rank, dev = ctx["args"], ctx["local_rank"], ctx["dev"]
     barrier, max_over_ranks = ctx["barrier"], ctx["max_over_ranks"]
-
-    # ---- workload: DB replicated per GPU, reads sharded (each rank draws its own shard) -------------
-    w = synth.workload(args.config)
-    if args.no_ambiguity:
-        w.iupac_rate = w.n_rate = 0.0
-    n_reads, scaling = job_reads(args, w, world)
-    if args.postings_scale != 1.0:
-        w.mean_postings = w.mean_postings * args.postings_scale
-        w.name += "_postings_x%g" % args.postings_scale
-    db = synth.make_db(w.alphabet, w.k, w.n_nodes, w.n_keys, w.mean_postings, seed=42 + w.index, key_mode=w.key_mode)
-    rb = synth.make_reads(db, n_reads, w.read_len, seed=1042 + w.index + 7919 * rank, iupac_rate=w.iupac_rate,
-                          n_rate=w.n_rate)
-    if args.partitioned and world > 1:
-        gdb = R.Database.from_synth_partitioned_dist(db, device=local_rank, replicate_table=args.replicate_table)
-    else:
-        gdb = R.Database.from_synth(db, devices=(local_rank,))
-    cfg = _abi.place_cfg()
-    K = cfg.keep_at_most
-    n = rb.n_reads
-
-    # ---- device-resident leg ("value") -----------------------------------------------------------
+    K, n = cfg.keep_at_most, rb.n_reads
     d_seq = torch.from_numpy(rb.seq).to(dev)
     d_off = torch.from_numpy(rb.seq_off.view(np.int64)).to(dev)
     d_n = torch.empty(n, dtype=torch.int32, device=dev)
@@ -350,12 +325,43 @@ def run_replicated(ctx):
     barrier()
     t_wall1 = time.time()
     launches = R.kernel_launch_count() - launches0
-    ms_total = ev0.elapsed_time(ev1)
-    ms_step = max_over_ranks(ms_total / args.steps)
+    ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
     clocks = sampler.stop(t_wall0, t_wall1)
-    value = world * n / (ms_step / 1e3)
     dev_out = {"n_rows": d_n.cpu().numpy(), "status": d_st.cpu().numpy(), "counts": d_cnt.cpu().numpy(),
                "score": d_score.cpu().numpy()}
+    return ms_step, dev_out, launches, clocks
+
+
+# ------------------------------------------------------------------------------------------- configs 1-4
+def run_replicated(ctx):
+    import torch
+    import torch.distributed as dist
+    import rappas_b200 as R
+    from rappas_b200 import _abi, synth
+    args, rank, local_rank, world, dev = ctx["args"], ctx["rank"], ctx["local_rank"], ctx["world"], ctx["dev"]
+    barrier, max_over_ranks = ctx["barrier"], ctx["max_over_ranks"]
+
+    # ---- workload: DB replicated per GPU, reads sharded (each rank draws its own shard) -------------
+    w = synth.workload(args.config)
+    if args.no_ambiguity:
+        w.iupac_rate = w.n_rate = 0.0
+    n_reads, scaling = job_reads(args, w, world)
+    if args.postings_scale != 1.0:
+        w.mean_postings = w.mean_postings * args.postings_scale
+        w.name += "_postings_x%g" % args.postings_scale
+    db = synth.make_db(w.alphabet, w.k, w.n_nodes, w.n_keys, w.mean_postings, seed=42 + w.index, key_mode=w.key_mode)
+    rb = synth.make_reads(db, n_reads, w.read_len, seed=1042 + w.index + 7919 * rank, iupac_rate=w.iupac_rate,
+                          n_rate=w.n_rate)
+    if args.partitioned and world > 1:
+        gdb = R.Database.from_synth_partitioned_dist(db, device=local_rank, replicate_table=args.replicate_table)
+    else:
+        gdb = R.Database.from_synth(db, devices=(local_rank,))
+    cfg = _abi.place_cfg()
+    K = cfg.keep_at_most
+    n = rb.n_reads
+
+    ms_step, dev_out, launches, clocks = device_leg(ctx, gdb, rb, cfg)
+    value = world * n / (ms_step / 1e3)
 
     # ---- end-to-end leg through the host-buffer C ABI: pinned (rp_host_alloc-style) and pageable callers ----
     e2e = None
@@ -545,6 +551,8 @@ def run_config5(ctx):
     clocks = sampler.stop(t_wall0, t_wall1)
     ms_step = max_over_ranks(float(np.mean(dev_ms)))
     e2e_dt = max_over_ranks(float(np.mean(e2e_s)))
+    if x is None and world == 1:  # one GPU: the usual device-resident leg (the host call sums its overlapping chunks' kernel times)
+        ms_step, _, launches, clocks = device_leg(ctx, part, rb, cfg)
     # ---- parity: a sample of THIS rank's reads against the oracle over the regenerated sub-DB
     import oracle_lib as O
     ns = min(n, 300)

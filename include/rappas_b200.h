@@ -184,6 +184,15 @@ int  rp_xchg_place(rp_xchg* x, const rp_place_cfg* cfg, int32_t n_local, const u
 int  rp_xchg_stats(const rp_xchg* x, double* device_ms, uint64_t* probes, uint64_t* payload_bytes, uint64_t* hits,
                    uint64_t* postings);
 void rp_xchg_free(rp_xchg* x);
+/* The host-side bookkeeping of one rp_xchg_place (pure host code, no GPU: exported so that the N > 1 logic can be
+ * tested on a CPU).  probes[(w * n_sub + j) * world + o] = probes of rank w's sub-batch j owned by o;
+ * units[(o * world + p) * n_sub + j] = 32 B units owner o sends home p for sub-batch j (NULL: keys only).  Outputs for
+ * `rank` (any may be NULL): key_send_off / key_recv_off [world + 1], seg_first [world * n_sub + 1],
+ * home_first [world * n_sub], pay_* [n_sub * world] (32 B units), caps = {send_cap, recv_cap, recv_total}. */
+int  rp_xchg_plan(int32_t world, int32_t n_sub, int32_t rank, int32_t direct_local, const uint64_t* probes,
+                  const uint64_t* units, uint64_t* key_send_off, uint64_t* key_recv_off, uint64_t* seg_first,
+                  uint64_t* home_first, uint64_t* pay_send_off, uint64_t* pay_send_cnt, uint64_t* pay_recv_off,
+                  uint64_t* pay_recv_cnt, uint64_t* caps);
 
 /* ---- placement of one batch of reads: replaces the per-read body of
  * PlacementProcess.processQueries (PlacementProcess.java:645-838) and the LWR / keep-factor

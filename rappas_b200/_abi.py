@@ -68,6 +68,7 @@ PROTOTYPES = {
     "xchg_stats": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
                          C.POINTER(C.c_uint64)]),
     "xchg_free": (None, [_P]),
+    "xchg_plan": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "db_free": (None, [_P]),
     "gap_intervals": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
     "pp_prepare": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, _P, _P]),

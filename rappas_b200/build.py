@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "librappas_b200.so")
 SOURCES = ["rp_db.cu", "rp_place.cu", "rp_dbbuild.cu", "rp_synthdb.cu", "rp_xchg.cu", "rp_ingest.cpp"]
-HEADERS = ["rp_common.h", "rp_device.cuh", "rp_synth.h", "rp_dbbuild_core.h", "rp_dbbuild_merge.h", os.path.join("..", "..", "include", "rappas_b200.h")]
+HEADERS = ["rp_common.h", "rp_device.cuh", "rp_xchg_plan.h", "rp_synth.h", "rp_dbbuild_core.h", "rp_dbbuild_merge.h", os.path.join("..", "..", "include", "rappas_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-O2,-Wall,-fvisibility=hidden", "--expt-relaxed-constexpr",

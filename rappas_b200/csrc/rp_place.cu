@@ -45,7 +45,7 @@
 namespace rp {
 
 constexpr uint32_t kSentinelBits = 0x7FFFFFFFu;  // a NaN no arithmetic here produces
-constexpr int kMaxPairsPerCta = 12;  // producer warps 0..P-1, consumer warps P..2P-1
+constexpr int kMaxPairsPerCta = 11;  // 704 threads: 88 registers per thread (768 threads = 80 registers spilt in the producer)  // producer warps 0..P-1, consumer warps P..2P-1
 #ifndef RP_STAGES
 #define RP_STAGES 2  /* 3 measured slower at equal shared memory (tools/try_stages.sh) */
 #endif
@@ -108,6 +108,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 
 // ------------------------------------------------------------------------------------ helpers
 // (table_probe / block_ptr / ldg_bucket: rp_device.cuh)
+// mask of the lanes below this one: a special register, re-read where it is needed instead of living in a register
+__device__ __forceinline__ uint32_t lanemask_lt() { uint32_t m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+
 __device__ __forceinline__ bool is_sentinel(float s) { return __float_as_uint(s) == kSentinelBits; }
 
 // total order used for selection: higher score first, lower node id on exact ties
@@ -393,6 +396,7 @@ __device__ __forceinline__ int finalize_rows(const CfgView& cfg, const TopList& 
 enum : int { kGrpLast = 1, kGrpBad = 2, kGrpTooLong = 4, kGrpStop = 8, kGrpAmb = 16, kGrpAmbGlobal = 32, kGrpPassEnd = 64 };
 constexpr int kGrpWsizeShift = 8, kGrpTabShift = 16, kGrpPassShift = 24;
 constexpr int kMaxPasses = 16;  // slices are routed by sixteenths of the node range
+constexpr int kMaxAmbWin = 8;   // ambiguous windows per group (their table info travels in pk[0..7] of the stage header)
 struct __align__(16) StageHdr {
   long long r;           // read index in the batch
   const uint8_t* seq;    // character g0 of the read: first window of this group
@@ -641,7 +645,6 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
   const int k = db.k;
   const uint32_t kmask = (k >= 32) ? 0xffffffffu : ((1u << k) - 1u);
   const int stage_bytes = w.stage_bytes;
-  const uint32_t lt_mask = (1u << lane) - 1u;
   // (read indices are 32-bit here: rp_place_batch_device refuses batches of 2^31 reads or more)
   uint32_t rn_raw = 0;  // lane 0: result of the atomicAdd that fetched the read after the next
   if (lane == 0) rn_raw = (uint32_t)atomicAdd(work_counter, 1ull);
@@ -672,7 +675,7 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       if (lane == o) x_mask = m;
     }
     const uint32_t mine = __shfl_sync(0xffffffffu, x_mask, own & 7u), cur = __shfl_sync(0xffffffffu, x_run, own & 7u);
-    return xv.rmeta[own & 7u] + (cur + __popc(mine & lt_mask));
+    return xv.rmeta[own & 7u] + (cur + __popc(mine & lanemask_lt()));
   };
 
   auto cls_of = [&](uint32_t raw, int i) -> uint32_t { return i < len ? lds_u8(cls_tab + raw) : (uint32_t)kClsPad; };
@@ -708,31 +711,67 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
     if (MODE == kXchg) probe_issue<MODE>(db, key, g_plain, io, answer_of(key, g_plain));
     else probe_issue<MODE>(db, key, g_plain, io);
   };
-  // The alternatives of the ambiguous window g0 (class bytes in cA): lane t < W_size probes alternative t,
-  // in which position o_m takes A_m[t mod |A_m|]  (AmbigSequenceKnife.java:249-256).  Returns W_size.
-  auto probe_alternatives = [&](bool& found, uint64_t& meta) -> int {
-    const uint32_t wbits = __ballot_sync(0xffffffffu, (cA & 0xC0) == kClsAmb) & kmask, rest = wbits & (wbits - 1);
-    const int o1 = __ffs(wbits) - 1, o2 = rest ? __ffs(rest) - 1 : o1;
-    const int id1 = __shfl_sync(0xffffffffu, cA, o1) & 0x3F, id2 = __shfl_sync(0xffffffffu, cA, o2) & 0x3F;
-    const int n1 = c_alpha.alt_n[id1], n2 = rest ? c_alpha.alt_n[id2] : 1;
-    const int wsize = n1 * n2;  // <= 20 (amino) / 16 (nucl, 2 ambiguities)
-    const uint32_t st1 = c_alpha.alt_states[id1][lane % n1], st2 = c_alpha.alt_states[id2][lane % n2];
+  // The ambiguous windows at g0 (class bytes in cA / cB).  An ambiguous character makes k CONSECUTIVE windows
+  // ambiguous, so they come in runs; a group takes up to kMaxAmbWin of them as long as their alternatives fit the
+  // 32 lanes: slot j = alternative t of window w (windows in order, a window's alternatives in order), in which
+  // position o_m takes A_m[t mod |A_m|]  (AmbigSequenceKnife.java:249-256).  (Round 1 made every ambiguous window a
+  // group of its own: a 775 bp read with five ambiguous characters was ~100 groups instead of ~25, and the
+  // per-group cost made such reads 3.6x slower.)  Returns the number of candidate windows; lane w < that keeps the
+  // window's W_size in aw_size and the end of its slot range in aw_end; aw_win = this slot's window (or -1).
+  auto probe_alternatives = [&](bool& found, uint64_t& meta, int& aw_size, int& aw_end, int& aw_win) -> int {
+    const uint32_t a0 = __ballot_sync(0xffffffffu, (cA & 0xC0) == kClsAmb), a1 = __ballot_sync(0xffffffffu, (cB & 0xC0) == kClsAmb);
+    // window `lane`: its ambiguous offsets and W_size
+    const uint32_t wbits = __funnelshift_r(a0, a1, lane) & kmask, rest = wbits & (wbits - 1);
+    const int na = __popc(wbits);
+    const bool treat = lane < min(32, Ql - g0) && na > 0 && na <= db.max_amb;
+    const int run = min(__ffs(~__ballot_sync(0xffffffffu, treat)) - 1, kMaxAmbWin);  // >= 1: window g0 is one
+    const int o1w = wbits ? __ffs(wbits) - 1 : 0, o2w = rest ? __ffs(rest) - 1 : o1w;
+    const int q1 = lane + o1w, q2 = lane + o2w;
+    const uint32_t c1a = __shfl_sync(0xffffffffu, cA, q1 & 31), c1b = __shfl_sync(0xffffffffu, cB, q1 & 31);
+    const uint32_t c2a = __shfl_sync(0xffffffffu, cA, q2 & 31), c2b = __shfl_sync(0xffffffffu, cB, q2 & 31);
+    const int id1w = (q1 < 32 ? c1a : c1b) & 0x3F, id2w = (q2 < 32 ? c2a : c2b) & 0x3F;
+    const int n1w = lane < run ? c_alpha.alt_n[id1w & (kMaxAltSets - 1)] : 1, n2w = (lane < run && rest) ? c_alpha.alt_n[id2w & (kMaxAltSets - 1)] : 1;
+    aw_size = lane < run ? n1w * n2w : 0;  // <= 20 (amino) / 16 (nucl, 2 ambiguities)
+    aw_end = aw_size;
+#pragma unroll
+    for (int d = 1; d < kMaxAmbWin; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, aw_end, d);
+      if (lane >= d) aw_end += t;
+    }
+    const int ncand = __popc(__ballot_sync(0xffffffffu, lane < run && aw_end <= 32));  // a prefix of the run; >= 1
+    // slot -> (window, alternative) and the window's description
+    int my_t = 0, o1 = 0, o2 = 0, id1 = 0, id2 = 0, n1 = 1, n2 = 1;
+    bool two = false;
+    aw_win = -1;
+    for (int w = 0; w < ncand; w++) {
+      const int end = __shfl_sync(0xffffffffu, aw_end, w), sz = __shfl_sync(0xffffffffu, aw_size, w);
+      const int wo1 = __shfl_sync(0xffffffffu, o1w, w), wo2 = __shfl_sync(0xffffffffu, o2w, w);
+      const int wi1 = __shfl_sync(0xffffffffu, id1w, w), wi2 = __shfl_sync(0xffffffffu, id2w, w);
+      const int wn1 = __shfl_sync(0xffffffffu, n1w, w), wn2 = __shfl_sync(0xffffffffu, n2w, w);
+      if (lane >= end - sz && lane < end) {
+        aw_win = w; my_t = lane - (end - sz);
+        o1 = wo1; o2 = wo2; id1 = wi1; id2 = wi2; n1 = wn1; n2 = wn2; two = wo2 != wo1;
+      }
+    }
+    const bool active = aw_win >= 0;
+    const int sh = active ? aw_win : 0;
+    const uint32_t st1 = c_alpha.alt_states[id1 & (kMaxAltSets - 1)][my_t % n1], st2 = c_alpha.alt_states[id2 & (kMaxAltSets - 1)][my_t % n2];
     uint64_t key = 0;
     for (int p = 0; p < db.bits; p++) {
-      uint64_t plane = __ballot_sync(0xffffffffu, (cA >> p) & 1u) & kmask & ~((1u << o1) | (1u << o2));
-      if (rest) plane |= (uint64_t)((st2 >> p) & 1u) << o2;
+      const uint32_t b0 = __ballot_sync(0xffffffffu, (cA >> p) & 1u), b1 = __ballot_sync(0xffffffffu, (cB >> p) & 1u);
+      uint64_t plane = __funnelshift_r(b0, b1, sh) & kmask & ~((1u << o1) | (1u << o2));
+      if (two) plane |= (uint64_t)((st2 >> p) & 1u) << o2;
       plane |= (uint64_t)((st1 >> p) & 1u) << o1;
       key |= plane << (p * k);
     }
-    if (MODE == kXchg) {  // the alternatives' answers, in alternative order; all of them are consumed
-      const uint64_t* a = answer_of(key, lane < wsize);
-      meta = lane < wsize ? __ldg(reinterpret_cast<const unsigned long long*>(a)) : kEmptyKey;
+    if (MODE == kXchg) {  // the alternatives' answers, in window and alternative order (x_run moves once the group knows how many windows it takes)
+      const uint64_t* a = answer_of(key, active);
+      meta = active ? __ldg(reinterpret_cast<const unsigned long long*>(a)) : kEmptyKey;
       found = meta != kEmptyKey;
-      if (lane < xv.n_parts) x_run += __popc(x_mask);
     } else {
-      found = lane < wsize && table_probe(db, key, meta);
+      found = active && table_probe(db, key, meta);
     }
-    return wsize;
+    return ncand;
   };
   // The NEXT read of the pair: its index comes from the atomic issued one read earlier and its two
   // offsets are requested when the current read starts, so a read start waits for its characters only.
@@ -812,6 +851,8 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
     uint64_t meta = 0;
     uint32_t n_post = 0, bytes = 0, my_chunks = 0, incl_chunks = 0, off = 0, incl = 0;
     int cons = 0, last = 0;
+    // group of ambiguous windows: lane w keeps window w's info word for the consumer
+    uint32_t amb_info = 0;
     bool more = false;  // another group of this pass follows (its probe is issued below)
     if (RP_UNLIKELY(g_bad)) {
       // an unsupported character aborts the reference whatever the length (AmbigSequenceKnife.java:124-128)
@@ -820,8 +861,8 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       flags |= kGrpLast;
     } else {
       bool found;
-      int wsize = 0;
-      if (RP_UNLIKELY(g_nv == 0)) wsize = probe_alternatives(found, meta);
+      int ncand = 0, aw_size = 0, aw_end = 0, aw_win = -1;
+      if (RP_UNLIKELY(g_nv == 0)) ncand = probe_alternatives(found, meta, aw_size, aw_end, aw_win);
       else found = probe_resolve<MODE>(io, meta);
       // node-range pass: only the windows whose list can touch this pass's slice are staged
       bool routed = found;
@@ -837,7 +878,9 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       const uint32_t sb = (routed && !giant) ? bytes : 0u;
       // one scan for both prefix sums: bytes in 32 B units (<= 2^15 over the warp) above the chunk count (< 2^13)
       my_chunks = sb ? (n_post + 31) >> 5 : 0u;
-      incl = (sb >> 5 << 13) | my_chunks;
+      // (ambiguous windows: every alternative's chunks start at a step of their own -- an odd count is padded with an
+      // idle B slot -- so that a window's steps are a contiguous range the consumer can treat by itself)
+      incl = (sb >> 5 << 13) | (RP_UNLIKELY(ncand != 0) ? (my_chunks + 1u) & ~1u : my_chunks);
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
@@ -846,22 +889,50 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       const uint32_t incl_bytes = incl >> 13 << 5;
       incl_chunks = incl & 0x1FFFu;
       const uint32_t nofit = __ballot_sync(0xffffffffu, incl_bytes > (uint32_t)stage_bytes);
-      if (RP_UNLIKELY(wsize != 0)) {
-        // all the alternatives found, plus a table of >= as many entries as they have postings, in one
-        // stage -- or nothing is staged and the consumer reads them from global memory
-        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-        const uint32_t tot_bytes = tot >> 13 << 5, tot_chunks = tot & 0x1FFFu;
-        const uint32_t foundm = __ballot_sync(0xffffffffu, routed), giantm = __ballot_sync(0xffffffffu, routed && giant);
-        const uint32_t room = (tot_bytes <= (uint32_t)stage_bytes ? (uint32_t)stage_bytes - tot_bytes : 0u) / 8u;
-        uint32_t lg = room ? 31 - __clz(room) : 0;                         // the largest table that fits ...
-        if (tot_chunks) lg = min(lg, 32u - __clz(64u * tot_chunks - 1u));  // ... up to twice the postings
-        const bool staged = !nofit && !giantm && (1u << lg) >= 32u * tot_chunks && lg >= 5;
-        flags |= (staged ? kGrpAmb : kGrpAmbGlobal) | (wsize << kGrpWsizeShift) | (lg << kGrpTabShift);
-        if (!found) meta = kEmptyKey;  // (the consumer's global-memory walk takes the alternatives' entries as they are)
-        hitm = stagedm = staged ? foundm : 0u;
-        cons = 1;
-        last = 31;
-        n_amb += 1;  // (matches inside the helpers are not counted: queryKmerMatchingDB is passed by value, :741-743)
+      if (RP_UNLIKELY(ncand != 0)) {
+        // Ambiguous windows: take them in order while the blocks of all their alternatives, plus ONE table of at least
+        // as many entries as the largest window has postings (the consumer treats the windows one after the
+        // other), fit the stage.  If not even the first fits, nothing is staged and the consumer walks that
+        // window's alternatives in global memory.
+        const uint32_t giantm = __ballot_sync(0xffffffffu, routed && giant), routedm = __ballot_sync(0xffffffffu, routed);
+        int taken = 0;
+        uint32_t c_prev = 0, b_taken = 0, min_lg_max = 5, step0_w = 0, nst_w = 0, want_lg_w = 5;
+        for (int w = 0; w < ncand; w++) {
+          const int end = __shfl_sync(0xffffffffu, aw_end, w), sz = __shfl_sync(0xffffffffu, aw_size, w);
+          const uint32_t lanes_w = (end >= 32 ? 0xffffffffu : ((1u << end) - 1u)) & ~((1u << (end - sz)) - 1u);
+          const uint32_t tot = __shfl_sync(0xffffffffu, incl, end - 1);
+          const uint32_t b_end = tot >> 13 << 5, chunks_w = (tot & 0x1FFFu) - c_prev;
+          const uint32_t min_lg = chunks_w ? max(5u, 32u - __clz(32u * chunks_w - 1u)) : 5u;  // entries >= postings (rounded to chunks)
+          const uint32_t room = b_end <= (uint32_t)stage_bytes ? ((uint32_t)stage_bytes - b_end) / 8u : 0u;
+          const uint32_t fit_lg = room ? 31 - __clz(room) : 0;
+          if ((giantm & lanes_w) || b_end > (uint32_t)stage_bytes || max(min_lg_max, min_lg) > fit_lg) break;
+          min_lg_max = max(min_lg_max, min_lg);
+          if (lane == w) {  // (chunk counts are even here: steps = chunks / 2)
+            step0_w = c_prev >> 1; nst_w = chunks_w >> 1;
+            want_lg_w = chunks_w ? 32u - __clz(64u * chunks_w - 1u) : 5u;
+          }
+          c_prev = tot & 0x1FFFu;
+          b_taken = b_end;
+          taken++;
+        }
+        cons = max(taken, 1);
+        const int end_taken = __shfl_sync(0xffffffffu, aw_end, cons - 1);
+        const uint32_t lanes_taken = end_taken >= 32 ? 0xffffffffu : ((1u << end_taken) - 1u);
+        if (MODE == kXchg && lane < xv.n_parts) x_run += __popc(x_mask & lanes_taken);  // the answers of the windows taken
+        n_amb += cons;  // (matches inside the helpers are not counted: queryKmerMatchingDB is passed by value, :741-743)
+        if (taken) {
+          const uint32_t room = ((uint32_t)stage_bytes - b_taken) / 8u, fit_lg = 31 - __clz(room);
+          flags |= kGrpAmb | (taken << kGrpWsizeShift);
+          hitm = stagedm = routedm & lanes_taken;
+          last = end_taken - 1;
+          // per window, for the consumer: first step, steps, W_size, log2 of its table (up to twice the postings)
+          if (lane < taken) amb_info = step0_w | (nst_w << 11) | ((uint32_t)aw_size << 20) | (min(want_lg_w, fit_lg) << 26);
+        } else {
+          flags |= kGrpAmbGlobal | (__shfl_sync(0xffffffffu, aw_size, 0) << kGrpWsizeShift);
+          hitm = stagedm = 0u;
+          last = 31;
+          if (!found || aw_win != 0) meta = kEmptyKey;  // (the consumer's global-memory walk takes window g0's alternatives as they are)
+        }
       } else {
         cons = nofit ? __ffs(nofit) - 1 : 32;  // >= 1: lane 0 alone always fits
         cons = min(cons, g_nv);
@@ -911,9 +982,10 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       // c & 1 of step c >> 1, unless the pair (c - 1, c) straddles two windows whose node ranges intersect: then
       // the pair is SPLIT into two steps with idle B slots, and every later step moves down by one.  A split is
       // owned by the lane of the odd chunk (the first chunk of its window).
-      const uint32_t c0 = incl_chunks_c - my_chunks_c;
+      const bool ambg = flags & kGrpAmb;  // (its scan counted every alternative's chunks rounded up to even)
+      const uint32_t c0 = incl_chunks_c - (ambg ? (my_chunks_c + 1u) & ~1u : my_chunks_c);
       const uint32_t q8 = (uint32_t)(meta_c >> kMetaQminShift) & 0xFFu;
-      const uint32_t prevm = stagedm & lt_mask;
+      const uint32_t prevm = stagedm & lanemask_lt();
       const uint32_t pq = __shfl_sync(0xffffffffu, q8, prevm ? 31 - __clz(prevm) : 0);
       const bool disjoint = (q8 >> 4) < (pq & 15u) || (pq >> 4) < (q8 & 15u);
 #ifdef RP_NOPAIR  /* bisect only: never pair the chunks of two windows */
@@ -922,7 +994,7 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       const bool split = bytes_c && (c0 & 1u) && !disjoint && !(flags & kGrpAmb);
 #endif
       const uint32_t splitm = __ballot_sync(0xffffffffu, split);
-      const uint32_t sbef = __popc(splitm & lt_mask) + (split ? 1u : 0u);
+      const uint32_t sbef = __popc(splitm & lanemask_lt()) + (split ? 1u : 0u);
       n_steps = (int)(((n_chunks + 1) >> 1) + __popc(splitm));
       const uint2 idle = make_uint2(stage0, 0u);
       if (bytes_c) {
@@ -942,7 +1014,13 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       }
       if (lane < 6)  // idle steps behind the list: the consumer works in rounds of 2 steps and looks 4 ahead
         asm volatile("st.shared.v4.u32 [%0], {%1,%2,%1,%2};" ::"r"(dl0 + 16 * (n_steps + lane)), "r"(stage0), "r"(0u) : "memory");
-      if (lane == 6 && (n_chunks & 1u)) sts_u64(dl0 + 16 * (n_steps - 1) + 8, idle);  // the last chunk has no partner
+      if (!ambg && lane == 6 && (n_chunks & 1u)) sts_u64(dl0 + 16 * (n_steps - 1) + 8, idle);  // the last chunk has no partner
+      if (ambg) {
+        // an alternative with an odd number of chunks: its last step has no B (my_chunks_c is the real count, the scan
+        // counted the padded one)
+        if (bytes_c && (my_chunks_c & 1u)) sts_u64(dl0 + 16 * ((incl_chunks_c - 1u) >> 1) + 8, idle);
+        if (lane < kMaxAmbWin) sts_u32(hdr + 64 + 4 * lane, amb_info);
+      }
     }
     if (lane == 0) {
       StageHdr h;
@@ -1006,12 +1084,18 @@ __device__ __forceinline__ void consumer(const AlphabetTables& c_alpha, const Db
       if (n_steps) accumulate_chunks<SLICED>(S, my_list, n_steps, QT0, db.T, lane, lo, width);
     } else if (!bad) {
       if (g.flags & kGrpAmb) {
-        // one ambiguous window, its alternatives staged (the list holds their chunks in alternative order: slot A
-        // then slot B of every step); the S_amb / C_amb table follows the blocks
-        const int tab_log2 = (g.flags >> kGrpTabShift) & 0xF;
-        if (n_steps)
-          ambiguous_staged(db, cfg, Sv, my_list, 2 * n_steps, w.stage + slot * w.stage_bytes + g.staged_bytes, tab_log2,
-                           (g.flags >> kGrpWsizeShift) & 0x1F, g.QT, lane, lo, width);
+        // up to kMaxAmbWin ambiguous windows, in order; the alternatives of each are staged (its steps hold their
+        // chunks in alternative order: slot A then slot B), and the S_amb / C_amb table of the window being treated
+        // follows the blocks
+        const int n_win = (g.flags >> kGrpWsizeShift) & 0x1F;
+        const uint32_t* info = reinterpret_cast<const uint32_t*>(w.meta + slot * kStageMetaBytes + 64);
+        for (int wi = 0; wi < n_win; wi++) {
+          const uint32_t iw = info[wi];
+          const int nst = (iw >> 11) & 0x1FF;
+          if (nst)
+            ambiguous_staged(db, cfg, Sv, my_list + 16 * (iw & 0x7FFu), 2 * nst, w.stage + slot * w.stage_bytes + g.staged_bytes,
+                             (iw >> 26) & 0xF, (iw >> 20) & 0x3F, g.QT, lane, lo, width);
+        }
       } else if (g.flags & kGrpAmbGlobal) {
         // one ambiguous window whose alternatives did not fit a stage
         ambiguous_window(db, cfg, Sv, reinterpret_cast<const uint64_t*>(w.meta + slot * kStageMetaBytes + 192),
@@ -1082,7 +1166,7 @@ constexpr int kMaxThreads = kMaxPairsPerCta * 64;
 constexpr int kWantPairs = 8;
 constexpr int max_threads_for(bool sliced) { return sliced ? kWantPairs * 64 : kMaxThreads; }
 template <bool SLICED, int MODE>
-__global__ void __launch_bounds__(max_threads_for(SLICED), 1)
+__global__ void __maxnreg__(SLICED ? 128 : 88)
 place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_constant__ DbView db,
              const __grid_constant__ CfgView cfg, const __grid_constant__ BatchView bt,
              const __grid_constant__ XchgView xv, unsigned long long* work_counter, float* amb_S, int* amb_C, int n_pad, int per_pair_bytes,

@@ -36,6 +36,7 @@
 
 #include "rp_common.h"
 #include "rp_device.cuh"
+#include "rp_xchg_plan.h"
 
 namespace rp {
 
@@ -411,8 +412,8 @@ struct XRank {
   long long n = 0, B = 1;
   int J = 0;
   std::vector<uint32_t> h_tot, h_seg;          // [P], [J][P]
-  std::vector<uint64_t> sendcnt, recvcnt;      // keys per peer
-  std::vector<uint64_t> koff, roff;            // start of peer p's segment in sendkeys / recvkeys
+  XKeyPlan kp;                                 // keys per peer, segment starts (rp_xchg_plan.h)
+  XPayPlan pp;                                 // posting blocks per sub-batch and peer
 };
 
 }  // namespace rp
@@ -659,11 +660,8 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
     XRank* r = R(l);
     RP_CUDA_TRY(dev(l));
     const int me = r->rank;
-    r->sendcnt.assign(W, 0); r->recvcnt.assign(W, 0); r->koff.assign(W + 1, 0); r->roff.assign(W + 1, 0);
-    for (int p = 0; p < W; p++)
-      for (int j = 0; j < J; j++) { r->sendcnt[p] += Sat(me, j, p); r->recvcnt[p] += Sat(p, j, me); }
-    for (int p = 0; p < W; p++) { r->koff[p + 1] = r->koff[p] + r->sendcnt[p]; r->roff[p + 1] = r->roff[p] + r->recvcnt[p]; }
-    const size_t ns = r->koff[W], nr = r->roff[W];
+    r->kp = plan_keys(W, J, me, S.data());
+    const size_t ns = r->kp.send_off[W], nr = r->kp.recv_off[W];
     probes_total += ns;
     if ((rc = r->sendkeys.ensure(ns + 1)) || (rc = r->recvkeys.ensure(nr + 1)) || (rc = r->ometa.ensure(nr + 1)) ||
         (rc = r->answer_out.ensure(nr + 1)) || (rc = r->units.ensure(nr + 1)) || (rc = r->uoff.ensure(nr + 2)) ||
@@ -677,15 +675,15 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
       a.k = r->db->desc.k; a.bits = alphabet_bits(r->db->desc.alphabet);
       a.max_amb = max_ambig_per_mer(r->db->desc.alphabet, r->db->desc.k); a.treat_amb = cfg->treat_amb; a.n_parts = W;
       a.base = r->base.p; a.keys = r->sendkeys.p;
-      for (int p = 0; p < W; p++) a.koff[p] = r->koff[p];
+      for (int p = 0; p < W; p++) a.koff[p] = r->kp.send_off[p];
       xk_enum<true><<<grid_for((size_t)r->n * 32, 256, r->dc->sm_count), 256, 0, r->sC>>>(r->db->alpha, a);
       g_kernel_launches.fetch_add(1);
       RP_CUDA_TRY(cudaGetLastError());
     }
     a2a.send[l] = (const uint8_t*)r->sendkeys.p; a2a.recv[l] = (uint8_t*)r->recvkeys.p;
     for (int p = 0; p < W; p++) {
-      a2a.soff[l][p] = r->koff[p] * 8; a2a.scnt[l][p] = r->sendcnt[p] * 8;
-      a2a.roff[l][p] = r->roff[p] * 8; a2a.rcnt[l][p] = r->recvcnt[p] * 8;
+      a2a.soff[l][p] = r->kp.send_off[p] * 8; a2a.scnt[l][p] = r->kp.send_cnt[p] * 8;
+      a2a.roff[l][p] = r->kp.recv_off[p] * 8; a2a.rcnt[l][p] = r->kp.recv_cnt[p] * 8;
     }
   }
   if (x->local) for (int l = 0; l < L; l++) { RP_CUDA_TRY(dev(l)); RP_CUDA_TRY(cudaStreamSynchronize(R(l)->sC)); }  // senders' keys are written
@@ -697,7 +695,7 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
     XRank* r = R(l);
     RP_CUDA_TRY(dev(l));
     const int me = r->rank;
-    const size_t nr = r->roff[W];
+    const size_t nr = r->kp.recv_off[W];
     DbView view = make_db_view(r->db, r->dc);
     view.table[0] = r->db->parts[me].d_table;
     view.bucket_shift[0] = 32;
@@ -710,12 +708,7 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
       g_kernel_launches.fetch_add(1);
       if ((rc = scan_u32(r, r->units.p, nr, r->uoff.p, r->sC))) return rc;
     }
-    bnd[l].clear();
-    for (int p = 0; p < W; p++) {
-      size_t i = r->roff[p];
-      for (int j = 0; j < J; j++) { bnd[l].push_back(i); i += Sat(p, j, me); }
-    }
-    bnd[l].push_back(nr);
+    bnd[l].assign(r->kp.seg_first.begin(), r->kp.seg_first.end());
     const int nb = (int)bnd[l].size();
     if ((rc = r->bnd_idx.ensure(nb)) || (rc = r->bnd_vals.ensure(nb))) return rc;
     RP_CUDA_TRY(cudaMemcpyAsync(r->bnd_idx.p, bnd[l].data(), nb * sizeof(size_t), cudaMemcpyHostToDevice, r->sC));
@@ -728,7 +721,7 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
   for (int l = 0; l < L; l++) {
     XRank* r = R(l);
     RP_CUDA_TRY(dev(l));
-    const size_t nr = r->roff[W];
+    const size_t nr = r->kp.recv_off[W];
     bvals[l].assign(bnd[l].size(), 0);
     RP_CUDA_TRY(cudaMemcpyAsync(bvals[l].data(), r->bnd_vals.p, bvals[l].size() * 4, cudaMemcpyDeviceToHost, r->sC));
     if (nr) {
@@ -753,54 +746,40 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
     XRank* r = R(l);
     a2a.send[l] = (const uint8_t*)r->answer_out.p; a2a.recv[l] = (uint8_t*)r->answer_in.p;
     for (int p = 0; p < W; p++) {
-      a2a.soff[l][p] = r->roff[p] * 4; a2a.scnt[l][p] = r->recvcnt[p] * 4;
-      a2a.roff[l][p] = r->koff[p] * 4; a2a.rcnt[l][p] = r->sendcnt[p] * 4;
+      a2a.soff[l][p] = r->kp.recv_off[p] * 4; a2a.scnt[l][p] = r->kp.recv_cnt[p] * 4;
+      a2a.roff[l][p] = r->kp.send_off[p] * 4; a2a.rcnt[l][p] = r->kp.send_cnt[p] * 4;
     }
   }
   if ((rc = alltoallv(x, a2a, sCs))) return rc;
   // ---- home: where every block will land (receive buffer of its sub-batch), rmeta
   uint64_t payload_total = 0;
-  std::vector<std::vector<uint64_t>> poff(L);  // [j][o] units
-  std::vector<uint64_t> cap_units(L, 0), send_units(L, 0);
   for (int l = 0; l < L; l++) {
     XRank* r = R(l);
     RP_CUDA_TRY(dev(l));
     const int me = r->rank;
-    const size_t ns = r->koff[W];
-    poff[l].assign((size_t)J * W, 0);
-    for (int j = 0; j < J; j++) {
-      uint64_t run = 0, out = 0;
-      for (int o = 0; o < W; o++) {
-        poff[l][(size_t)j * W + o] = run;
-        if (!(direct_local && o == me)) run += Uat(o, me, j);
-        if (!(direct_local && o == me)) out += Uat(me, o, j);
-      }
-      cap_units[l] = std::max(cap_units[l], run);
-      send_units[l] = std::max(send_units[l], out);
-      payload_total += run * kBlockAlign;
-    }
+    const size_t ns = r->kp.send_off[W];
+    r->pp = plan_payload(W, J, me, direct_local, U.data());
+    payload_total += r->pp.recv_total * kBlockAlign;
     for (int b = 0; b < 2; b++)
-      if ((rc = r->recvpay[b].ensure(cap_units[l] * kBlockAlign + 512)) || (rc = r->sendpay[b].ensure(send_units[l] * kBlockAlign + 512))) return rc;
+      if ((rc = r->recvpay[b].ensure(r->pp.recv_cap * kBlockAlign + 512)) || (rc = r->sendpay[b].ensure(r->pp.send_cap * kBlockAlign + 512))) return rc;
     if (ns) {
       xk_answer_units<<<grid_for(ns, 256, r->dc->sm_count), 256, 0, r->sC>>>(r->answer_in.p, ns, r->aunits.p);
       g_kernel_launches.fetch_add(1);
       if ((rc = scan_u32(r, r->aunits.p, ns, r->ascan.p, r->sC))) return rc;
     }
     std::vector<HomeSeg> hs((size_t)W * J);
-    for (int o = 0; o < W; o++) {
-      size_t q = 0;
-      for (int j = 0; j < J; j++) { hs[(size_t)o * J + j] = HomeSeg{q, poff[l][(size_t)j * W + o]}; q += Sat(me, j, o); }
-    }
+    for (int o = 0; o < W; o++)
+      for (int j = 0; j < J; j++) hs[(size_t)o * J + j] = HomeSeg{(size_t)r->kp.home_first[(size_t)o * J + j], r->pp.recv_off[(size_t)j * W + o]};
     if ((rc = r->hsegs.ensure(hs.size()))) return rc;
     RP_CUDA_TRY(cudaMemcpyAsync(r->hsegs.p, hs.data(), hs.size() * sizeof(HomeSeg), cudaMemcpyHostToDevice, r->sC));
     RP_CUDA_TRY(cudaStreamSynchronize(r->sC));  // hs is a stack vector
     for (int o = 0; o < W; o++) {
-      const size_t cntq = r->sendcnt[o];
+      const size_t cntq = r->kp.send_cnt[o];
       if (!cntq) continue;
       if (direct_local && o == me)
-        xk_copy_u64<<<grid_for(cntq, 256, r->dc->sm_count), 256, 0, r->sC>>>(r->ometa.p + r->roff[me], cntq, r->rmeta.p + r->koff[o]);
+        xk_copy_u64<<<grid_for(cntq, 256, r->dc->sm_count), 256, 0, r->sC>>>(r->ometa.p + r->kp.recv_off[me], cntq, r->rmeta.p + r->kp.send_off[o]);
       else
-        xk_home_meta<<<grid_for(cntq, 256, r->dc->sm_count), 256, 0, r->sC>>>(r->answer_in.p, r->ascan.p, r->koff[o], cntq, o,
+        xk_home_meta<<<grid_for(cntq, 256, r->dc->sm_count), 256, 0, r->sC>>>(r->answer_in.p, r->ascan.p, r->kp.send_off[o], cntq, o,
                                                                                r->hsegs.p + (size_t)o * J, J, r->rmeta.p);
       g_kernel_launches.fetch_add(1);
     }
@@ -823,16 +802,12 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
         for (int l2 = 0; l2 < L; l2++) RP_CUDA_TRY(cudaStreamWaitEvent(r->sP, R(l2)->evA2A[b], 0));
       PackArgs pa;
       memset(&pa, 0, sizeof pa);
-      uint64_t run = 0;
       size_t most = 0;
       for (int p = 0; p < W; p++) {
-        if (direct_local && p == me) continue;
+        if (!r->pp.send_cnt[(size_t)j * W + p]) continue;
         const size_t i0 = bnd[l][(size_t)p * J + j], i1 = bnd[l][(size_t)p * J + j + 1];
-        if (i1 > i0) {
-          pa.seg[pa.n_seg++] = PackSeg{i0, i1, r->sendpay[b].p, run};
-          most = std::max(most, i1 - i0);
-        }
-        run += Uat(me, p, j);
+        pa.seg[pa.n_seg++] = PackSeg{i0, i1, r->sendpay[b].p, r->pp.send_off[(size_t)j * W + p]};
+        most = std::max(most, i1 - i0);
       }
       if (pa.n_seg) {
         dim3 grid(grid_for(most, 8, r->dc->sm_count), pa.n_seg);
@@ -850,12 +825,10 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
       const int me = r->rank;
       if (j >= 2) RP_CUDA_TRY(cudaStreamWaitEvent(r->sN, r->evAcc[b], 0));  // recvpay[b] has been consumed
       a2a.send[l] = r->sendpay[b].p; a2a.recv[l] = r->recvpay[b].p;
-      uint64_t run = 0;
       for (int p = 0; p < W; p++) {
-        if (direct_local && p == me) continue;
-        a2a.soff[l][p] = run * kBlockAlign; a2a.scnt[l][p] = Uat(me, p, j) * kBlockAlign;
-        run += Uat(me, p, j);
-        a2a.roff[l][p] = poff[l][(size_t)j * W + p] * kBlockAlign; a2a.rcnt[l][p] = Uat(p, me, j) * kBlockAlign;
+        const size_t i = (size_t)j * W + p;
+        a2a.soff[l][p] = r->pp.send_off[i] * kBlockAlign; a2a.scnt[l][p] = r->pp.send_cnt[i] * kBlockAlign;
+        a2a.roff[l][p] = r->pp.recv_off[i] * kBlockAlign; a2a.rcnt[l][p] = r->pp.recv_cnt[i] * kBlockAlign;
       }
     }
     // every rank's pack of this sub-batch must be done before a copy reads its send buffer
@@ -881,7 +854,7 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
         bt.dump_scores = nullptr;
         XchgView xv;
         memset(&xv, 0, sizeof xv);
-        for (int o = 0; o < W; o++) xv.rmeta[o] = r->rmeta.p + r->koff[o];
+        for (int o = 0; o < W; o++) xv.rmeta[o] = r->rmeta.p + r->kp.send_off[o];
         xv.base = r->base.p + (size_t)r0 * W;
         xv.n_parts = W;
         const int sms = (x->reserve_sms > 0 && !x->local) ? std::max(1, r->dc->sm_count - x->reserve_sms) : 0;
@@ -1007,6 +980,26 @@ int rp_xchg_place(rp_xchg* x, const rp_place_cfg* cfg, int32_t n_local, const ui
       return set_error(RP_E_INVALID, "NULL buffer for local rank %d", l);
   }
   return xchg_place(x, cfg, io);
+}
+
+int rp_xchg_plan(int32_t world, int32_t n_sub, int32_t rank, int32_t direct_local, const uint64_t* probes, const uint64_t* units,
+                 uint64_t* key_send_off, uint64_t* key_recv_off, uint64_t* seg_first, uint64_t* home_first,
+                 uint64_t* pay_send_off, uint64_t* pay_send_cnt, uint64_t* pay_recv_off, uint64_t* pay_recv_cnt, uint64_t* caps) {
+  if (world < 1 || world > kMaxParts || n_sub < 1 || rank < 0 || rank >= world || !probes) return set_error(RP_E_INVALID, "bad argument");
+  const XKeyPlan k = plan_keys(world, n_sub, rank, probes);
+  if (key_send_off) std::copy(k.send_off.begin(), k.send_off.end(), key_send_off);
+  if (key_recv_off) std::copy(k.recv_off.begin(), k.recv_off.end(), key_recv_off);
+  if (seg_first) std::copy(k.seg_first.begin(), k.seg_first.end(), seg_first);
+  if (home_first) std::copy(k.home_first.begin(), k.home_first.end(), home_first);
+  if (units) {
+    const XPayPlan y = plan_payload(world, n_sub, rank, direct_local != 0, units);
+    if (pay_send_off) std::copy(y.send_off.begin(), y.send_off.end(), pay_send_off);
+    if (pay_send_cnt) std::copy(y.send_cnt.begin(), y.send_cnt.end(), pay_send_cnt);
+    if (pay_recv_off) std::copy(y.recv_off.begin(), y.recv_off.end(), pay_recv_off);
+    if (pay_recv_cnt) std::copy(y.recv_cnt.begin(), y.recv_cnt.end(), pay_recv_cnt);
+    if (caps) { caps[0] = y.send_cap; caps[1] = y.recv_cap; caps[2] = y.recv_total; }
+  }
+  return RP_OK;
 }
 
 int rp_xchg_stats(const rp_xchg* x, double* device_ms, uint64_t* probes, uint64_t* payload_bytes, uint64_t* hits,

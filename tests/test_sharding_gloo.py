@@ -100,3 +100,68 @@ def test_partition_of_keys_matches_restatement_and_balances(alphabet, k):
         assert np.array_equal(own, _owner_restatement(alphabet, k, keys, w))
         cnt = np.bincount(own, minlength=w)
         assert cnt.min() > 0.9 * len(keys) / w and cnt.max() < 1.1 * len(keys) / w
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Exchange form (rp_xchg.cu): the host-side plan -- who sends how many keys / posting-block units to whom, and
+# where they land -- computed by every rank from the all-gathered count matrices.  World-size-2 and -3 gloo
+# groups on the CPU: every rank derives ITS plan (rp_xchg_plan, pure host code of the product library) and the
+# ranks' plans must agree pairwise: what l sends p is what p expects from l, and the receive ranges tile.
+def _plan_worker(rank, world, port, tmp):
+    import torch
+    import torch.distributed as dist
+    from rappas_b200 import _abi
+    from rappas_b200._lib import check, load
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        J = 5
+        rng = np.random.default_rng(100 + rank)
+        mine = rng.integers(0, 1000, size=(J, world)).astype(np.uint64)      # probes of my sub-batch j for owner o
+        mine[rng.integers(0, J)] = 0                                         # an empty sub-batch
+        g = [torch.empty(J * world, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(g, torch.from_numpy(mine.reshape(-1).astype(np.int64)))
+        probes = np.stack([t.numpy().astype(np.uint64).reshape(J, world) for t in g])         # [w][j][o]
+        # units I (as owner) send to home p for sub-batch j: any function of the probes I receive
+        units_mine = (probes[:, :, rank] * np.uint64(3) // np.uint64(2)).astype(np.uint64)    # [p][j]
+        g = [torch.empty(world * J, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(g, torch.from_numpy(units_mine.reshape(-1).astype(np.int64)))
+        units = np.stack([t.numpy().astype(np.uint64).reshape(world, J) for t in g])          # [o][p][j]
+        fn = load()
+        plans = {}
+        for direct in (0, 1):
+            o = {k: np.zeros(n, np.uint64) for k, n in (("kso", world + 1), ("kro", world + 1), ("seg", world * J + 1),
+                                                        ("home", world * J), ("pso", J * world), ("psc", J * world),
+                                                        ("pro", J * world), ("prc", J * world), ("caps", 3))}
+            check(fn["xchg_plan"](world, J, rank, direct, _abi.ptr(np.ascontiguousarray(probes)), _abi.ptr(np.ascontiguousarray(units)),
+                                  *[_abi.ptr(o[k]) for k in ("kso", "kro", "seg", "home", "pso", "psc", "pro", "prc", "caps")]))
+            plans[direct] = o
+            # my own view is self-consistent
+            assert o["kso"][-1] == probes[rank].sum() and o["kro"][-1] == probes[:, :, rank].sum()
+            assert np.array_equal(np.diff(o["seg"]), probes[:, :, rank].reshape(-1))          # (source p, sub-batch j) order
+            for j in range(J):
+                rc, ro = o["prc"][j * world:(j + 1) * world], o["pro"][j * world:(j + 1) * world]
+                assert np.array_equal(ro, np.concatenate([[0], np.cumsum(rc)[:-1]]))          # receive ranges tile
+                assert rc.sum() <= o["caps"][1]
+                if direct:
+                    assert rc[rank] == 0 and o["psc"][j * world + rank] == 0
+        # pairwise agreement: gather everybody's send / receive counts
+        for direct in (0, 1):
+            o = plans[direct]
+            g = [None] * world
+            dist.all_gather_object(g, {"kso": o["kso"], "kro": o["kro"], "psc": o["psc"], "prc": o["prc"]})
+            for l in range(world):
+                for p in range(world):
+                    assert g[l]["kso"][p + 1] - g[l]["kso"][p] == g[p]["kro"][l + 1] - g[p]["kro"][l]
+                    for j in range(J):
+                        assert g[l]["psc"][j * world + p] == g[p]["prc"][j * world + l]
+        open(os.path.join(tmp, "plan%d" % rank), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world", [2, 3])
+def test_exchange_plan_agrees_across_ranks(tmp_path, world):
+    mp.spawn(_plan_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / ("plan%d" % r)).exists() for r in range(world))
