@@ -246,6 +246,14 @@ int  rp_extract_kmers(rp_db* db, const uint8_t* seq, const uint64_t* seq_off, in
                       const uint64_t* win_off, uint64_t* out_code, uint8_t* out_kind,
                       int32_t* out_nalt, int32_t* out_hits, int32_t* out_status);
 
+/* The same two stages AS THE PLACEMENT KERNEL'S PRODUCER COMPUTES THEM (rp_extract_kmers is a separate, simpler
+ * kernel): one placement launch that also records, per window, the k-mer code it built from the ballots and what
+ * its probe found.  out_code: code of a plain window, ~0 otherwise; out_hits: postings found (-1 = not in the DB),
+ * -2 = skipped window, -3 = ambiguous window (treated by the alternatives path), 0xFCFCFCFC = not visited (the
+ * read was cut short by an unsupported character).  Diagnostic: device 0, one launch, no pipelining. */
+int  rp_place_windows(rp_db* db, const rp_place_cfg* cfg, const uint8_t* seq, const uint64_t* seq_off, int64_t n_reads,
+                      const uint64_t* win_off, uint64_t* out_code, int32_t* out_hits);
+
 /* ---- parity diagnostic for the scoring stage (K3): the full per-node vector S[] of every
  * read after its last window (PlacementProcess.java:719-735, 1161-1172, 1223-1234).
  *   out_scores[n_reads][n_nodes]   NaN where the node was never touched (C[x]==0)

@@ -86,6 +86,7 @@ PROTOTYPES = {
     "place_batch_device": (C.c_int, [_P, C.c_int32, C.POINTER(RpPlaceCfg), _P, _P, C.c_int64,
                                      _P, _P, _P, _P, _P, _P, _P]),
     "extract_kmers": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, _P]),
+    "place_windows": (C.c_int, [_P, C.POINTER(RpPlaceCfg), _P, _P, C.c_int64, _P, _P, _P]),
     "node_scores": (C.c_int, [_P, C.POINTER(RpPlaceCfg), _P, _P, C.c_int64, _P, _P]),
     "reads_load_fasta": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
     "reads_from_memory": (C.c_int, [_P, C.c_uint64, C.POINTER(_P)]),

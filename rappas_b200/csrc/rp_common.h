@@ -165,6 +165,11 @@ struct BatchView {
   int32_t* counts;  // may be null
   int32_t* status;
   float* dump_scores;  // may be null: [n_reads][n_nodes]
+  // diagnostics of K1 + K2 as the PRODUCER of the placement kernel computes them (rp_place_windows): per window
+  // (index dump_win_off[r] + j) the planar key and the postings found (-1 miss, -2 skipped, -3 ambiguous); null = off
+  const uint64_t* dump_win_off;
+  uint64_t* dump_key;
+  int32_t* dump_hits;
 };
 
 // per (device, stream) resources

@@ -45,7 +45,8 @@
 namespace rp {
 
 constexpr uint32_t kSentinelBits = 0x7FFFFFFFu;  // a NaN no arithmetic here produces
-constexpr int kMaxPairsPerCta = 11;  // 704 threads: 88 registers per thread (768 threads = 80 registers spilt in the producer)  // producer warps 0..P-1, consumer warps P..2P-1
+constexpr int kMaxPairsPerCta = 12;  // producer warps 0..P-1, consumer warps P..2P-1 (registers are allocated per 4 warps:
+                                     // 22 or 24 warps leave 80 per thread, only <= 20 warps would get more)  // producer warps 0..P-1, consumer warps P..2P-1
 #ifndef RP_STAGES
 #define RP_STAGES 2  /* 3 measured slower at equal shared memory (tools/try_stages.sh) */
 #endif
@@ -399,7 +400,7 @@ constexpr int kMaxPasses = 16;  // slices are routed by sixteenths of the node r
 constexpr int kMaxAmbWin = 8;   // ambiguous windows per group (their table info travels in pk[0..7] of the stage header)
 struct __align__(16) StageHdr {
   long long r;           // read index in the batch
-  const uint8_t* seq;    // character g0 of the read: first window of this group
+  long long unused0;
   int Q;                 // len - k + 1 of the read (may be <= 0)
   float QT;              // (float)Q * T
   int flags;             // kGrp*
@@ -724,7 +725,8 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
     const uint32_t wbits = __funnelshift_r(a0, a1, lane) & kmask, rest = wbits & (wbits - 1);
     const int na = __popc(wbits);
     const bool treat = lane < min(32, Ql - g0) && na > 0 && na <= db.max_amb;
-    const int run = min(__ffs(~__ballot_sync(0xffffffffu, treat)) - 1, kMaxAmbWin);  // >= 1: window g0 is one
+    const uint32_t not_treat = ~__ballot_sync(0xffffffffu, treat);
+    const int run = min(not_treat ? __ffs(not_treat) - 1 : 32, kMaxAmbWin);  // >= 1: window g0 is one
     const int o1w = wbits ? __ffs(wbits) - 1 : 0, o2w = rest ? __ffs(rest) - 1 : o1w;
     const int q1 = lane + o1w, q2 = lane + o2w;
     const uint32_t c1a = __shfl_sync(0xffffffffu, cA, q1 & 31), c1b = __shfl_sync(0xffffffffu, cB, q1 & 31);
@@ -776,8 +778,8 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
   // The NEXT read of the pair: its index comes from the atomic issued one read earlier and its two
   // offsets are requested when the current read starts, so a read start waits for its characters only.
   // (Prefetching those too costs the producer more registers than it has: it spills.)
-  uint32_t nx_r = 0, nx_base = 0;
-  uint64_t nx_o0 = 0, nx_o1 = 0;
+  uint32_t nx_r = 0, nx_base = 0, nx_len = 0;  // nx_len: kMaxReadLen + 1 = too long
+  uint64_t nx_o0 = 0;
   bool nx_have = false;
   auto fetch_next_offsets = [&]() {
     nx_r = __shfl_sync(0xffffffffu, rn_raw, 0);
@@ -785,7 +787,7 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
     if (nx_have) {
       if (lane == 0) rn_raw = (uint32_t)atomicAdd(work_counter, 1ull);  // consumed when that read starts
       nx_o0 = bt.seq_off[nx_r];
-      nx_o1 = bt.seq_off[nx_r + 1];
+      nx_len = (uint32_t)min(bt.seq_off[nx_r + 1] - nx_o0, (uint64_t)kMaxReadLen + 1u);
       if (MODE == kXchg && lane < xv.n_parts) nx_base = xv.base[(size_t)nx_r * xv.n_parts + lane];
     }
   };
@@ -808,8 +810,8 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
     if (!nx_have) return false;
     r = nx_r;
     s = bt.seq + (nx_o0 - bt.seq_base);
-    too_long = (nx_o1 - nx_o0) > (uint64_t)kMaxReadLen;
-    len = too_long ? 0 : (int)(nx_o1 - nx_o0);
+    too_long = nx_len > (uint32_t)kMaxReadLen;
+    len = too_long ? 0 : (int)nx_len;
     Ql = len - k + 1;  // sk.getMerCount()
     QT = __fmul_rn((float)Ql, db.T);  // Q*PPStarThresholdAsLog10 (int*float)
     pass = 0;
@@ -846,7 +848,6 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
     int flags = (too_long ? kGrpTooLong : 0) | (SLICED ? pass << kGrpPassShift : 0);
     int n_steps = 0;
     uint32_t hitm = 0, stagedm = 0, total = 0;
-    const uint8_t* seq_g0 = s + g0;
     // per-lane results of this group that the publication below needs
     uint64_t meta = 0;
     uint32_t n_post = 0, bytes = 0, my_chunks = 0, incl_chunks = 0, off = 0, incl = 0;
@@ -920,6 +921,11 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
         const uint32_t lanes_taken = end_taken >= 32 ? 0xffffffffu : ((1u << end_taken) - 1u);
         if (MODE == kXchg && lane < xv.n_parts) x_run += __popc(x_mask & lanes_taken);  // the answers of the windows taken
         n_amb += cons;  // (matches inside the helpers are not counted: queryKmerMatchingDB is passed by value, :741-743)
+        if (RP_UNLIKELY(bt.dump_key != nullptr) && lane < cons && (!SLICED || pass == 0)) {
+          const uint64_t o = bt.dump_win_off[r] + (uint64_t)(g0 + lane);
+          bt.dump_key[o] = ~0ull;
+          bt.dump_hits[o] = -3;
+        }
         if (taken) {
           const uint32_t room = ((uint32_t)stage_bytes - b_taken) / 8u, fit_lg = 31 - __clz(room);
           flags |= kGrpAmb | (taken << kGrpWsizeShift);
@@ -942,6 +948,11 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
         stagedm = __ballot_sync(0xffffffffu, sb != 0u) & lanes;
         n_match += __popc((SLICED ? __ballot_sync(0xffffffffu, found) : hitm) & lanes);
         n_skip += __popc(__ballot_sync(0xffffffffu, g_skip) & lanes);
+        if (RP_UNLIKELY(bt.dump_key != nullptr) && lane < cons && (!SLICED || pass == 0)) {  // K1 + K2 as computed here
+          const uint64_t o = bt.dump_win_off[r] + (uint64_t)(g0 + lane);
+          bt.dump_key[o] = g_plain ? ((uint64_t)io.klo | ((uint64_t)io.khi << 32)) : ~0ull;
+          bt.dump_hits[o] = g_plain ? (found ? (int)(meta & 0xFFFF) : -1) : -2;
+        }
         if (MODE == kXchg && lane < xv.n_parts) x_run += __popc(x_mask & lanes);  // the answers of the windows taken
       }
       off = incl_bytes - sb;
@@ -1024,7 +1035,7 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
     }
     if (lane == 0) {
       StageHdr h;
-      h.r = r; h.seq = seq_g0; h.Q = Ql; h.QT = QT; h.flags = flags;
+      h.r = r; h.unused0 = 0; h.Q = Ql; h.QT = QT; h.flags = flags;
       h.n_match = n_match; h.n_amb = n_amb; h.n_skip = n_skip;
       h.n_chunks = n_steps; h.hitm = hitm; h.staged_bytes = total; h.stagedm = stagedm;
       h.pad[0] = h.pad[1] = 0;
@@ -1164,9 +1175,16 @@ constexpr int kMaxThreads = kMaxPairsPerCta * 64;
 // a sliced tree runs at most kWantPairs pairs per SM (that is what the number of passes is chosen for), so its
 // kernel may use the 128 registers a 512-thread CTA gets: the slice arithmetic spilt at 80
 constexpr int kWantPairs = 8;
-constexpr int max_threads_for(bool sliced) { return sliced ? kWantPairs * 64 : kMaxThreads; }
+// (the cuckoo probe keeps four 16 B slots per lane in flight across the publication of the previous group: that
+// variant spills at 80 registers, RP_CUCKOO_PAIRS = 10 gives it 96)
+#ifndef RP_CUCKOO_PAIRS
+#define RP_CUCKOO_PAIRS 12
+#endif
+constexpr int max_threads_for(bool sliced, int mode = kDirect) {
+  return sliced ? kWantPairs * 64 : mode == kCuckoo ? RP_CUCKOO_PAIRS * 64 : kMaxThreads;
+}
 template <bool SLICED, int MODE>
-__global__ void __maxnreg__(SLICED ? 128 : 88)
+__global__ void __launch_bounds__(max_threads_for(SLICED, MODE), 1)
 place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_constant__ DbView db,
              const __grid_constant__ CfgView cfg, const __grid_constant__ BatchView bt,
              const __grid_constant__ XchgView xv, unsigned long long* work_counter, float* amb_S, int* amb_C, int n_pad, int per_pair_bytes,
@@ -1348,7 +1366,7 @@ int compute_geometry(const rp_db* db, DeviceCtx* dc) {
   if (cta_fixed + g.per_warp_bytes > optin)
     return set_error(RP_E_UNSUPPORTED, "n_nodes=%d: one pair needs %zu B of shared memory (> %zu B per CTA) even with %d passes",
                      db->desc.n_nodes, g.per_warp_bytes, optin, n_pass);
-  const int max_pairs_cta = max_threads_for(n_pass > 1) / 64;
+  const int max_pairs_cta = max_threads_for(n_pass > 1, db->xchg ? kXchg : db_is_direct(db, dc) ? kDirect : kCuckoo) / 64;
   int max_pairs_sm = 16;
   if (const char* e = getenv("RP_PAIRS_PER_SM")) max_pairs_sm = std::max(1, std::min(16, atoi(e)));
   // registers bind before shared memory does on small trees (768 threads x 80 registers fill the file):
@@ -1605,7 +1623,7 @@ static int place_on_device(rp_db* db, DeviceCtx* dc, const rp_place_cfg* cfg, co
     BatchView bt;
     bt.seq = sc->d_seq; bt.seq_off = sc->d_off; bt.seq_base = b0; bt.n_reads = n;
     bt.n_rows = sc->d_n_rows; bt.node = sc->d_node; bt.score = sc->d_score; bt.lwr = sc->d_lwr;
-    bt.counts = out_counts ? sc->d_counts : nullptr; bt.status = sc->d_status; bt.dump_scores = nullptr;
+    bt.counts = out_counts ? sc->d_counts : nullptr; bt.status = sc->d_status; bt.dump_scores = nullptr; bt.dump_win_off = nullptr; bt.dump_key = nullptr; bt.dump_hits = nullptr;
     if (out_dump) {
       const size_t nd = (size_t)n * db->desc.n_nodes;
       if (!d_dump[b]) RP_CUDA_BRK(cudaMalloc((void**)&d_dump[b], (size_t)kChunk * db->desc.n_nodes * sizeof(float)));
@@ -1726,6 +1744,62 @@ int rp_node_scores(rp_db* db, const rp_place_cfg* cfg, const uint8_t* seq, const
                     status.data(), out_scores);
 }
 
+int rp_place_windows(rp_db* db, const rp_place_cfg* cfg, const uint8_t* seq, const uint64_t* seq_off, int64_t n_reads,
+                     const uint64_t* win_off, uint64_t* out_code, int32_t* out_hits) {
+  if (!db) return set_error(RP_E_INVALID, "db is NULL");
+  int rc = check_cfg(cfg);
+  if (rc) return rc;
+  if (n_reads <= 0) return n_reads == 0 ? RP_OK : set_error(RP_E_INVALID, "n_reads < 0");
+  if (!seq_off || !win_off || !out_code || !out_hits) return set_error(RP_E_INVALID, "NULL buffer");
+  if (seq_off[0] != 0 || win_off[0] != 0) return set_error(RP_E_INVALID, "seq_off[0] and win_off[0] must be 0");
+  const int k = db->desc.k, bits = alphabet_bits(db->desc.alphabet), K = cfg->keep_at_most;
+  DeviceCtx* dc = db->dev[0];
+  std::lock_guard<std::mutex> lock(dc->mu);
+  RP_CUDA_TRY(cudaSetDevice(dc->device));
+  StreamCtx* sc = &dc->sc[0];
+  if ((rc = ensure_stream_ctx(db, dc, sc))) return rc;
+  const uint64_t nbytes = seq_off[n_reads], nw = win_off[n_reads];
+  if ((rc = ensure_io(sc, nbytes, (size_t)n_reads, K, true))) return rc;
+  uint64_t *d_woff = nullptr, *d_key = nullptr;
+  int32_t* d_hits = nullptr;
+  auto body = [&]() -> int {
+    RP_CUDA_TRY(cudaMalloc((void**)&d_woff, (n_reads + 1) * 8));
+    RP_CUDA_TRY(cudaMalloc((void**)&d_key, (nw + 1) * 8));
+    RP_CUDA_TRY(cudaMalloc((void**)&d_hits, (nw + 1) * 4));
+    RP_CUDA_TRY(cudaMemset(d_key, 0xFF, (nw + 1) * 8));
+    RP_CUDA_TRY(cudaMemset(d_hits, 0xFC, (nw + 1) * 4));  // 0xFCFCFCFC: "not visited" (reads cut short by a bad character)
+    if (nbytes) RP_CUDA_TRY(cudaMemcpy(sc->d_seq, seq, nbytes, cudaMemcpyHostToDevice));
+    RP_CUDA_TRY(cudaMemcpy(sc->d_off, seq_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice));
+    RP_CUDA_TRY(cudaMemcpy(d_woff, win_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice));
+    BatchView bt;
+    bt.seq = sc->d_seq; bt.seq_off = sc->d_off; bt.seq_base = 0; bt.n_reads = n_reads;
+    bt.n_rows = sc->d_n_rows; bt.node = sc->d_node; bt.score = sc->d_score; bt.lwr = sc->d_lwr;
+    bt.counts = sc->d_counts; bt.status = sc->d_status;
+    bt.dump_scores = nullptr; bt.dump_win_off = d_woff; bt.dump_key = d_key; bt.dump_hits = d_hits;
+    int r2 = launch_place(db, dc, sc, cfg, bt, sc->stream, false);
+    if (r2) return r2;
+    RP_CUDA_TRY(cudaStreamSynchronize(sc->stream));
+    if (nw) {
+      RP_CUDA_TRY(cudaMemcpy(out_code, d_key, nw * 8, cudaMemcpyDeviceToHost));
+      RP_CUDA_TRY(cudaMemcpy(out_hits, d_hits, nw * 4, cudaMemcpyDeviceToHost));
+    }
+    return RP_OK;
+  };
+  rc = body();
+  cudaFree(d_woff); cudaFree(d_key); cudaFree(d_hits);
+  if (rc) return rc;
+  // planar key (bit p of state i at bit p*k + i) -> ABI code (state i in bits [bits*i, bits*i + bits))
+  for (uint64_t i = 0; i < nw; i++) {
+    const uint64_t key = out_code[i];
+    if (key == ~0ull) continue;
+    uint64_t code = 0;
+    for (int j = 0; j < k; j++)
+      for (int pl = 0; pl < bits; pl++) code |= ((key >> (pl * k + j)) & 1ull) << (bits * j + pl);
+    out_code[i] = code;
+  }
+  return RP_OK;
+}
+
 int rp_place_batch_device(rp_db* db, int32_t device_index, const rp_place_cfg* cfg, const uint8_t* d_seq,
                           const uint64_t* d_seq_off, int64_t n_reads, int32_t* d_out_n_rows, uint16_t* d_out_node,
                           float* d_out_score, double* d_out_lwr, int32_t* d_out_counts, int32_t* d_out_status,
@@ -1760,7 +1834,7 @@ int rp_place_batch_device(rp_db* db, int32_t device_index, const rp_place_cfg* c
   BatchView bt;
   bt.seq = d_seq; bt.seq_off = d_seq_off; bt.seq_base = 0; bt.n_reads = n_reads;
   bt.n_rows = d_out_n_rows; bt.node = d_out_node; bt.score = d_out_score; bt.lwr = d_out_lwr;
-  bt.counts = d_out_counts; bt.status = d_out_status; bt.dump_scores = nullptr;
+  bt.counts = d_out_counts; bt.status = d_out_status; bt.dump_scores = nullptr; bt.dump_win_off = nullptr; bt.dump_key = nullptr; bt.dump_hits = nullptr;
   rc = launch_place(db, dc, sc, cfg, bt, us, false);
   if (rc == RP_OK) RP_CUDA_TRY(cudaEventRecord(slot->last, us));
   return rc;

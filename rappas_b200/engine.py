@@ -204,6 +204,16 @@ class Database:
                                       _abi.ptr(out["nalt"]), _abi.ptr(out["hits"]), _abi.ptr(out["status"])))
         return out
 
+    def place_windows(self, reads: ReadBatch, cfg=None):
+        """K1 + K2 as the placement kernel's producer computes them: per window (code, hits); see rp_place_windows."""
+        cfg = cfg or _abi.place_cfg()
+        woff = reads.window_offsets(self.k)
+        nw = int(woff[-1])
+        code, hits = np.zeros(nw, np.uint64), np.zeros(nw, np.int32)
+        check(load()["place_windows"](self._h, C.byref(cfg), _abi.ptr(reads.seq), _abi.ptr(reads.seq_off), reads.n_reads,
+                                      _abi.ptr(woff), _abi.ptr(code), _abi.ptr(hits)))
+        return {"win_off": woff, "code": code, "hits": hits}
+
     def node_scores(self, reads: ReadBatch, cfg=None):
         cfg = cfg or _abi.place_cfg()
         S = np.empty((reads.n_reads, self.n_nodes), np.float32)

@@ -404,3 +404,22 @@ def test_pinned_and_pageable_callers_give_the_same_rows():
         del seq, off, out
         for p in ptrs:
             fn["host_free"](p)
+
+
+def test_kmers_and_hits_of_the_placement_kernel_itself(case):
+    """K1 + K2 measured ON place_kernel: the codes its producer builds from ballots and funnel shifts and what its
+    probes (cuckoo buckets / direct-address table) find, window by window, against the oracle's AmbigSequenceKnife +
+    hash lookup (rp_extract_kmers is a separate kernel and is held to the same oracle above)."""
+    _, db, rb, g, o = case
+    ex = o.extract(rb)
+    pw = g.place_windows(rb)
+    woff = ex["win_off"].astype(np.int64)
+    ok_read = ex["status"] == 0
+    visited = pw["hits"] != np.int32(-50529028)  # 0xFCFCFCFC: windows behind an unsupported character
+    win_read = np.repeat(np.arange(rb.n_reads), np.diff(woff))
+    assert visited[ok_read[win_read]].all()
+    plain = (ex["kind"] == _abi.WIN_PLAIN) & ok_read[win_read]
+    assert np.array_equal(pw["code"][plain], ex["code"][plain])
+    assert np.array_equal(pw["hits"][plain], ex["hits"][plain])
+    assert (pw["hits"][(ex["kind"] == _abi.WIN_SKIPPED) & ok_read[win_read]] == -2).all()
+    assert (pw["hits"][(ex["kind"] == _abi.WIN_AMBIG) & ok_read[win_read]] == -3).all()

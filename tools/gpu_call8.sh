@@ -1,0 +1,12 @@
+mkdir -p gpurun_out; rm -f gpurun_out/sweep8.jsonl
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_exchange.py -x -q > gpurun_out/t_par8.log 2>&1; tail -5 gpurun_out/t_par8.log
+timeout 300 python tools/sweep_geom.py --config 2 --tag NEW --envs ";RP_NO_DIRECT=1" >> gpurun_out/sweep8.jsonl 2>> gpurun_out/sweep8.err
+timeout 300 python tools/sweep_geom.py --config 4 --tag NEW >> gpurun_out/sweep8.jsonl 2>> gpurun_out/sweep8.err
+RAPPAS_B200_LIB=build/variants/CK10.so timeout 300 python tools/sweep_geom.py --config 4 --tag CK10 >> gpurun_out/sweep8.jsonl 2>> gpurun_out/sweep8.err
+RAPPAS_B200_LIB=build/variants/CK10.so timeout 300 python tools/sweep_geom.py --config 2 --tag CK10 --envs "RP_NO_DIRECT=1" >> gpurun_out/sweep8.jsonl 2>> gpurun_out/sweep8.err
+timeout 300 python tools/sweep_geom.py --config 5 --reads 100000 --tag NEWgenome >> gpurun_out/sweep8.jsonl 2>> gpurun_out/sweep8.err
+cat gpurun_out/sweep8.jsonl
+for a in "" "--no-ambiguity"; do
+timeout 300 python bench.py --config 5 --reads 200000 --steps 2 --warmup 1 --k5 13 $a > gpurun_out/c8_one_k13$a.json 2> gpurun_out/c8_one_k13$a.err; python -c "
+import json; j=json.loads(open('gpurun_out/c8_one_k13$a.json').read().strip().split('\n')[-1]); print('one_k13 $a value=%.3e e2e=%.3e ok=%s'%(j['value'],j['e2e']['value'],j['matches_oracle']))" || tail -3 gpurun_out/c8_one_k13$a.err
+done
