@@ -40,6 +40,19 @@ public final class RappasB200 implements AutoCloseable {
     private static final MethodHandle JPLACE = fn("rp_jplace_write", FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, ADDRESS,
             ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
     private static final MethodHandle LAST_ERROR = fn("rp_last_error", FunctionDescriptor.of(ADDRESS));
+    // int rp_host_alloc(void** out, uint64_t bytes); void rp_host_free(void*): page-locked batch buffers, so that the
+    // library's H2D / kernel / D2H pipeline copies straight from / to them (a pageable buffer is staged by the library)
+    private static final MethodHandle HOST_ALLOC = fn("rp_host_alloc", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG));
+    private static final MethodHandle HOST_FREE = fn("rp_host_free", FunctionDescriptor.ofVoid(ADDRESS));
+
+    /** A reusable page-locked buffer of `bytes` bytes (free with freePinned). */
+    public MemorySegment allocPinned(long bytes) throws Throwable {
+        MemorySegment pp = arena.allocate(ADDRESS);
+        check((int) HOST_ALLOC.invokeExact(pp, bytes));
+        return pp.get(ADDRESS, 0).reinterpret(bytes);
+    }
+
+    public void freePinned(MemorySegment m) throws Throwable { HOST_FREE.invokeExact(m); }
 
     /** struct rp_place_cfg { int32 keep_at_most; float keep_factor; int32 treat_amb; int32 amb_with_max; float ns_bound; int32 reserved0; } */
     static final MemoryLayout CFG = MemoryLayout.structLayout(JAVA_INT, JAVA_FLOAT, JAVA_INT, JAVA_INT, JAVA_FLOAT, JAVA_INT);

@@ -719,7 +719,36 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
   // group of its own: a 775 bp read with five ambiguous characters was ~100 groups instead of ~25, and the
   // per-group cost made such reads 3.6x slower.)  Returns the number of candidate windows; lane w < that keeps the
   // window's W_size in aw_size and the end of its slot range in aw_end; aw_win = this slot's window (or -1).
+  // BATCH = SLICED: the plain kernels keep round 1's one-window form -- the batched form costs the producer registers
+  // (the cuckoo variant spilt at 80) and ~800 instructions, 15-20 % on configs that hardly meet an ambiguous window,
+  // while the shapes that do (long reads, config 5) run on big trees, i.e. on the sliced kernels.
+  constexpr bool BATCH = SLICED;
   auto probe_alternatives = [&](bool& found, uint64_t& meta, int& aw_size, int& aw_end, int& aw_win) -> int {
+    if (!BATCH) {  // window g0 alone: lane t < W_size probes alternative t (class bytes in cA)
+      const uint32_t wbits = __ballot_sync(0xffffffffu, (cA & 0xC0) == kClsAmb) & kmask, rest = wbits & (wbits - 1);
+      const int o1 = __ffs(wbits) - 1, o2 = rest ? __ffs(rest) - 1 : o1;
+      const int id1 = __shfl_sync(0xffffffffu, cA, o1) & 0x3F, id2 = __shfl_sync(0xffffffffu, cA, o2) & 0x3F;
+      const int n1 = c_alpha.alt_n[id1], n2 = rest ? c_alpha.alt_n[id2] : 1;
+      const int wsize = n1 * n2;  // <= 20 (amino) / 16 (nucl, 2 ambiguities)
+      const uint32_t st1 = c_alpha.alt_states[id1][lane % n1], st2 = c_alpha.alt_states[id2][lane % n2];
+      uint64_t key = 0;
+      for (int p = 0; p < db.bits; p++) {
+        uint64_t plane = __ballot_sync(0xffffffffu, (cA >> p) & 1u) & kmask & ~((1u << o1) | (1u << o2));
+        if (rest) plane |= (uint64_t)((st2 >> p) & 1u) << o2;
+        plane |= (uint64_t)((st1 >> p) & 1u) << o1;
+        key |= plane << (p * k);
+      }
+      if (MODE == kXchg) {
+        const uint64_t* a = answer_of(key, lane < wsize);
+        meta = lane < wsize ? __ldg(reinterpret_cast<const unsigned long long*>(a)) : kEmptyKey;
+        found = meta != kEmptyKey;
+        if (lane < xv.n_parts) x_run += __popc(x_mask);
+      } else {
+        found = lane < wsize && table_probe(db, key, meta);
+      }
+      aw_size = wsize;
+      return 1;
+    }
     const uint32_t a0 = __ballot_sync(0xffffffffu, (cA & 0xC0) == kClsAmb), a1 = __ballot_sync(0xffffffffu, (cB & 0xC0) == kClsAmb);
     // window `lane`: its ambiguous offsets and W_size
     const uint32_t wbits = __funnelshift_r(a0, a1, lane) & kmask, rest = wbits & (wbits - 1);
@@ -881,7 +910,7 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       my_chunks = sb ? (n_post + 31) >> 5 : 0u;
       // (ambiguous windows: every alternative's chunks start at a step of their own -- an odd count is padded with an
       // idle B slot -- so that a window's steps are a contiguous range the consumer can treat by itself)
-      incl = (sb >> 5 << 13) | (RP_UNLIKELY(ncand != 0) ? (my_chunks + 1u) & ~1u : my_chunks);
+      incl = (sb >> 5 << 13) | ((BATCH && RP_UNLIKELY(ncand != 0)) ? (my_chunks + 1u) & ~1u : my_chunks);
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
@@ -890,7 +919,28 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       const uint32_t incl_bytes = incl >> 13 << 5;
       incl_chunks = incl & 0x1FFFu;
       const uint32_t nofit = __ballot_sync(0xffffffffu, incl_bytes > (uint32_t)stage_bytes);
-      if (RP_UNLIKELY(ncand != 0)) {
+      if (!BATCH && RP_UNLIKELY(ncand != 0)) {
+        // one ambiguous window: all the alternatives found, plus a table of >= as many entries as they have postings,
+        // in one stage -- or nothing is staged and the consumer reads them from global memory
+        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t tot_bytes = tot >> 13 << 5, tot_chunks = tot & 0x1FFFu;
+        const uint32_t foundm = __ballot_sync(0xffffffffu, routed), giantm = __ballot_sync(0xffffffffu, routed && giant);
+        const uint32_t room = (tot_bytes <= (uint32_t)stage_bytes ? (uint32_t)stage_bytes - tot_bytes : 0u) / 8u;
+        uint32_t lg = room ? 31 - __clz(room) : 0;                         // the largest table that fits ...
+        if (tot_chunks) lg = min(lg, 32u - __clz(64u * tot_chunks - 1u));  // ... up to twice the postings
+        const bool staged = !nofit && !giantm && (1u << lg) >= 32u * tot_chunks && lg >= 5;
+        flags |= staged ? (kGrpAmb | (1 << kGrpWsizeShift)) : (kGrpAmbGlobal | (aw_size << kGrpWsizeShift));
+        hitm = stagedm = staged ? foundm : 0u;
+        cons = 1;
+        last = 31;
+        n_amb += 1;  // (matches inside the helpers are not counted: queryKmerMatchingDB is passed by value, :741-743)
+        if (lane == 0) amb_info = (((tot_chunks + 1) >> 1) << 11) | ((uint32_t)aw_size << 20) | (lg << 26);
+        if (!found) meta = kEmptyKey;  // (the consumer's global-memory walk takes the alternatives' entries as they are)
+        if (RP_UNLIKELY(bt.dump_key != nullptr) && lane == 0 && (!SLICED || pass == 0)) {
+          bt.dump_key[bt.dump_win_off[r] + (uint64_t)g0] = ~0ull;
+          bt.dump_hits[bt.dump_win_off[r] + (uint64_t)g0] = -3;
+        }
+      } else if (BATCH && RP_UNLIKELY(ncand != 0)) {
         // Ambiguous windows: take them in order while the blocks of all their alternatives, plus ONE table of at least
         // as many entries as the largest window has postings (the consumer treats the windows one after the
         // other), fit the stage.  If not even the first fits, nothing is staged and the consumer walks that
@@ -993,7 +1043,7 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
       // c & 1 of step c >> 1, unless the pair (c - 1, c) straddles two windows whose node ranges intersect: then
       // the pair is SPLIT into two steps with idle B slots, and every later step moves down by one.  A split is
       // owned by the lane of the odd chunk (the first chunk of its window).
-      const bool ambg = flags & kGrpAmb;  // (its scan counted every alternative's chunks rounded up to even)
+      const bool ambg = BATCH && (flags & kGrpAmb);  // (its scan counted every alternative's chunks rounded up to even)
       const uint32_t c0 = incl_chunks_c - (ambg ? (my_chunks_c + 1u) & ~1u : my_chunks_c);
       const uint32_t q8 = (uint32_t)(meta_c >> kMetaQminShift) & 0xFFu;
       const uint32_t prevm = stagedm & lanemask_lt();
@@ -1030,9 +1080,10 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
         // an alternative with an odd number of chunks: its last step has no B (my_chunks_c is the real count, the scan
         // counted the padded one)
         if (bytes_c && (my_chunks_c & 1u)) sts_u64(dl0 + 16 * ((incl_chunks_c - 1u) >> 1) + 8, idle);
-        if (lane < kMaxAmbWin) sts_u32(hdr + 64 + 4 * lane, amb_info);
       }
     }
+    // (also when none of the windows' alternatives is in the DB and nothing is staged: the consumer walks the info words)
+    if ((flags & kGrpAmb) && lane < kMaxAmbWin) sts_u32(hdr + 64 + 4 * lane, amb_info);
     if (lane == 0) {
       StageHdr h;
       h.r = r; h.unused0 = 0; h.Q = Ql; h.QT = QT; h.flags = flags;

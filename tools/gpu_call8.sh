@@ -2,8 +2,8 @@ mkdir -p gpurun_out; rm -f gpurun_out/sweep8.jsonl
 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_exchange.py -x -q > gpurun_out/t_par8.log 2>&1; tail -5 gpurun_out/t_par8.log
 timeout 300 python tools/sweep_geom.py --config 2 --tag NEW --envs ";RP_NO_DIRECT=1" >> gpurun_out/sweep8.jsonl 2>> gpurun_out/sweep8.err
 timeout 300 python tools/sweep_geom.py --config 4 --tag NEW >> gpurun_out/sweep8.jsonl 2>> gpurun_out/sweep8.err
-RAPPAS_B200_LIB=build/variants/CK10.so timeout 300 python tools/sweep_geom.py --config 4 --tag CK10 >> gpurun_out/sweep8.jsonl 2>> gpurun_out/sweep8.err
-RAPPAS_B200_LIB=build/variants/CK10.so timeout 300 python tools/sweep_geom.py --config 2 --tag CK10 --envs "RP_NO_DIRECT=1" >> gpurun_out/sweep8.jsonl 2>> gpurun_out/sweep8.err
+
+
 timeout 300 python tools/sweep_geom.py --config 5 --reads 100000 --tag NEWgenome >> gpurun_out/sweep8.jsonl 2>> gpurun_out/sweep8.err
 cat gpurun_out/sweep8.jsonl
 for a in "" "--no-ambiguity"; do
