@@ -180,7 +180,7 @@ __device__ __forceinline__ void ambiguous_window(const DbView& db, const CfgView
           if (c == 0) sa = v;
           if (v > sa) sa = v;
         } else {
-          sa = (float)((double)sa + pow(10.0, (double)v));  // S_amb[x]+=Math.pow(10,v) : f32 += f64
+          sa = __fadd_rn(sa, exp10f(v));  // S_amb[x]+=Math.pow(10,v)  (:1155; f32 arithmetic here, see ambiguous_staged)
         }
         __stcg(Sa + x, sa);
         __stcg(Ca + x, c + 1);
@@ -209,8 +209,8 @@ __device__ __forceinline__ void ambiguous_window(const DbView& db, const CfgView
           } else {
             // float avgProba=(S_amb[x] + (W_size-C_amb[x])*PPStarThreshold) / W_size;   (:1168)
             const float avg = __fdiv_rn(__fadd_rn(sa, __fmul_rn((float)(n - c), db.Tlin)), (float)n);
-            // S[x]+=Math.log10(avgProba)-PPStarThresholdAsLog10;   f32 += f64   (:1169)
-            s = (float)((double)s + (log10((double)avg) - (double)db.T));
+            // S[x]+=Math.log10(avgProba)-PPStarThresholdAsLog10;   (:1169; f32 here, see ambiguous_staged)
+            s = __fadd_rn(s, __fsub_rn(log10f(avg), db.T));
           }
           S[x] = s;
           __stcg(Ca + x, 0);
@@ -548,7 +548,11 @@ __device__ __forceinline__ void ambiguous_staged(const DbView& db, const CfgView
       if (cfg.amb_with_max) {
         if (c == 0 || v > sa) sa = v;
       } else {
-        sa = (float)((double)sa + pow(10.0, (double)v));  // S_amb[x]+=Math.pow(10,v) : f32 += f64
+        // S_amb[x]+=Math.pow(10,v)  (:1155).  The reference adds an f64 power into the f32 S_amb; here power and sum are
+        // f32 (exp10f, <= 2 ulp): the f64 pow was ~300 instructions per posting and, with the log10 below, made a read
+        // with ambiguity codes 5x slower than one without.  The difference reaches S[x] through log10(avg) as <= 1e-6
+        // absolute per window, against an f32 S[x] of magnitude Q*T (hundreds to thousands: ulp >= 6e-5).
+        sa = __fadd_rn(sa, exp10f(v));
       }
       sts_u64(tab + 8 * h, make_uint2(x | ((c + 1) << 16), __float_as_uint(sa)));
     }
@@ -566,8 +570,8 @@ __device__ __forceinline__ void ambiguous_staged(const DbView& db, const CfgView
       } else {
         // float avgProba=(S_amb[x] + (W_size-C_amb[x])*PPStarThreshold) / W_size;   (:1168)
         const float avg = __fdiv_rn(__fadd_rn(sa, __fmul_rn((float)(n - (int)c), db.Tlin)), (float)n);
-        // S[x]+=Math.log10(avgProba)-PPStarThresholdAsLog10;   f32 += f64   (:1169)
-        s = (float)((double)s + (log10((double)avg) - (double)db.T));
+        // S[x]+=Math.log10(avgProba)-PPStarThresholdAsLog10;   (:1169; the reference evaluates in f64 and narrows, here f32)
+        s = __fadd_rn(s, __fsub_rn(log10f(avg), db.T));
       }
       S[x] = s;
     }
@@ -1226,6 +1230,9 @@ constexpr int kMaxThreads = kMaxPairsPerCta * 64;
 // a sliced tree runs at most kWantPairs pairs per SM (that is what the number of passes is chosen for), so its
 // kernel may use the 128 registers a 512-thread CTA gets: the slice arithmetic spilt at 80
 constexpr int kWantPairs = 8;
+// passes are added until this many pairs fit (config 3, 9 999 nodes: 1 / 2 / 3 passes = 4 / 7 / 8 pairs run 28.7 / 25.6 /
+// 28.6 ms per 1 M reads: a pass more costs the producer a whole walk of the read)
+constexpr int kPassTargetPairs = 7;
 // (the cuckoo probe keeps four 16 B slots per lane in flight across the publication of the previous group: that
 // variant spills at 80 registers, RP_CUCKOO_PAIRS = 10 gives it 96)
 #ifndef RP_CUCKOO_PAIRS
@@ -1398,7 +1405,7 @@ int compute_geometry(const rp_db* db, DeviceCtx* dc) {
   };
   int n_pass = 1;
   for (; n_pass < kMaxPasses; n_pass++)
-    if ((optin - cta_fixed) / pair_bytes(stage_for(n_pass), slice_for(n_pass)) >= (size_t)kWantPairs) break;
+    if ((optin - cta_fixed) / pair_bytes(stage_for(n_pass), slice_for(n_pass)) >= (size_t)kPassTargetPairs) break;
   if (const char* e = getenv("RP_PASSES")) n_pass = std::max(1, std::min(kMaxPasses, atoi(e)));
   while (n_pass > 1 && slice_for(n_pass) == slice_for(n_pass - 1)) n_pass--;  // no empty slices
   g.n_pass = n_pass;
@@ -1441,6 +1448,19 @@ int compute_geometry(const rp_db* db, DeviceCtx* dc) {
       best_total = c * tpc;
       g.ctas_per_sm = c;
       pairs_cta = tpc;
+    }
+  }
+  // shared memory the chosen pairs leave unused goes to the stages (a sliced tree runs at most kWantPairs pairs, and
+  // its nominal stage is small: larger stages take more windows per group and hold the tables of ambiguous windows)
+  if (g.ctas_per_sm == 1 && !getenv("RP_STAGE_BYTES")) {
+    long st = std::min<long>(3 * stage, 32768L - 128);
+    for (; st > stage; st -= 128)
+      if (cta_fixed + pairs_cta * pair_bytes(st, g.slice) <= optin) break;
+    if (st > stage) {
+      stage = st;
+      g.stage_bytes = (int)stage;
+      g.max_chunks = (int)chunks_for(stage);
+      g.per_warp_bytes = pair_bytes(stage, g.slice);
     }
   }
   g.warps_per_cta = pairs_cta * 2;
@@ -1672,6 +1692,7 @@ static int place_on_device(rp_db* db, DeviceCtx* dc, const rp_place_cfg* cfg, co
     if (nbytes) RP_CUDA_BRK(cudaMemcpyAsync(sc->d_seq, src_seq, nbytes, cudaMemcpyHostToDevice, st));
     RP_CUDA_BRK(cudaMemcpyAsync(sc->d_off, src_off, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     BatchView bt;
+    memset(&bt, 0, sizeof bt);
     bt.seq = sc->d_seq; bt.seq_off = sc->d_off; bt.seq_base = b0; bt.n_reads = n;
     bt.n_rows = sc->d_n_rows; bt.node = sc->d_node; bt.score = sc->d_score; bt.lwr = sc->d_lwr;
     bt.counts = out_counts ? sc->d_counts : nullptr; bt.status = sc->d_status; bt.dump_scores = nullptr; bt.dump_win_off = nullptr; bt.dump_key = nullptr; bt.dump_hits = nullptr;
@@ -1823,6 +1844,7 @@ int rp_place_windows(rp_db* db, const rp_place_cfg* cfg, const uint8_t* seq, con
     RP_CUDA_TRY(cudaMemcpy(sc->d_off, seq_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice));
     RP_CUDA_TRY(cudaMemcpy(d_woff, win_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice));
     BatchView bt;
+    memset(&bt, 0, sizeof bt);
     bt.seq = sc->d_seq; bt.seq_off = sc->d_off; bt.seq_base = 0; bt.n_reads = n_reads;
     bt.n_rows = sc->d_n_rows; bt.node = sc->d_node; bt.score = sc->d_score; bt.lwr = sc->d_lwr;
     bt.counts = sc->d_counts; bt.status = sc->d_status;
@@ -1883,6 +1905,7 @@ int rp_place_batch_device(rp_db* db, int32_t device_index, const rp_place_cfg* c
   if ((rc = ensure_stream_ctx(db, dc, sc))) return rc;
   if (slot->shared) RP_CUDA_TRY(cudaStreamWaitEvent(us, slot->last, 0));  // another stream may still be using the slot
   BatchView bt;
+  memset(&bt, 0, sizeof bt);
   bt.seq = d_seq; bt.seq_off = d_seq_off; bt.seq_base = 0; bt.n_reads = n_reads;
   bt.n_rows = d_out_n_rows; bt.node = d_out_node; bt.score = d_out_score; bt.lwr = d_out_lwr;
   bt.counts = d_out_counts; bt.status = d_out_status; bt.dump_scores = nullptr; bt.dump_win_off = nullptr; bt.dump_key = nullptr; bt.dump_hits = nullptr;

@@ -848,6 +848,7 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
         view.n_parts = W; view.table_parts = 1; view.direct = nullptr;
         for (int o = 0; o < W; o++) view.blocks[o] = (direct_local && o == me) ? r->db->parts[me].d_blocks : r->recvpay[b].p;
         BatchView bt;
+        memset(&bt, 0, sizeof bt);
         bt.seq = r->seq.p; bt.seq_off = r->off.p + r0; bt.seq_base = 0; bt.n_reads = r1 - r0;
         bt.n_rows = r->o_n_rows.p + r0; bt.node = r->o_node.p + r0 * K; bt.score = r->o_score.p + r0 * K;
         bt.lwr = r->o_lwr.p + r0 * K; bt.counts = io[l].counts ? r->o_counts.p + 4 * r0 : nullptr; bt.status = r->o_status.p + r0;
