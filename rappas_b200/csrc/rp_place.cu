@@ -1002,11 +1002,13 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
         stagedm = __ballot_sync(0xffffffffu, sb != 0u) & lanes;
         n_match += __popc((SLICED ? __ballot_sync(0xffffffffu, found) : hitm) & lanes);
         n_skip += __popc(__ballot_sync(0xffffffffu, g_skip) & lanes);
+#ifndef RP_NO_DUMP
         if (RP_UNLIKELY(bt.dump_key != nullptr) && lane < cons && (!SLICED || pass == 0)) {  // K1 + K2 as computed here
           const uint64_t o = bt.dump_win_off[r] + (uint64_t)(g0 + lane);
           bt.dump_key[o] = g_plain ? ((uint64_t)io.klo | ((uint64_t)io.khi << 32)) : ~0ull;
           bt.dump_hits[o] = g_plain ? (found ? (int)(meta & 0xFFFF) : -1) : -2;
         }
+#endif
         if (MODE == kXchg && lane < xv.n_parts) x_run += __popc(x_mask & lanes);  // the answers of the windows taken
       }
       off = incl_bytes - sb;
@@ -1452,7 +1454,7 @@ int compute_geometry(const rp_db* db, DeviceCtx* dc) {
   }
   // shared memory the chosen pairs leave unused goes to the stages (a sliced tree runs at most kWantPairs pairs, and
   // its nominal stage is small: larger stages take more windows per group and hold the tables of ambiguous windows)
-  if (g.ctas_per_sm == 1 && !getenv("RP_STAGE_BYTES")) {
+  if (n_pass > 1 && g.ctas_per_sm == 1 && !getenv("RP_STAGE_BYTES")) {
     long st = std::min<long>(3 * stage, 32768L - 128);
     for (; st > stage; st -= 128)
       if (cta_fixed + pairs_cta * pair_bytes(st, g.slice) <= optin) break;
