@@ -643,7 +643,7 @@ __device__ __forceinline__ bool probe_resolve(const ProbeIO& io, uint64_t& meta)
 // the passes whose slice its (node-sorted) posting list can touch: the table entry carries the first and the
 // last sixteenth of the padded node range the list spans.  Every node belongs to exactly one pass and the
 // windows of a pass are visited in order, so each S[x] still sees the reference's f32 addition sequence.
-template <bool SLICED, int MODE>
+template <bool SLICED, int MODE, bool DUMP, bool BATCH>
 __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const DbView& db, const CfgView& cfg,
                                          const BatchView& bt, const XchgView& xv, unsigned long long* work_counter,
                                          const PairSmem& w, uint32_t cls_tab, int lane, int n_pad, int slice, int n_pass) {
@@ -723,10 +723,10 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
   // group of its own: a 775 bp read with five ambiguous characters was ~100 groups instead of ~25, and the
   // per-group cost made such reads 3.6x slower.)  Returns the number of candidate windows; lane w < that keeps the
   // window's W_size in aw_size and the end of its slot range in aw_end; aw_win = this slot's window (or -1).
-  // BATCH = SLICED: the plain kernels keep round 1's one-window form -- the batched form costs the producer registers
-  // (the cuckoo variant spilt at 80) and ~800 instructions, 15-20 % on configs that hardly meet an ambiguous window,
-  // while the shapes that do (long reads, config 5) run on big trees, i.e. on the sliced kernels.
-  constexpr bool BATCH = SLICED;
+  // BATCH: only sliced kernels have the batched form, and only batches that carry ambiguity codes run it (two builds
+  // of the kernel are launched, a character count picks the one that proceeds: launch_place).  The batched form costs
+  // the producer registers (the plain cuckoo variant spilt at 80) and ~1 500 instructions of code that sits between
+  // the hot blocks: 15-20 % on the plain kernels and 12 % on config 3, which never meet an ambiguous window.
   auto probe_alternatives = [&](bool& found, uint64_t& meta, int& aw_size, int& aw_end, int& aw_win) -> int {
     if (!BATCH) {  // window g0 alone: lane t < W_size probes alternative t (class bytes in cA)
       const uint32_t wbits = __ballot_sync(0xffffffffu, (cA & 0xC0) == kClsAmb) & kmask, rest = wbits & (wbits - 1);
@@ -940,7 +940,7 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
         n_amb += 1;  // (matches inside the helpers are not counted: queryKmerMatchingDB is passed by value, :741-743)
         if (lane == 0) amb_info = (((tot_chunks + 1) >> 1) << 11) | ((uint32_t)aw_size << 20) | (lg << 26);
         if (!found) meta = kEmptyKey;  // (the consumer's global-memory walk takes the alternatives' entries as they are)
-        if (RP_UNLIKELY(bt.dump_key != nullptr) && lane == 0 && (!SLICED || pass == 0)) {
+        if (DUMP && bt.dump_key != nullptr && lane == 0 && (!SLICED || pass == 0)) {
           bt.dump_key[bt.dump_win_off[r] + (uint64_t)g0] = ~0ull;
           bt.dump_hits[bt.dump_win_off[r] + (uint64_t)g0] = -3;
         }
@@ -975,7 +975,7 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
         const uint32_t lanes_taken = end_taken >= 32 ? 0xffffffffu : ((1u << end_taken) - 1u);
         if (MODE == kXchg && lane < xv.n_parts) x_run += __popc(x_mask & lanes_taken);  // the answers of the windows taken
         n_amb += cons;  // (matches inside the helpers are not counted: queryKmerMatchingDB is passed by value, :741-743)
-        if (RP_UNLIKELY(bt.dump_key != nullptr) && lane < cons && (!SLICED || pass == 0)) {
+        if (DUMP && bt.dump_key != nullptr && lane < cons && (!SLICED || pass == 0)) {
           const uint64_t o = bt.dump_win_off[r] + (uint64_t)(g0 + lane);
           bt.dump_key[o] = ~0ull;
           bt.dump_hits[o] = -3;
@@ -1002,13 +1002,11 @@ __device__ __forceinline__ void producer(const AlphabetTables& c_alpha, const Db
         stagedm = __ballot_sync(0xffffffffu, sb != 0u) & lanes;
         n_match += __popc((SLICED ? __ballot_sync(0xffffffffu, found) : hitm) & lanes);
         n_skip += __popc(__ballot_sync(0xffffffffu, g_skip) & lanes);
-#ifndef RP_NO_DUMP
-        if (RP_UNLIKELY(bt.dump_key != nullptr) && lane < cons && (!SLICED || pass == 0)) {  // K1 + K2 as computed here
+        if (DUMP && bt.dump_key != nullptr && lane < cons && (!SLICED || pass == 0)) {  // K1 + K2 as computed here
           const uint64_t o = bt.dump_win_off[r] + (uint64_t)(g0 + lane);
           bt.dump_key[o] = g_plain ? ((uint64_t)io.klo | ((uint64_t)io.khi << 32)) : ~0ull;
           bt.dump_hits[o] = g_plain ? (found ? (int)(meta & 0xFFFF) : -1) : -2;
         }
-#endif
         if (MODE == kXchg && lane < xv.n_parts) x_run += __popc(x_mask & lanes);  // the answers of the windows taken
       }
       off = incl_bytes - sb;
@@ -1243,13 +1241,21 @@ constexpr int kPassTargetPairs = 7;
 constexpr int max_threads_for(bool sliced, int mode = kDirect) {
   return sliced ? kWantPairs * 64 : mode == kCuckoo ? RP_CUCKOO_PAIRS * 64 : kMaxThreads;
 }
-template <bool SLICED, int MODE>
+// DUMP: the diagnostic build of rp_place_windows (records the producer's keys and hits); a template parameter because
+// even a never-taken branch in the producer costs the plain cuckoo kernel 7-9 % (registers and code layout)
+template <bool SLICED, int MODE, bool DUMP = false, bool BATCH = SLICED>
 __global__ void __launch_bounds__(max_threads_for(SLICED, MODE), 1)
 place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_constant__ DbView db,
              const __grid_constant__ CfgView cfg, const __grid_constant__ BatchView bt,
              const __grid_constant__ XchgView xv, unsigned long long* work_counter, float* amb_S, int* amb_C, int n_pad, int per_pair_bytes,
-             int stage_bytes, int max_chunks, int slice, int n_pass) {
+             int stage_bytes, int max_chunks, int slice, int n_pass, unsigned int amb_thr) {
   extern __shared__ __align__(128) uint8_t smem[];
+  // sliced kernels come in two builds, launched back to back; work_counter[1] = ambiguity characters in the batch
+  // (amb_count_kernel) decides which of them does the work, the other returns at once
+  if (SLICED && amb_thr != 0xFFFFFFFFu) {
+    const bool many = (unsigned int)__ldcg(work_counter + 1) >= amb_thr;
+    if (many != BATCH) return;
+  }
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int pairs = blockDim.x >> 6;
@@ -1287,7 +1293,7 @@ place_kernel(const __grid_constant__ AlphabetTables c_alpha, const __grid_consta
   // local memory around them, and with ~227 KB of shared memory carved out there is no L1 left, so every
   // such spill was an L2 round trip: 20 % of the kernel time, profiles/r01_v5_spill_stalls.txt.)
   if (is_producer) {
-    producer<SLICED, MODE>(c_alpha, db, cfg, bt, xv, work_counter, w, smem_u32(smem), lane, n_pad, slice, n_pass);
+    producer<SLICED, MODE, DUMP, BATCH>(c_alpha, db, cfg, bt, xv, work_counter, w, smem_u32(smem), lane, n_pad, slice, n_pass);
   } else {
     const size_t gp = (size_t)blockIdx.x * pairs + pair;
     consumer<SLICED>(c_alpha, db, cfg, bt, w, amb_S + gp * n_pad, amb_C + gp * n_pad, n_pad, slice, lane);
@@ -1372,11 +1378,18 @@ __global__ void fill_f32_kernel(float* p, size_t n, float v) {
 // worth of posting blocks.  Trees whose S[] would leave fewer than kWantPairs reads per SM are walked in
 // node-range passes (S = one slice).  RP_STAGE_BYTES / RP_PASSES / RP_PAIRS_PER_SM override for tuning.
 typedef void (*place_kernel_t)(const AlphabetTables, const DbView, const CfgView, const BatchView, const XchgView,
-                               unsigned long long*, float*, int*, int, int, int, int, int, int);
-static place_kernel_t kernel_for(bool sliced, int mode) {
-  if (mode == kXchg) return sliced ? place_kernel<true, kXchg> : place_kernel<false, kXchg>;
-  if (mode == kDirect) return sliced ? place_kernel<true, kDirect> : place_kernel<false, kDirect>;
-  return sliced ? place_kernel<true, kCuckoo> : place_kernel<false, kCuckoo>;
+                               unsigned long long*, float*, int*, int, int, int, int, int, int, unsigned int);
+// batch: sliced kernels only -- the build whose ambiguous windows are batched (see producer)
+static place_kernel_t kernel_for(bool sliced, int mode, bool dump = false, bool batch = true) {
+  if (dump) {
+    if (mode == kDirect) return sliced ? place_kernel<true, kDirect, true> : place_kernel<false, kDirect, true>;
+    return sliced ? place_kernel<true, kCuckoo, true> : place_kernel<false, kCuckoo, true>;
+  }
+  if (!sliced) return mode == kXchg ? place_kernel<false, kXchg> : mode == kDirect ? place_kernel<false, kDirect> : place_kernel<false, kCuckoo>;
+  if (batch) return mode == kXchg ? place_kernel<true, kXchg, false, true> : mode == kDirect ? place_kernel<true, kDirect, false, true>
+                                                                                                : place_kernel<true, kCuckoo, false, true>;
+  return mode == kXchg ? place_kernel<true, kXchg, false, false> : mode == kDirect ? place_kernel<true, kDirect, false, false>
+                                                                                     : place_kernel<true, kCuckoo, false, false>;
 }
 static bool db_is_direct(const rp_db* db, const DeviceCtx* dc) {
   return !db->partitioned && !dc->parts.empty() && db->parts[dc->parts[0]].d_direct != nullptr;
@@ -1468,6 +1481,8 @@ int compute_geometry(const rp_db* db, DeviceCtx* dc) {
   g.warps_per_cta = pairs_cta * 2;
   g.smem_bytes = cta_fixed + pairs_cta * g.per_warp_bytes;
   RP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+  if (n_pass > 1)
+    RP_CUDA_TRY(cudaFuncSetAttribute(kernel_for(true, mode, false, false), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
   // what the hardware really keeps resident (registers may bind before shared memory does)
   int resident = 0;
   RP_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, g.warps_per_cta * 32, g.smem_bytes));
@@ -1495,7 +1510,7 @@ int ensure_stream_ctx(const rp_db* db, DeviceCtx* dc, StreamCtx* sc) {
   RP_CUDA_TRY(cudaMalloc((void**)&sc->d_amb_C, n * sizeof(int)));
   RP_CUDA_TRY(cudaMemset(sc->d_amb_S, 0, n * sizeof(float)));
   RP_CUDA_TRY(cudaMemset(sc->d_amb_C, 0, n * sizeof(int)));
-  RP_CUDA_TRY(cudaMalloc((void**)&sc->d_counter, sizeof(unsigned long long)));
+  RP_CUDA_TRY(cudaMalloc((void**)&sc->d_counter, 2 * sizeof(unsigned long long)));  // read scheduler, ambiguity count
   return RP_OK;
 }
 
@@ -1513,20 +1528,67 @@ static CfgView make_cfg_view(const rp_place_cfg* c) {
   return v;
 }
 
+// ambiguity characters of a batch (sliced kernels: picks the build that runs)
+__global__ void amb_count_kernel(const __grid_constant__ AlphabetTables c_alpha, const uint8_t* seq, const uint64_t* seq_off,
+                                 uint64_t seq_base, long long n_reads, unsigned long long* out) {
+  __shared__ uint8_t amb[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) amb[i] = (c_alpha.cls[i] & 0xC0) == kClsAmb && c_alpha.cls[i] != kClsBad;
+  __syncthreads();
+  const uint8_t* p = seq + (seq_off[0] - seq_base);
+  const uint64_t n = seq_off[n_reads] - seq_off[0];
+  const uint64_t head = std::min<uint64_t>(n, (16 - ((uintptr_t)p & 15)) & 15), body = (n - head) / 16;
+  unsigned int cnt = 0;
+  const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = tid; i < body; i += nth) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p + head) + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) cnt += amb[w[j] & 255] + amb[(w[j] >> 8) & 255] + amb[(w[j] >> 16) & 255] + amb[w[j] >> 24];
+  }
+  for (uint64_t i = tid; i < head; i += nth) cnt += amb[p[i]];
+  for (uint64_t i = head + body * 16 + tid; i < n; i += nth) cnt += amb[p[i]];
+  for (int d = 16; d; d >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, d);
+  if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(out, (unsigned long long)cnt);
+}
+
+// The launch(es) of one batch.  Plain trees: one kernel.  Sliced trees: count the batch's ambiguity characters, then
+// launch both builds of the kernel; the one the count selects proceeds (>= one such character per two reads: the
+// build that batches ambiguous windows), the other returns at once -- no host round trip.
+static int launch_variants(const rp_db* db, DeviceCtx* dc, int mode, const DbView& view, const rp_place_cfg* cfg, const BatchView& bt,
+                           const XchgView& xv, unsigned long long* d_counter, float* d_amb_S, int* d_amb_C, int grid,
+                           cudaStream_t stream) {
+  const LaunchGeom& g = dc->geom;
+  const bool sliced = g.n_pass > 1, dump = bt.dump_key != nullptr;
+  RP_CUDA_TRY(cudaMemsetAsync(d_counter, 0, 2 * sizeof(unsigned long long), stream));
+  unsigned int thr = 0xFFFFFFFFu;
+  if (sliced && !dump) {
+    amb_count_kernel<<<dc->sm_count * 4, 256, 0, stream>>>(db->alpha, bt.seq, bt.seq_off, bt.seq_base, bt.n_reads, d_counter + 1);
+    g_kernel_launches.fetch_add(1);
+    thr = (unsigned int)std::max<long long>(1, bt.n_reads / 2);
+    if (getenv("RP_AMB_BATCH")) thr = atoi(getenv("RP_AMB_BATCH")) ? 0u : 0xFFFFFFFEu;  // tests: force one build
+  }
+  for (int b = 0; b < (sliced && !dump ? 2 : 1); b++) {
+    place_kernel_t kern = kernel_for(sliced, mode, dump, b == 1 || !sliced || dump);
+    if (dump) RP_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem_bytes));
+    kern<<<grid, g.warps_per_cta * 32, g.smem_bytes, stream>>>(db->alpha, view, make_cfg_view(cfg), bt, xv, d_counter, d_amb_S,
+                                                                 d_amb_C, g.n_pad, (int)g.per_warp_bytes, g.stage_bytes,
+                                                                 g.max_chunks, g.slice, g.n_pass, thr);
+    RP_CUDA_TRY(cudaGetLastError());
+    g_kernel_launches.fetch_add(1);
+  }
+  return RP_OK;
+}
+
 // enqueue the placement kernel for one device-resident batch on `stream`
 static int launch_place(const rp_db* db, DeviceCtx* dc, StreamCtx* sc, const rp_place_cfg* cfg, const BatchView& bt,
                         cudaStream_t stream, bool time_it) {
   const LaunchGeom& g = dc->geom;
-  RP_CUDA_TRY(cudaMemsetAsync(sc->d_counter, 0, sizeof(unsigned long long), stream));
-  if (time_it) RP_CUDA_TRY(cudaEventRecord(sc->ev_k0, stream));
-  place_kernel_t kern = kernel_for(g.n_pass > 1, db_is_direct(db, dc) ? kDirect : kCuckoo);
   XchgView xv;
   memset(&xv, 0, sizeof xv);
-  kern<<<g.grid, g.warps_per_cta * 32, g.smem_bytes, stream>>>(
-      db->alpha, make_db_view(db, dc), make_cfg_view(cfg), bt, xv, sc->d_counter, sc->d_amb_S, sc->d_amb_C, g.n_pad,
-      (int)g.per_warp_bytes, g.stage_bytes, g.max_chunks, g.slice, g.n_pass);
-  RP_CUDA_TRY(cudaGetLastError());
-  g_kernel_launches.fetch_add(1);
+  if (time_it) RP_CUDA_TRY(cudaEventRecord(sc->ev_k0, stream));
+  int rc = launch_variants(db, dc, db_is_direct(db, dc) ? kDirect : kCuckoo, make_db_view(db, dc), cfg, bt, xv, sc->d_counter,
+                           sc->d_amb_S, sc->d_amb_C, g.grid, stream);
+  if (rc) return rc;
   if (time_it) RP_CUDA_TRY(cudaEventRecord(sc->ev_k1, stream));
   return RP_OK;
 }
@@ -1535,16 +1597,9 @@ int launch_place_xchg(const rp_db* db, DeviceCtx* dc, const rp_place_cfg* cfg, c
                       const XchgView& xv, unsigned long long* d_counter, float* d_amb_S, int* d_amb_C, int grid_sms,
                       cudaStream_t stream) {
   const LaunchGeom& g = dc->geom;
-  RP_CUDA_TRY(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream));
-  place_kernel_t kern = kernel_for(g.n_pass > 1, kXchg);
   int grid = g.grid;
   if (grid_sms > 0) grid = std::min(grid, grid_sms * g.ctas_per_sm);
-  kern<<<grid, g.warps_per_cta * 32, g.smem_bytes, stream>>>(db->alpha, view, make_cfg_view(cfg), bt, xv, d_counter, d_amb_S,
-                                                               d_amb_C, g.n_pad, (int)g.per_warp_bytes, g.stage_bytes,
-                                                               g.max_chunks, g.slice, g.n_pass);
-  RP_CUDA_TRY(cudaGetLastError());
-  g_kernel_launches.fetch_add(1);
-  return RP_OK;
+  return launch_variants(db, dc, kXchg, view, cfg, bt, xv, d_counter, d_amb_S, d_amb_C, grid, stream);
 }
 
 template <typename T>

@@ -337,14 +337,17 @@ def test_node_range_passes_and_table_forms(name, env, monkeypatch):
 
 
 @pytest.mark.parametrize("env", [dict(RP_STAGE_BYTES="1024"), dict(RP_STAGE_BYTES="16384"), dict(RP_PASSES="2"),
-                                 dict(RP_PASSES="4", RP_STAGE_BYTES="2048")],
+                                 dict(RP_PASSES="4", RP_STAGE_BYTES="2048"), dict(RP_PASSES="2", RP_AMB_BATCH="0"),
+                                 dict(RP_PASSES="3", RP_AMB_BATCH="1", RP_STAGE_BYTES="1536")],
                          ids=lambda e: ",".join("%s=%s" % kv for kv in sorted(e.items())))
 @pytest.mark.parametrize("name", ["nucl_k6_ambig", "nucl_k10_long_lists", "nucl_k16_two_ambig", "amino_k3"])
 def test_ambiguous_windows_staged_and_from_global_memory(name, env, monkeypatch):
     """An ambiguous window is a group of its own: its alternatives' blocks are staged and S_amb / C_amb is a
     table in the stage's tail -- or, when they do not fit, the consumer walks them in global memory.  The
     geometry knobs (read when the DB is loaded) push the same reads down both branches, and through 2 and 4
-    node-range passes (the table then holds the nodes of the pass's slice only)."""
+    node-range passes (the table then holds the nodes of the pass's slice only).  Sliced trees have two builds of the
+    kernel -- ambiguous windows one per group, or up to eight consecutive ones per group -- and a count of the batch's
+    ambiguity characters picks one on the device; RP_AMB_BATCH forces either."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     spec = CASES[name]
