@@ -1420,7 +1420,8 @@ int compute_geometry(const rp_db* db, DeviceCtx* dc) {
   };
   int n_pass = 1;
   for (; n_pass < kMaxPasses; n_pass++)
-    if ((optin - cta_fixed) / pair_bytes(stage_for(n_pass), slice_for(n_pass)) >= (size_t)kPassTargetPairs) break;
+    // (with the stage as small as the adjustment below may make it: three quarters of the nominal one)
+    if ((optin - cta_fixed) / pair_bytes((stage_for(n_pass) * 3 / 4 + 127) & ~127L, slice_for(n_pass)) >= (size_t)kPassTargetPairs) break;
   if (const char* e = getenv("RP_PASSES")) n_pass = std::max(1, std::min(kMaxPasses, atoi(e)));
   while (n_pass > 1 && slice_for(n_pass) == slice_for(n_pass - 1)) n_pass--;  // no empty slices
   g.n_pass = n_pass;
