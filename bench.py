@@ -503,6 +503,9 @@ def run_config5(ctx):
                           np.zeros(0, np.uint16), np.zeros(0, np.float32))
     rb = synth.make_reads(proxy, n, w.read_len, seed=1042 + w.index + 7919 * rank, mode="uniform", iupac_rate=w.iupac_rate,
                           n_rate=w.n_rate)
+    # page-locked copies of the batch, as a caller that used rp_host_alloc would hold it
+    _pin = [torch.from_numpy(rb.seq).pin_memory(), torch.from_numpy(rb.seq_off.view(np.int64)).pin_memory()]
+    rb = synth.ReadBatch(_pin[0].numpy(), _pin[1].numpy().view(np.uint64))
     cfg = _abi.place_cfg()
     K = cfg.keep_at_most
     t0 = time.perf_counter()

@@ -32,6 +32,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "rp_common.h"
@@ -582,6 +583,15 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
   auto dev = [&](int l) { return cudaSetDevice(R(l)->dc->device); };
   const bool direct_local = !getenv("RP_XCHG_COPY_LOCAL");  // a rank reads its own partition's blocks in place
   int rc;
+  // RP_XCHG_DEBUG: wall clock of the phases (each ends with a synchronisation of the ranks' streams)
+  const bool dbg = getenv("RP_XCHG_DEBUG") != nullptr;
+  auto t_prev = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!dbg) return;
+    const auto t = std::chrono::steady_clock::now();
+    fprintf(stderr, "rp_xchg[%d] %-28s %8.2f ms\n", x->ranks[0]->rank, what, std::chrono::duration<double, std::milli>(t - t_prev).count());
+    t_prev = t;
+  };
   // ---- 0/1: reads to the device, count the probes per (read, owner), column scans
   for (int l = 0; l < L; l++) {
     XRank* r = R(l);
@@ -613,6 +623,7 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
     RP_CUDA_TRY(cudaMemcpyAsync(r->h_tot.data(), r->tot.p, W * 4, cudaMemcpyDeviceToHost, r->sC));
   }
   for (int l = 0; l < L; l++) { RP_CUDA_TRY(dev(l)); RP_CUDA_TRY(cudaStreamSynchronize(R(l)->sC)); }
+  lap("h2d + count + column scan");
   // ---- sub-batches: about RP_XCHG_PROBES probes each (their posting blocks are what the pipeline buffers hold)
   uint64_t target = 8u << 20;
   if (const char* e = getenv("RP_XCHG_PROBES")) target = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));
@@ -645,6 +656,7 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
   for (int l = 0; l < L; l++) { v[l].assign((size_t)J * W, 0); for (size_t i = 0; i < v[l].size(); i++) v[l][i] = R(l)->h_seg[i]; }
   std::vector<uint64_t> S;
   if ((rc = host_allgather(x, v, (size_t)J * W, S))) return rc;
+  lap("sub-batch plan (2 all-gathers)");
   auto Sat = [&](int w, int j, int o) { return S[((size_t)w * J + j) * W + o]; };
   // ---- 2: keys to their owners
   A2A a2a;
@@ -737,6 +749,7 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
     for (int p = 0; p < W; p++)
       for (int j = 0; j < J; j++) v[l][(size_t)p * J + j] = bvals[l][(size_t)p * J + j + 1] - bvals[l][(size_t)p * J + j];
   }
+  lap("fill + keys a2a + lookup + scan");
   std::vector<uint64_t> U;  // U[(o * W + p) * J + j] = units owner o sends home p for sub-batch j
   if ((rc = host_allgather(x, v, (size_t)W * J, U))) return rc;
   auto Uat = [&](int o, int p, int j) { return U[((size_t)o * W + p) * J + j]; };
@@ -790,6 +803,7 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
       return rc;
   }
   for (int l = 0; l < L; l++) { RP_CUDA_TRY(dev(l)); RP_CUDA_TRY(cudaStreamSynchronize(R(l)->sC)); }
+  lap("answers a2a + home meta");
   // ---- 4 + 5: pack | all-to-all | placement, pipelined over the sub-batches (buffers j & 1)
   for (int j = 0; j < J; j++) {
     const int b = j & 1;
@@ -893,6 +907,9 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
     RP_CUDA_TRY(cudaEventElapsedTime(&ms, R(l)->ev0, R(l)->ev1));
     ms_max = std::max<double>(ms_max, ms);
   }
+  lap("pack | a2a | placement pipeline");
+  if (dbg) fprintf(stderr, "rp_xchg[%d] J=%d sub-batches, %llu probes sent, %.2f GB received\n", x->ranks[0]->rank, J,
+                   (unsigned long long)probes_total, payload_total / 1e9);
   x->last_ms = ms_max;
   x->last_probes = probes_total;
   x->last_payload = payload_total;
