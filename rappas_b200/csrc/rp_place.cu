@@ -1399,7 +1399,8 @@ int compute_geometry(const rp_db* db, DeviceCtx* dc) {
   LaunchGeom g;
   g.n_pad = (db->desc.n_nodes + 127) & ~127;
   const size_t cta_fixed = 256;
-  const size_t optin = dc->smem_optin;         // 227 KB on sm_100
+  // (exchange form: 4 KB are left to the pack kernel's CTAs, which run beside the placement CTA: rp_xchg.cu)
+  const size_t optin = dc->smem_optin - (db->xchg ? 4096 : 0);  // 227 KB on sm_100
   const size_t sm_total = optin + 1024;        // 228 KB per SM, 1 KB reserved per resident CTA
   // (exchange form: the handle holds one partition, and the kernel gathers what the owners sent -- same mean)
   const uint64_t keys_here = db->xchg ? db->parts[dc->local_part].n_keys : db->desc.n_keys;

@@ -336,8 +336,12 @@ __global__ void __launch_bounds__(kScanThreads) xk_scan_tiles(const uint32_t* in
 // dbase + uoff[i] - uoff[i0].  A warp takes 32 probes and copies their blocks one after the other, 16 B per lane.
 struct PackSeg { size_t i0, i1; uint8_t* dst; uint64_t dbase; };
 struct PackArgs { PackSeg seg[kMaxParts]; int n_seg; };
-__global__ void __launch_bounds__(256) xk_pack(const __grid_constant__ PackArgs a, const uint8_t* blocks, const uint64_t* ometa,
-                                               const uint32_t* units, const uint32_t* uoff) {
+// 128-thread CTAs of <= 40 registers and no shared memory: one of them fits on an SM BESIDE a placement CTA (which
+// leaves 4 KB of shared memory and ~12 k registers in the exchange form), so the pack of sub-batch j+1 runs in the
+// memory and issue slots the placement of sub-batch j leaves idle instead of waiting for a free SM.
+constexpr int kPackThreads = 128;
+__global__ void __launch_bounds__(kPackThreads, 8) xk_pack(const __grid_constant__ PackArgs a, const uint8_t* blocks, const uint64_t* ometa,
+                                                           const uint32_t* units, const uint32_t* uoff) {
   const PackSeg sg = a.seg[blockIdx.y];
   const int lane = threadIdx.x & 31;
   const size_t warps = (size_t)gridDim.x * (blockDim.x >> 5);
@@ -824,8 +828,8 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
         most = std::max(most, i1 - i0);
       }
       if (pa.n_seg) {
-        dim3 grid(grid_for(most, 8, r->dc->sm_count), pa.n_seg);
-        xk_pack<<<grid, 256, 0, r->sP>>>(pa, r->db->parts[me].d_blocks, r->ometa.p, r->units.p, r->uoff.p);
+        dim3 grid(std::max(1, std::min<int>((int)((most + 127) / 128), r->dc->sm_count * 8 / pa.n_seg + 1)), pa.n_seg);
+        xk_pack<<<grid, kPackThreads, 0, r->sP>>>(pa, r->db->parts[me].d_blocks, r->ometa.p, r->units.p, r->uoff.p);
         g_kernel_launches.fetch_add(1);
         RP_CUDA_TRY(cudaGetLastError());
       }
