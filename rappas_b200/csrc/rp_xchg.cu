@@ -629,7 +629,7 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
   for (int l = 0; l < L; l++) { RP_CUDA_TRY(dev(l)); RP_CUDA_TRY(cudaStreamSynchronize(R(l)->sC)); }
   lap("h2d + count + column scan");
   // ---- sub-batches: about RP_XCHG_PROBES probes each (their posting blocks are what the pipeline buffers hold)
-  uint64_t target = 8u << 20;
+  uint64_t target = 16u << 20;  // (2 GPUs, config-5 shape: 2 M / 8 M / 16 M / 32 M / one batch = 34 / 26 / 26 / 26 / 34 ms of pipeline)
   if (const char* e = getenv("RP_XCHG_PROBES")) target = std::max<uint64_t>(1024, strtoull(e, nullptr, 10));
   std::vector<std::vector<uint64_t>> v(L);
   for (int l = 0; l < L; l++) {
@@ -947,7 +947,7 @@ int rp_xchg_create(rp_db* partition, int32_t rank, int32_t world, const uint8_t*
   rp_xchg* x = new rp_xchg();
   x->world = world;
   x->ranks.push_back(R);
-  x->reserve_sms = 16;
+  x->reserve_sms = 8;
   if (const char* e = getenv("RP_XCHG_RESERVE_SMS")) x->reserve_sms = atoi(e);
   ncclUniqueId uid;
   memcpy(&uid, id, sizeof uid);

@@ -3,7 +3,7 @@ mkdir -p gpurun_out; rm -f gpurun_out/c8g_*.json
 nvidia-smi topo -m | head -12 > gpurun_out/c8g_topo.txt
 run() { # tag args...
   tag=$1; shift
-  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29$((RANDOM % 800 + 100)) \
+  timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29$((RANDOM % 800 + 100)) \
     bench.py --gpus 8 "$@" > gpurun_out/c8g_$tag.json 2> gpurun_out/c8g_$tag.err
   python - <<PY
 import json
@@ -14,7 +14,7 @@ except Exception as e:
     print('$tag FAILED', e); print(open('gpurun_out/c8g_$tag.err').read()[-2000:])
 PY
 }
-run cfg5_xchg --config 5 --steps 3 --warmup 1
-run cfg5_xchg_noamb --config 5 --steps 2 --warmup 1 --no-ambiguity
+export RP_XCHG_DEBUG=1
+run cfg5_xchg --config 5 --steps 2 --warmup 1
+grep "rp_xchg\[0\]" gpurun_out/c8g_cfg5_xchg.err | tail -7 | cut -c1-80
 run cfg3 --steps 5 --warmup 3 --no-cpu
-run cfg2 --config 2 --steps 10 --warmup 3 --no-cpu
