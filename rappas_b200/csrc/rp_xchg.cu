@@ -431,6 +431,12 @@ struct rp_xchg {
   bool local = false;
   ncclComm_t comm = nullptr;
   DBuf<uint64_t> gather_dev;   // NCCL: staging of the small host all-gathers
+  DBuf<uint64_t> bar_dev;      // NCCL: the 8-byte all-gathers that serve as barriers on a stream
+  // push mode: the receive buffers of every rank, mapped into this process (CUDA IPC); [rank][buffer]
+  bool push = false;
+  uint8_t* peer_recv[kMaxParts][2] = {};
+  cudaIpcMemHandle_t peer_handle[kMaxParts][2] = {};
+  bool peer_open[kMaxParts][2] = {};
   int reserve_sms = 0;
   double last_ms = 0.0;
   uint64_t last_probes = 0, last_payload = 0, last_hits = 0, last_postings = 0;
@@ -500,6 +506,47 @@ static int alltoallv(rp_xchg* x, const A2A& a, std::vector<cudaStream_t> streams
   RP_NCCL_TRY(N->GroupEnd());
   if (a.scnt[0][me])
     RP_CUDA_TRY(cudaMemcpyAsync(a.recv[0] + a.roff[0][me], a.send[0] + a.soff[0][me], a.scnt[0][me], cudaMemcpyDeviceToDevice, streams[0]));
+  return RP_OK;
+}
+
+// every rank's stream passes this point only after all ranks' streams have reached it (NCCL mode)
+static int stream_barrier(rp_xchg* x, cudaStream_t st) {
+  int rc = x->bar_dev.ensure((size_t)x->world + 1);
+  if (rc) return rc;
+  RP_NCCL_TRY(nccl_api()->AllGather(x->bar_dev.p + x->world, x->bar_dev.p, 1, ncclUint64, x->comm, st));
+  return RP_OK;
+}
+
+// push mode: (re)map the ranks' receive buffers (their owners may have re-allocated them for this batch)
+static int map_peer_buffers(rp_xchg* x) {
+  const int W = x->world;
+  if (x->local) {
+    for (int p = 0; p < W; p++)
+      for (int b = 0; b < 2; b++) x->peer_recv[p][b] = x->ranks[p]->recvpay[b].p;
+    return RP_OK;
+  }
+  XRank* R = x->ranks[0];
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  std::vector<std::vector<uint64_t>> v(1, std::vector<uint64_t>(16, 0));
+  for (int b = 0; b < 2; b++) {
+    cudaIpcMemHandle_t h;
+    RP_CUDA_TRY(cudaIpcGetMemHandle(&h, R->recvpay[b].p));
+    memcpy(v[0].data() + 8 * b, &h, 64);
+  }
+  std::vector<uint64_t> all;
+  int rc = host_allgather(x, v, 16, all);
+  if (rc) return rc;
+  for (int p = 0; p < W; p++)
+    for (int b = 0; b < 2; b++) {
+      if (p == R->rank) { x->peer_recv[p][b] = R->recvpay[b].p; continue; }
+      cudaIpcMemHandle_t h;
+      memcpy(&h, all.data() + (size_t)p * 16 + 8 * b, 64);
+      if (x->peer_open[p][b] && memcmp(&h, &x->peer_handle[p][b], 64) == 0) continue;
+      if (x->peer_open[p][b]) { cudaIpcCloseMemHandle(x->peer_recv[p][b]); x->peer_open[p][b] = false; }
+      RP_CUDA_TRY(cudaIpcOpenMemHandle((void**)&x->peer_recv[p][b], h, cudaIpcMemLazyEnablePeerAccess));
+      x->peer_handle[p][b] = h;
+      x->peer_open[p][b] = true;
+    }
   return RP_OK;
 }
 
@@ -778,7 +825,8 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
     r->pp = plan_payload(W, J, me, direct_local, U.data());
     payload_total += r->pp.recv_total * kBlockAlign;
     for (int b = 0; b < 2; b++)
-      if ((rc = r->recvpay[b].ensure(r->pp.recv_cap * kBlockAlign + 512)) || (rc = r->sendpay[b].ensure(r->pp.send_cap * kBlockAlign + 512))) return rc;
+      if ((rc = r->recvpay[b].ensure(r->pp.recv_cap * kBlockAlign + 512)) ||
+          (!x->push && (rc = r->sendpay[b].ensure(r->pp.send_cap * kBlockAlign + 512)))) return rc;
     if (ns) {
       xk_answer_units<<<grid_for(ns, 256, r->dc->sm_count), 256, 0, r->sC>>>(r->answer_in.p, ns, r->aunits.p);
       g_kernel_launches.fetch_add(1);
@@ -808,8 +856,76 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
   }
   for (int l = 0; l < L; l++) { RP_CUDA_TRY(dev(l)); RP_CUDA_TRY(cudaStreamSynchronize(R(l)->sC)); }
   lap("answers a2a + home meta");
+  // PUSH MODE (default; RP_XCHG_PUSH=0 = the NCCL all-to-all of the blocks): owners write the posting blocks they gather
+  // straight into the homes' receive buffers over peer memory.  The pack kernel's small CTAs run BESIDE the
+  // placement CTAs, so the transfer of sub-batch j+1 really overlaps the placement of sub-batch j; an NCCL
+  // send/recv kernel cannot (it needs SMs of its own, which a persistent placement kernel does not give back before
+  // it ends: measured, the pipeline took accumulate + transfer whatever the settings), and sequential peer WRITES
+  // have none of the translation trouble of random peer gathers.  Two 8-byte all-gathers per sub-batch are the
+  // barriers: "every home has consumed buffer b" before the pushes, "every owner has pushed" before the placement.
+  if (x->push) {
+    if ((rc = map_peer_buffers(x))) return rc;
+    std::vector<std::vector<XPayPlan>> home_plan(L);  // [local rank][home p]: where my blocks land in p's buffer
+    for (int l = 0; l < L; l++)
+      for (int p = 0; p < W; p++) home_plan[l].push_back(plan_payload(W, J, p, direct_local, U.data()));
+    for (int j = 0; j < J; j++) {
+      const int b = j & 1;
+      for (int l = 0; l < L; l++) {  // owners: barrier 1, push
+        XRank* r = R(l);
+        RP_CUDA_TRY(dev(l));
+        const int me = r->rank;
+        if (j >= 2) {
+          if (x->local) { for (int l2 = 0; l2 < L; l2++) RP_CUDA_TRY(cudaStreamWaitEvent(r->sP, R(l2)->evAcc[b], 0)); }
+          else { RP_CUDA_TRY(cudaStreamWaitEvent(r->sP, r->evAcc[b], 0)); if ((rc = stream_barrier(x, r->sP))) return rc; }
+        }
+        PackArgs pa;
+        memset(&pa, 0, sizeof pa);
+        size_t most = 0;
+        for (int p = 0; p < W; p++) {
+          if (!r->pp.send_cnt[(size_t)j * W + p]) continue;
+          const size_t i0 = bnd[l][(size_t)p * J + j], i1 = bnd[l][(size_t)p * J + j + 1];
+          pa.seg[pa.n_seg++] = PackSeg{i0, i1, x->peer_recv[p][b], home_plan[l][p].recv_off[(size_t)j * W + me]};
+          most = std::max(most, i1 - i0);
+        }
+        if (pa.n_seg) {
+          dim3 grid(std::max(1, std::min<int>((int)((most + 127) / 128), r->dc->sm_count * 8 / pa.n_seg + 1)), pa.n_seg);
+          xk_pack<<<grid, kPackThreads, 0, r->sP>>>(pa, r->db->parts[me].d_blocks, r->ometa.p, r->units.p, r->uoff.p);
+          g_kernel_launches.fetch_add(1);
+          RP_CUDA_TRY(cudaGetLastError());
+        }
+        if (!x->local && (rc = stream_barrier(x, r->sP))) return rc;  // barrier 2
+        RP_CUDA_TRY(cudaEventRecord(r->evPack[b], r->sP));
+      }
+      for (int l = 0; l < L; l++) {  // homes: placement
+        XRank* r = R(l);
+        RP_CUDA_TRY(dev(l));
+        const int me = r->rank;
+        if (x->local) { for (int l2 = 0; l2 < L; l2++) RP_CUDA_TRY(cudaStreamWaitEvent(r->sC, R(l2)->evPack[b], 0)); }
+        else RP_CUDA_TRY(cudaStreamWaitEvent(r->sC, r->evPack[b], 0));
+        const long long r0 = std::min<long long>(r->n, (long long)j * r->B), r1 = std::min<long long>(r->n, r0 + r->B);
+        if (r1 > r0) {
+          DbView view = make_db_view(r->db, r->dc);
+          view.n_parts = W; view.table_parts = 1; view.direct = nullptr;
+          for (int o = 0; o < W; o++) view.blocks[o] = (direct_local && o == me) ? r->db->parts[me].d_blocks : r->recvpay[b].p;
+          BatchView bt;
+          memset(&bt, 0, sizeof bt);
+          bt.seq = r->seq.p; bt.seq_off = r->off.p + r0; bt.seq_base = 0; bt.n_reads = r1 - r0;
+          bt.n_rows = r->o_n_rows.p + r0; bt.node = r->o_node.p + r0 * K; bt.score = r->o_score.p + r0 * K;
+          bt.lwr = r->o_lwr.p + r0 * K; bt.counts = io[l].counts ? r->o_counts.p + 4 * r0 : nullptr; bt.status = r->o_status.p + r0;
+          XchgView xv;
+          memset(&xv, 0, sizeof xv);
+          for (int o = 0; o < W; o++) xv.rmeta[o] = r->rmeta.p + r->kp.send_off[o];
+          xv.base = r->base.p + (size_t)r0 * W;
+          xv.n_parts = W;
+          const int sms = (x->reserve_sms > 0 && !x->local) ? std::max(1, r->dc->sm_count - x->reserve_sms) : 0;
+          if ((rc = launch_place_xchg(r->db, r->dc, cfg, view, bt, xv, r->sc.d_counter, r->sc.d_amb_S, r->sc.d_amb_C, sms, r->sC))) return rc;
+        }
+        RP_CUDA_TRY(cudaEventRecord(r->evAcc[b], r->sC));
+      }
+    }
+  }
   // ---- 4 + 5: pack | all-to-all | placement, pipelined over the sub-batches (buffers j & 1)
-  for (int j = 0; j < J; j++) {
+  for (int j = 0; j < (x->push ? 0 : J); j++) {
     const int b = j & 1;
     // pack (owner side)
     for (int l = 0; l < L; l++) {
@@ -948,6 +1064,7 @@ int rp_xchg_create(rp_db* partition, int32_t rank, int32_t world, const uint8_t*
   x->world = world;
   x->ranks.push_back(R);
   x->reserve_sms = 8;
+  x->push = !(getenv("RP_XCHG_PUSH") && atoi(getenv("RP_XCHG_PUSH")) == 0);
   if (const char* e = getenv("RP_XCHG_RESERVE_SMS")) x->reserve_sms = atoi(e);
   ncclUniqueId uid;
   memcpy(&uid, id, sizeof uid);
@@ -968,6 +1085,7 @@ int rp_xchg_create_local(rp_db** partitions, int32_t world, rp_xchg** out) {
   rp_xchg* x = new rp_xchg();
   x->world = world;
   x->local = true;
+  x->push = !(getenv("RP_XCHG_PUSH") && atoi(getenv("RP_XCHG_PUSH")) == 0);
   for (int p = 0; p < world; p++) {
     XRank* R = nullptr;
     int rc = adopt_partition(partitions[p], p, world, &R);
@@ -980,6 +1098,13 @@ int rp_xchg_create_local(rp_db** partitions, int32_t world, rp_xchg** out) {
 
 void rp_xchg_free(rp_xchg* x) {
   if (!x) return;
+  if (!x->local && !x->ranks.empty() && cudaSetDevice(x->ranks[0]->dc->device) == cudaSuccess) {
+    cudaDeviceSynchronize();
+    for (int p = 0; p < kMaxParts; p++)
+      for (int b = 0; b < 2; b++)
+        if (x->peer_open[p][b]) cudaIpcCloseMemHandle(x->peer_recv[p][b]);
+  }
+  x->bar_dev.release();
   for (XRank* R : x->ranks) free_rank(R);
   if (x->comm && nccl_api()) nccl_api()->CommDestroy(x->comm);
   x->gather_dev.release();

@@ -65,7 +65,9 @@ def _xchg_worker(rank, world, port, tmp):
     try:
         ids = [exchange.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, 0)
-        os.environ["RP_XCHG_PROBES"] = "300000"  # several sub-batches: the three-stream pipeline
+        os.environ["RP_XCHG_PROBES"] = "300000"  # several sub-batches: the pipeline and its buffer hand-over
+        if os.environ.get("RP_TEST_XCHG_PUSH") is not None:
+            os.environ["RP_XCHG_PUSH"] = os.environ["RP_TEST_XCHG_PUSH"]
         # (a) host-built DB, every rank uploads only its partition
         db = synth.make_db(0, 10, 1999, n_keys=150000, mean_postings=24, seed=7)
         rb = synth.make_reads(db, 3000 + 500 * rank, (50, 400), seed=100 + rank, iupac_rate=0.004, n_rate=0.002)
@@ -105,11 +107,13 @@ def _xchg_worker(rank, world, port, tmp):
         dist.destroy_process_group()
 
 
-def test_exchange_form_one_process_per_gpu_over_nccl(tmp_path):
+@pytest.mark.parametrize("push", ["1", "0"], ids=["push over peer memory", "nccl all-to-all of the blocks"])
+def test_exchange_form_one_process_per_gpu_over_nccl(tmp_path, push, monkeypatch):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
         pytest.skip("needs >= 2 GPUs")
+    monkeypatch.setenv("RP_TEST_XCHG_PUSH", push)
     world = min(torch.cuda.device_count(), 4)
     mp.spawn(_xchg_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / ("ok%d" % r)).exists() for r in range(world))
