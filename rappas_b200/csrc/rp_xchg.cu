@@ -333,34 +333,58 @@ __global__ void __launch_bounds__(kScanThreads) xk_scan_tiles(const uint32_t* in
 }
 
 // Step 4.  Copies the posting blocks of the probes [i0, i1) (those that hit) into dst: block i at 32 B unit
-// dbase + uoff[i] - uoff[i0].  A warp takes 32 probes and copies their blocks one after the other, 16 B per lane.
+// dbase + uoff[i] - uoff[i0].  A warp takes 32 probes; their blocks are consecutive in the destination (uoff is a
+// running sum), so the warp's work is ONE contiguous run of 16 B pieces: piece q belongs to the probe whose running
+// sum first exceeds q (a 5-step search over the lanes' sums), every lane moves a piece per step whatever the block
+// sizes, and kPackUnroll independent loads are in flight per lane.  (First form: the blocks one after the other, 16 B
+// per lane -- a 288 B block kept 18 lanes busy for one dependent load -> store round trip: 0.5 TB/s, and at 8 GPUs the
+// pack of 22 GB per rank and batch was 40 % of the pipeline.)
 struct PackSeg { size_t i0, i1; uint8_t* dst; uint64_t dbase; };
 struct PackArgs { PackSeg seg[kMaxParts]; int n_seg; };
-// 128-thread CTAs of <= 40 registers and no shared memory: one of them fits on an SM BESIDE a placement CTA (which
+// 128-thread CTAs of <= 64 registers and no shared memory: one of them fits on an SM BESIDE a placement CTA (which
 // leaves 4 KB of shared memory and ~12 k registers in the exchange form), so the pack of sub-batch j+1 runs in the
 // memory and issue slots the placement of sub-batch j leaves idle instead of waiting for a free SM.
 constexpr int kPackThreads = 128;
-__global__ void __launch_bounds__(kPackThreads, 8) xk_pack(const __grid_constant__ PackArgs a, const uint8_t* blocks, const uint64_t* ometa,
-                                                           const uint32_t* units, const uint32_t* uoff) {
+constexpr int kPackUnroll = 4;
+__global__ void __launch_bounds__(kPackThreads, 8) xk_pack(const __grid_constant__ PackArgs a, const uint8_t* __restrict__ blocks,
+                                                           const uint64_t* __restrict__ ometa, const uint32_t* __restrict__ units,
+                                                           const uint32_t* __restrict__ uoff) {
   const PackSeg sg = a.seg[blockIdx.y];
   const int lane = threadIdx.x & 31;
   const size_t warps = (size_t)gridDim.x * (blockDim.x >> 5);
   const uint32_t u0 = sg.i0 < sg.i1 ? uoff[sg.i0] : 0u;
   for (size_t w = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); sg.i0 + w * 32 < sg.i1; w += warps) {
     const size_t i = sg.i0 + w * 32 + lane;
-    uint64_t src = 0, dst = 0;
-    uint32_t nu = 0;
+    uint64_t src = 0;
+    uint32_t n16 = 0, first = 0;  // this probe's pieces, and the piece of the warp's run its block starts at
     if (i < sg.i1) {
-      nu = units[i];
+      n16 = 2u * units[i];
       src = (ometa[i] >> 16) & kMetaOffMask;
-      dst = sg.dbase + (uoff[i] - u0);
+      first = 2u * (uoff[i] - u0);
     }
-    for (uint32_t todo = __ballot_sync(0xffffffffu, nu != 0u); todo; todo &= todo - 1) {
-      const int t = __ffs(todo) - 1;
-      const uint32_t n16 = 2u * __shfl_sync(0xffffffffu, nu, t);
-      const uint4* sp = reinterpret_cast<const uint4*>(blocks) + 2 * __shfl_sync(0xffffffffu, src, t);
-      uint4* dp = reinterpret_cast<uint4*>(sg.dst) + 2 * __shfl_sync(0xffffffffu, dst, t);
-      for (uint32_t q = lane; q < n16; q += 32) dp[q] = __ldg(sp + q);
+    const uint32_t run0 = __shfl_sync(0xffffffffu, first, 0);  // lane 0's block starts the run (i0 + 32 w <= i1 - 1)
+    first -= run0;
+    const uint32_t end = i < sg.i1 ? first + n16 : 0xFFFFFFFFu;  // running sum after this probe (lanes past i1: never chosen)
+    const uint32_t total = __reduce_max_sync(0xffffffffu, i < sg.i1 ? first + n16 : 0u);
+    uint4* const dp = reinterpret_cast<uint4*>(sg.dst) + 2 * sg.dbase + run0;
+    for (uint32_t base = 0; base < total; base += 32 * kPackUnroll) {
+      uint4 v[kPackUnroll];
+#pragma unroll
+      for (int u = 0; u < kPackUnroll; u++) {
+        const uint32_t q = base + 32 * u + lane;
+        int t = 0;
+#pragma unroll
+        for (int d = 16; d; d >>= 1)
+          if (__shfl_sync(0xffffffffu, end, t + d - 1) <= q) t += d;
+        const uint32_t f = __shfl_sync(0xffffffffu, first, t);
+        const uint64_t sb = __shfl_sync(0xffffffffu, src, t);
+        if (q < total) v[u] = __ldg(reinterpret_cast<const uint4*>(blocks) + 2 * sb + (q - f));
+      }
+#pragma unroll
+      for (int u = 0; u < kPackUnroll; u++) {
+        const uint32_t q = base + 32 * u + lane;
+        if (q < total) dp[q] = v[u];
+      }
     }
   }
 }
@@ -397,6 +421,8 @@ struct XRank {
   DeviceCtx* dc = nullptr;
   cudaStream_t sC = nullptr, sP = nullptr, sN = nullptr;
   StreamCtx sc;          // scheduler counter + ambiguity scratch of the placement kernel
+  StreamCtx sc2;         // push mode: odd sub-batches are placed on sc2.stream with their own counter and scratch, so the
+                         // CTAs of sub-batch j+1 take over the SMs one by one as the last reads of sub-batch j finish
   // batch
   DBuf<uint8_t> seq;
   DBuf<uint64_t> off;
@@ -434,6 +460,7 @@ struct rp_xchg {
   DBuf<uint64_t> bar_dev;      // NCCL: the 8-byte all-gathers that serve as barriers on a stream
   // push mode: the receive buffers of every rank, mapped into this process (CUDA IPC); [rank][buffer]
   bool push = false;
+  bool two_streams = true;     // push mode: placement of even / odd sub-batches on two streams (RP_XCHG_ONE_STREAM=1: one)
   uint8_t* peer_recv[kMaxParts][2] = {};
   cudaIpcMemHandle_t peer_handle[kMaxParts][2] = {};
   bool peer_open[kMaxParts][2] = {};
@@ -575,10 +602,12 @@ static void free_rank(XRank* R) {
     R->bnd_vals.release(); R->bnd_idx.release(); R->hsegs.release(); R->stat.release();
     for (int i = 0; i < 2; i++) { R->sendpay[i].release(); R->recvpay[i].release(); }
     R->o_n_rows.release(); R->o_status.release(); R->o_counts.release(); R->o_node.release(); R->o_score.release(); R->o_lwr.release();
-    cudaFree(R->sc.d_counter); cudaFree(R->sc.d_amb_S); cudaFree(R->sc.d_amb_C);
-    if (R->sc.ev_k0) cudaEventDestroy(R->sc.ev_k0);
-    if (R->sc.ev_k1) cudaEventDestroy(R->sc.ev_k1);
-    if (R->sc.stream) cudaStreamDestroy(R->sc.stream);
+    for (StreamCtx* c : {&R->sc, &R->sc2}) {
+      cudaFree(c->d_counter); cudaFree(c->d_amb_S); cudaFree(c->d_amb_C);
+      if (c->ev_k0) cudaEventDestroy(c->ev_k0);
+      if (c->ev_k1) cudaEventDestroy(c->ev_k1);
+      if (c->stream) cudaStreamDestroy(c->stream);
+    }
     for (int i = 0; i < 2; i++) {
       if (R->evPack[i]) cudaEventDestroy(R->evPack[i]);
       if (R->evA2A[i]) cudaEventDestroy(R->evA2A[i]);
@@ -616,7 +645,7 @@ static int adopt_partition(rp_db* db, int rank, int world, XRank** out) {
   R->db = db;
   R->rank = rank;
   R->dc = dc;
-  if ((rc = init_rank(R)) || (rc = ensure_stream_ctx(db, dc, &R->sc))) { free_rank(R); return rc; }
+  if ((rc = init_rank(R)) || (rc = ensure_stream_ctx(db, dc, &R->sc)) || (rc = ensure_stream_ctx(db, dc, &R->sc2))) { free_rank(R); return rc; }
   *out = R;
   return RP_OK;
 }
@@ -863,8 +892,14 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
   // it ends: measured, the pipeline took accumulate + transfer whatever the settings), and sequential peer WRITES
   // have none of the translation trouble of random peer gathers.  Two 8-byte all-gathers per sub-batch are the
   // barriers: "every home has consumed buffer b" before the pushes, "every owner has pushed" before the placement.
+  std::vector<cudaEvent_t> dbg_ev;  // RP_XCHG_DEBUG: [4j .. 4j+3] = pack start/end, placement start/end of local rank 0
   if (x->push) {
     if ((rc = map_peer_buffers(x))) return rc;
+    if (dbg) {
+      RP_CUDA_TRY(dev(0));
+      dbg_ev.resize(4 * (size_t)J);
+      for (auto& e : dbg_ev) RP_CUDA_TRY(cudaEventCreate(&e));
+    }
     std::vector<std::vector<XPayPlan>> home_plan(L);  // [local rank][home p]: where my blocks land in p's buffer
     for (int l = 0; l < L; l++)
       for (int p = 0; p < W; p++) home_plan[l].push_back(plan_payload(W, J, p, direct_local, U.data()));
@@ -887,12 +922,14 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
           pa.seg[pa.n_seg++] = PackSeg{i0, i1, x->peer_recv[p][b], home_plan[l][p].recv_off[(size_t)j * W + me]};
           most = std::max(most, i1 - i0);
         }
+        if (dbg && l == 0) RP_CUDA_TRY(cudaEventRecord(dbg_ev[4 * j], r->sP));
         if (pa.n_seg) {
           dim3 grid(std::max(1, std::min<int>((int)((most + 127) / 128), r->dc->sm_count * 8 / pa.n_seg + 1)), pa.n_seg);
           xk_pack<<<grid, kPackThreads, 0, r->sP>>>(pa, r->db->parts[me].d_blocks, r->ometa.p, r->units.p, r->uoff.p);
           g_kernel_launches.fetch_add(1);
           RP_CUDA_TRY(cudaGetLastError());
         }
+        if (dbg && l == 0) RP_CUDA_TRY(cudaEventRecord(dbg_ev[4 * j + 1], r->sP));
         if (!x->local && (rc = stream_barrier(x, r->sP))) return rc;  // barrier 2
         RP_CUDA_TRY(cudaEventRecord(r->evPack[b], r->sP));
       }
@@ -900,8 +937,12 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
         XRank* r = R(l);
         RP_CUDA_TRY(dev(l));
         const int me = r->rank;
-        if (x->local) { for (int l2 = 0; l2 < L; l2++) RP_CUDA_TRY(cudaStreamWaitEvent(r->sC, R(l2)->evPack[b], 0)); }
-        else RP_CUDA_TRY(cudaStreamWaitEvent(r->sC, r->evPack[b], 0));
+        // two placement streams: sub-batch j+1 does not wait for the slowest read of sub-batch j
+        StreamCtx& scb = (b && x->two_streams) ? r->sc2 : r->sc;
+        cudaStream_t sPl = (b && x->two_streams) ? r->sc2.stream : r->sC;
+        if (x->local) { for (int l2 = 0; l2 < L; l2++) RP_CUDA_TRY(cudaStreamWaitEvent(sPl, R(l2)->evPack[b], 0)); }
+        else RP_CUDA_TRY(cudaStreamWaitEvent(sPl, r->evPack[b], 0));
+        if (dbg && l == 0) RP_CUDA_TRY(cudaEventRecord(dbg_ev[4 * j + 2], sPl));
         const long long r0 = std::min<long long>(r->n, (long long)j * r->B), r1 = std::min<long long>(r->n, r0 + r->B);
         if (r1 > r0) {
           DbView view = make_db_view(r->db, r->dc);
@@ -918,9 +959,10 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
           xv.base = r->base.p + (size_t)r0 * W;
           xv.n_parts = W;
           const int sms = (x->reserve_sms > 0 && !x->local) ? std::max(1, r->dc->sm_count - x->reserve_sms) : 0;
-          if ((rc = launch_place_xchg(r->db, r->dc, cfg, view, bt, xv, r->sc.d_counter, r->sc.d_amb_S, r->sc.d_amb_C, sms, r->sC))) return rc;
+          if ((rc = launch_place_xchg(r->db, r->dc, cfg, view, bt, xv, scb.d_counter, scb.d_amb_S, scb.d_amb_C, sms, sPl))) return rc;
         }
-        RP_CUDA_TRY(cudaEventRecord(r->evAcc[b], r->sC));
+        if (dbg && l == 0) RP_CUDA_TRY(cudaEventRecord(dbg_ev[4 * j + 3], sPl));
+        RP_CUDA_TRY(cudaEventRecord(r->evAcc[b], sPl));
       }
     }
   }
@@ -1003,6 +1045,7 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
     XRank* r = R(l);
     RP_CUDA_TRY(dev(l));
     const size_t n = (size_t)r->n;
+    if (x->push && x->two_streams && J > 1) RP_CUDA_TRY(cudaStreamWaitEvent(r->sC, r->evAcc[1], 0));  // the odd sub-batches
     RP_CUDA_TRY(cudaEventRecord(r->ev1, r->sC));
     if (!n) continue;
     RP_CUDA_TRY(cudaMemcpyAsync(io[l].n_rows, r->o_n_rows.p, n * 4, cudaMemcpyDeviceToHost, r->sC));
@@ -1028,6 +1071,15 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
     ms_max = std::max<double>(ms_max, ms);
   }
   lap("pack | a2a | placement pipeline");
+  if (!dbg_ev.empty()) {  // device time line of local rank 0 (ms after the first pack began)
+    RP_CUDA_TRY(dev(0));
+    for (int j = 0; j < J; j++) {
+      float t[4];
+      for (int i = 0; i < 4; i++) RP_CUDA_TRY(cudaEventElapsedTime(&t[i], dbg_ev[0], dbg_ev[4 * j + i]));
+      fprintf(stderr, "rp_xchg[%d]   sub-batch %d: push %.2f..%.2f  placement %.2f..%.2f ms\n", x->ranks[0]->rank, j, t[0], t[1], t[2], t[3]);
+    }
+    for (auto& e : dbg_ev) cudaEventDestroy(e);
+  }
   if (dbg) fprintf(stderr, "rp_xchg[%d] J=%d sub-batches, %llu probes sent, %.2f GB received\n", x->ranks[0]->rank, J,
                    (unsigned long long)probes_total, payload_total / 1e9);
   x->last_ms = ms_max;
@@ -1065,6 +1117,7 @@ int rp_xchg_create(rp_db* partition, int32_t rank, int32_t world, const uint8_t*
   x->ranks.push_back(R);
   x->reserve_sms = 8;
   x->push = !(getenv("RP_XCHG_PUSH") && atoi(getenv("RP_XCHG_PUSH")) == 0);
+  x->two_streams = !(getenv("RP_XCHG_ONE_STREAM") && atoi(getenv("RP_XCHG_ONE_STREAM")) != 0);
   if (const char* e = getenv("RP_XCHG_RESERVE_SMS")) x->reserve_sms = atoi(e);
   ncclUniqueId uid;
   memcpy(&uid, id, sizeof uid);
@@ -1086,6 +1139,7 @@ int rp_xchg_create_local(rp_db** partitions, int32_t world, rp_xchg** out) {
   x->world = world;
   x->local = true;
   x->push = !(getenv("RP_XCHG_PUSH") && atoi(getenv("RP_XCHG_PUSH")) == 0);
+  x->two_streams = !(getenv("RP_XCHG_ONE_STREAM") && atoi(getenv("RP_XCHG_ONE_STREAM")) != 0);
   for (int p = 0; p < world; p++) {
     XRank* R = nullptr;
     int rc = adopt_partition(partitions[p], p, world, &R);

@@ -26,7 +26,7 @@ def check_against_oracle(outs, batches, o, cfg, So_fn=None):
 
 
 @pytest.mark.parametrize("env", [dict(), dict(RP_XCHG_PROBES="20000"), dict(RP_XCHG_COPY_LOCAL="1", RP_XCHG_PROBES="50000"),
-                                 dict(RP_XCHG_PUSH="0", RP_XCHG_PROBES="30000")],
+                                 dict(RP_XCHG_PUSH="0", RP_XCHG_PROBES="30000"), dict(RP_XCHG_ONE_STREAM="1", RP_XCHG_PROBES="30000")],
                          ids=lambda e: ",".join("%s=%s" % kv for kv in sorted(e.items())) or "default")
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
 def test_exchange_form_matches_the_oracle(world, env, monkeypatch):
@@ -34,7 +34,7 @@ def test_exchange_form_matches_the_oracle(world, env, monkeypatch):
     per-node scores are those of the oracle (and of the replicated DB) bit for bit.  RP_XCHG_PROBES forces many
     sub-batches (the push | placement pipeline with its two buffers), RP_XCHG_COPY_LOCAL sends a rank's own partition
     through the buffers too, RP_XCHG_PUSH=0 takes the pack | all-to-all | placement form instead of owners writing
-    into the homes' receive buffers."""
+    into the homes' receive buffers, RP_XCHG_ONE_STREAM=1 places all sub-batches on one stream instead of two."""
     import rappas_b200 as R
     from rappas_b200 import exchange
     for k, v in env.items():

@@ -431,3 +431,54 @@ def test_kmers_and_hits_of_the_placement_kernel_itself(case):
     assert np.array_equal(pw["hits"][plain], ex["hits"][plain])
     assert (pw["hits"][(ex["kind"] == _abi.WIN_SKIPPED) & ok_read[win_read]] == -2).all()
     assert (pw["hits"][(ex["kind"] == _abi.WIN_AMBIG) & ok_read[win_read]] == -3).all()
+
+
+def test_the_full_config3_database():
+    """BASELINE.json configs[2] at its full DB size (k = 12, 9 999 nodes, 12.6 M keys, 604 M postings, 4.2 GB in HBM;
+    direct-address table, two node-range passes): a sample of its reads against the oracle -- extraction, per-node
+    scores and rows.  This is the DB the default bench line is measured on."""
+    w = synth.workload(3)
+    db = synth.make_db(w.alphabet, w.k, w.n_nodes, w.n_keys, w.mean_postings, seed=42 + w.index, key_mode=w.key_mode)
+    rb = synth.make_reads(db, 4000, w.read_len, seed=17, iupac_rate=0.002, n_rate=0.001)
+    g, o = both(db)
+    try:
+        parity.assert_extract_equal(g.extract(rb), o.extract(rb))
+        for kw in (dict(), dict(amb_with_max=True)):
+            cfg = _abi.place_cfg(**kw)
+            oo = o.place(rb, cfg)
+            So, _ = o.node_scores(rb, cfg, hitcount=False)
+            amb = None if kw else amb_reads(oo)
+            parity.assert_placements_equal(g.place(rb, cfg), oo, 7, amb, So=So)
+            parity.assert_scores_equal(g.node_scores(rb, cfg), So, amb)
+    finally:
+        g.close()
+        o.close()
+
+
+def test_k15_long_reads_of_the_config5_shape():
+    """BASELINE.json configs[4] in shape: k = 15 (30-bit keys, cuckoo table -- no direct form), 9 999 nodes, reads of
+    50-1500 bp with IUPAC codes and N runs, lists of ~48 postings; the replicated DB and, with the same keys split
+    over 3 owners, the exchange form."""
+    import rappas_b200 as R
+    from rappas_b200 import exchange
+    db = synth.make_db(0, 15, 9999, n_keys=1_500_000, mean_postings=48, seed=47, key_mode="genome")
+    rb = synth.make_reads(db, 500, (50, 1500), seed=5, mutation=0.02, iupac_rate=0.005, n_rate=0.002)
+    g, o = both(db)
+    parts = [R.Database.partition_of_synth(db, 0, p, 3) for p in range(3)]
+    x = exchange.Exchange.local(parts)
+    try:
+        parity.assert_extract_equal(g.extract(rb), o.extract(rb))
+        cfg = _abi.place_cfg()
+        oo = o.place(rb, cfg)
+        assert oo["counts"][:, _abi.CNT_MATCHED].sum() > 20 * rb.n_reads  # the reads do find their genome
+        So, _ = o.node_scores(rb, cfg, hitcount=False)
+        gg = g.place(rb, cfg)
+        parity.assert_placements_equal(gg, oo, 7, amb_reads(oo), So=So)
+        empty = synth.make_reads(db, 0, (50, 60), seed=1)
+        xx = x.place([rb, empty, empty], cfg)[0]
+        for key in ("n_rows", "node", "score", "lwr", "counts", "status"):
+            assert np.array_equal(xx[key], gg[key], equal_nan=True), key
+    finally:
+        x.close()
+        g.close()
+        o.close()
