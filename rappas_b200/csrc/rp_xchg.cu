@@ -126,6 +126,10 @@ struct EnumArgs {
 };
 template <bool FILL>
 __global__ void __launch_bounds__(256) xk_enum(const __grid_constant__ AlphabetTables c_alpha, const __grid_constant__ EnumArgs a) {
+  // class bytes from shared memory: every lane looks up its own character, which a constant bank serialises
+  __shared__ uint8_t cls_tab[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) cls_tab[i] = c_alpha.cls[i];
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
   const int k = a.k, P = a.n_parts;
@@ -149,10 +153,11 @@ __global__ void __launch_bounds__(256) xk_enum(const __grid_constant__ AlphabetT
       }
       if (lane < P) acc += __popc(omask);
     };
+    uint32_t cA, cB = lane < len ? cls_tab[s[lane]] : (uint32_t)kClsPad;
     for (long long g0 = 0; g0 < Ql; g0 += 32) {
-      const long long i0 = g0 + lane, i1 = i0 + 32;
-      const uint32_t cA = i0 < len ? c_alpha.cls[s[i0]] : (uint32_t)kClsPad;
-      const uint32_t cB = i1 < len ? c_alpha.cls[s[i1]] : (uint32_t)kClsPad;
+      const long long i1 = g0 + lane + 32;
+      cA = cB;  // characters [g0, g0 + 32) were the second half of the previous group
+      cB = i1 < len ? cls_tab[s[i1]] : (uint32_t)kClsPad;
       const uint32_t a0 = __ballot_sync(0xffffffffu, (cA & 0xC0) == kClsAmb), a1 = __ballot_sync(0xffffffffu, (cB & 0xC0) == kClsAmb);
       const int na = __popc(__funnelshift_r(a0, a1, lane) & kmask);
       const bool valid = g0 + lane < Ql;
