@@ -426,7 +426,7 @@ struct XRank {
   DeviceCtx* dc = nullptr;
   cudaStream_t sC = nullptr, sP = nullptr, sN = nullptr;
   StreamCtx sc;          // scheduler counter + ambiguity scratch of the placement kernel
-  StreamCtx sc2;         // push mode: odd sub-batches are placed on sc2.stream with their own counter and scratch, so the
+  StreamCtx sc2;         // odd sub-batches are placed on sc2.stream with their own counter and scratch, so the
                          // CTAs of sub-batch j+1 take over the SMs one by one as the last reads of sub-batch j finish
   // batch
   DBuf<uint8_t> seq;
@@ -465,7 +465,7 @@ struct rp_xchg {
   DBuf<uint64_t> bar_dev;      // NCCL: the 8-byte all-gathers that serve as barriers on a stream
   // push mode: the receive buffers of every rank, mapped into this process (CUDA IPC); [rank][buffer]
   bool push = false;
-  bool two_streams = true;     // push mode: placement of even / odd sub-batches on two streams (RP_XCHG_ONE_STREAM=1: one)
+  bool two_streams = true;     // placement of even / odd sub-batches on two streams (RP_XCHG_ONE_STREAM=1: one)
   uint8_t* peer_recv[kMaxParts][2] = {};
   cudaIpcMemHandle_t peer_handle[kMaxParts][2] = {};
   bool peer_open[kMaxParts][2] = {};
@@ -1022,7 +1022,9 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
       XRank* r = R(l);
       RP_CUDA_TRY(dev(l));
       const int me = r->rank;
-      RP_CUDA_TRY(cudaStreamWaitEvent(r->sC, r->evA2A[b], 0));
+      StreamCtx& scb = (b && x->two_streams) ? r->sc2 : r->sc;  // (two placement streams: see the push form)
+      cudaStream_t sPl = (b && x->two_streams) ? r->sc2.stream : r->sC;
+      RP_CUDA_TRY(cudaStreamWaitEvent(sPl, r->evA2A[b], 0));
       const long long r0 = std::min<long long>(r->n, (long long)j * r->B), r1 = std::min<long long>(r->n, r0 + r->B);
       if (r1 > r0) {
         DbView view = make_db_view(r->db, r->dc);
@@ -1040,9 +1042,9 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
         xv.base = r->base.p + (size_t)r0 * W;
         xv.n_parts = W;
         const int sms = (x->reserve_sms > 0 && !x->local) ? std::max(1, r->dc->sm_count - x->reserve_sms) : 0;
-        if ((rc = launch_place_xchg(r->db, r->dc, cfg, view, bt, xv, r->sc.d_counter, r->sc.d_amb_S, r->sc.d_amb_C, sms, r->sC))) return rc;
+        if ((rc = launch_place_xchg(r->db, r->dc, cfg, view, bt, xv, scb.d_counter, scb.d_amb_S, scb.d_amb_C, sms, sPl))) return rc;
       }
-      RP_CUDA_TRY(cudaEventRecord(r->evAcc[b], r->sC));
+      RP_CUDA_TRY(cudaEventRecord(r->evAcc[b], sPl));
     }
   }
   // ---- results
@@ -1050,7 +1052,7 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
     XRank* r = R(l);
     RP_CUDA_TRY(dev(l));
     const size_t n = (size_t)r->n;
-    if (x->push && x->two_streams && J > 1) RP_CUDA_TRY(cudaStreamWaitEvent(r->sC, r->evAcc[1], 0));  // the odd sub-batches
+    if (x->two_streams && J > 1) RP_CUDA_TRY(cudaStreamWaitEvent(r->sC, r->evAcc[1], 0));  // the odd sub-batches
     RP_CUDA_TRY(cudaEventRecord(r->ev1, r->sC));
     if (!n) continue;
     RP_CUDA_TRY(cudaMemcpyAsync(io[l].n_rows, r->o_n_rows.p, n * 4, cudaMemcpyDeviceToHost, r->sC));

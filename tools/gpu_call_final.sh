@@ -3,7 +3,7 @@ mkdir -p gpurun_out; rm -f gpurun_out/fin_*
 timeout 2400 python -m pytest tests -m gpu -x -q 2>&1 | tail -4 | tee gpurun_out/fin_pytest_gpu.txt
 timeout 900 python bench.py > gpurun_out/fin_bench_default.json 2> gpurun_out/fin_bench_default.err; tail -c 1800 gpurun_out/fin_bench_default.json
 timeout 600 python bench.py --impl reference > gpurun_out/fin_bench_reference.json 2> gpurun_out/fin_bench_reference.err; tail -c 700 gpurun_out/fin_bench_reference.json
-for c in 2 4 1 5; do
+for c in 1; do
   timeout 600 python bench.py --config $c --no-cpu > gpurun_out/fin_bench_cfg$c.json 2> gpurun_out/fin_bench_cfg$c.err
   python - <<PY
 import json
