@@ -169,7 +169,12 @@ int  rp_db_partition_blob(rp_db* db, uint8_t* blob_out);
  *   rp_xchg_create_local  all `world` ranks inside ONE process on one GPU (collectives = device copies): how a
  *                       1-GPU box tests the form; rp_xchg_place then takes `world` batches at once
  *   rp_xchg_place       n_local = 1 (NCCL) or world (local); arrays of n_local pointers, each as in rp_place_batch
- *                       (seq_off[l][0] == 0; out_counts may be NULL or hold NULL entries) */
+ *                       (seq_off[l][0] == 0; out_counts may be NULL or hold NULL entries)
+ * Transport of the posting blocks (read when the rp_xchg is created): by default the owners write them into the
+ * homes' receive buffers over peer memory (CUDA IPC between the ranks' processes: all ranks on one node with peer
+ * access, which is what NVSwitch gives); RP_XCHG_PUSH=0 = ncclSend / ncclRecv instead.  Tuning knobs, all optional:
+ * RP_XCHG_PROBES (probes per pipelined sub-batch, 16 M), RP_XCHG_RESERVE_SMS (SMs the placement kernel leaves free,
+ * 8), RP_XCHG_ONE_STREAM=1, RP_XCHG_DEBUG=1 (phase times and the device time line of rank 0 on stderr). */
 #define RP_XCHG_ID_BYTES 128
 typedef struct rp_xchg rp_xchg;
 int  rp_xchg_unique_id(uint8_t* id_out);
