@@ -395,7 +395,7 @@ __device__ __forceinline__ int finalize_rows(const CfgView& cfg, const TopList& 
 // kGrpPassEnd: last group of a node-range pass that is not the read's last (the consumer selects over the slice
 // and resets it); the pass index travels in bits 24-27.
 enum : int { kGrpLast = 1, kGrpBad = 2, kGrpTooLong = 4, kGrpStop = 8, kGrpAmb = 16, kGrpAmbGlobal = 32, kGrpPassEnd = 64 };
-constexpr int kGrpWsizeShift = 8, kGrpTabShift = 16, kGrpPassShift = 24;
+constexpr int kGrpWsizeShift = 8, kGrpPassShift = 24;
 constexpr int kMaxPasses = 16;  // slices are routed by sixteenths of the node range
 constexpr int kMaxAmbWin = 8;   // ambiguous windows per group (their table info travels in pk[0..7] of the stage header)
 struct __align__(16) StageHdr {

@@ -742,7 +742,6 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
   std::vector<uint64_t> S;
   if ((rc = host_allgather(x, v, (size_t)J * W, S))) return rc;
   lap("sub-batch plan (2 all-gathers)");
-  auto Sat = [&](int w, int j, int o) { return S[((size_t)w * J + j) * W + o]; };
   // ---- 2: keys to their owners
   A2A a2a;
   auto a2a_reset = [&]() {
@@ -784,7 +783,8 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
     }
   }
   if (x->local) for (int l = 0; l < L; l++) { RP_CUDA_TRY(dev(l)); RP_CUDA_TRY(cudaStreamSynchronize(R(l)->sC)); }  // senders' keys are written
-  if ((rc = alltoallv(x, a2a, sCs))) return rc;
+  rc = alltoallv(x, a2a, sCs);
+  if (rc) return rc;
   // ---- 3: lookups, answers, payload sizes
   // boundaries of (source p, sub-batch j) in the received order; U[(p * J + j)] = 32 B units this rank sends p for j
   std::vector<std::vector<size_t>> bnd(L);
@@ -848,7 +848,8 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
       a2a.roff[l][p] = r->kp.send_off[p] * 4; a2a.rcnt[l][p] = r->kp.send_cnt[p] * 4;
     }
   }
-  if ((rc = alltoallv(x, a2a, sCs))) return rc;
+  rc = alltoallv(x, a2a, sCs);
+  if (rc) return rc;
   // ---- home: where every block will land (receive buffer of its sub-batch), rmeta
   uint64_t payload_total = 0;
   for (int l = 0; l < L; l++) {
@@ -1003,7 +1004,6 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
     for (int l = 0; l < L; l++) {
       XRank* r = R(l);
       RP_CUDA_TRY(dev(l));
-      const int me = r->rank;
       if (j >= 2) RP_CUDA_TRY(cudaStreamWaitEvent(r->sN, r->evAcc[b], 0));  // recvpay[b] has been consumed
       a2a.send[l] = r->sendpay[b].p; a2a.recv[l] = r->recvpay[b].p;
       for (int p = 0; p < W; p++) {
@@ -1015,7 +1015,8 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
     // every rank's pack of this sub-batch must be done before a copy reads its send buffer
     for (int l = 0; l < L; l++)
       for (int l2 = 0; l2 < L; l2++) { RP_CUDA_TRY(dev(l)); RP_CUDA_TRY(cudaStreamWaitEvent(R(l)->sN, R(l2)->evPack[b], 0)); }
-    if ((rc = alltoallv(x, a2a, sNs))) return rc;
+    rc = alltoallv(x, a2a, sNs);
+    if (rc) return rc;
     for (int l = 0; l < L; l++) { RP_CUDA_TRY(dev(l)); RP_CUDA_TRY(cudaEventRecord(R(l)->evA2A[b], R(l)->sN)); }
     // placement (home side)
     for (int l = 0; l < L; l++) {
