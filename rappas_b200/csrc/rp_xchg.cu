@@ -837,7 +837,6 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
   lap("fill + keys a2a + lookup + scan");
   std::vector<uint64_t> U;  // U[(o * W + p) * J + j] = units owner o sends home p for sub-batch j
   if ((rc = host_allgather(x, v, (size_t)W * J, U))) return rc;
-  auto Uat = [&](int o, int p, int j) { return U[((size_t)o * W + p) * J + j]; };
   // answers back to the homes (all sub-batches at once: 4 B per probe)
   a2a_reset();
   for (int l = 0; l < L; l++) {
