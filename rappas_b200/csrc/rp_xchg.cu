@@ -568,17 +568,29 @@ static int map_peer_buffers(rp_xchg* x) {
   std::vector<uint64_t> all;
   int rc = host_allgather(x, v, 16, all);
   if (rc) return rc;
-  for (int p = 0; p < W; p++)
+  int failed_peer = -1;
+  cudaError_t why = cudaSuccess;
+  for (int p = 0; p < W && failed_peer < 0; p++)
     for (int b = 0; b < 2; b++) {
       if (p == R->rank) { x->peer_recv[p][b] = R->recvpay[b].p; continue; }
       cudaIpcMemHandle_t h;
       memcpy(&h, all.data() + (size_t)p * 16 + 8 * b, 64);
       if (x->peer_open[p][b] && memcmp(&h, &x->peer_handle[p][b], 64) == 0) continue;
       if (x->peer_open[p][b]) { cudaIpcCloseMemHandle(x->peer_recv[p][b]); x->peer_open[p][b] = false; }
-      RP_CUDA_TRY(cudaIpcOpenMemHandle((void**)&x->peer_recv[p][b], h, cudaIpcMemLazyEnablePeerAccess));
+      why = cudaIpcOpenMemHandle((void**)&x->peer_recv[p][b], h, cudaIpcMemLazyEnablePeerAccess);
+      if (why != cudaSuccess) { cudaGetLastError(); failed_peer = p; break; }
       x->peer_handle[p][b] = h;
       x->peer_open[p][b] = true;
     }
+  // every rank learns whether every rank could map its peers: a rank that returned alone would leave the others
+  // waiting in the pipeline's barriers
+  v[0].assign(1, failed_peer >= 0 ? 1u : 0u);
+  if ((rc = host_allgather(x, v, 1, all))) return rc;
+  for (int p = 0; p < W; p++)
+    if (all[p])
+      return set_error(RP_E_CUDA, "rank %d cannot map a peer's receive buffer%s%s: the push transport needs CUDA IPC and peer access "
+                       "between all ranks (one node); set RP_XCHG_PUSH=0 for ncclSend / ncclRecv",
+                       p, p == R->rank ? ": " : "", p == R->rank ? cudaGetErrorString(why) : "");
   return RP_OK;
 }
 
