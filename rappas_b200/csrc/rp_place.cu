@@ -1685,6 +1685,12 @@ static int place_on_device(rp_db* db, DeviceCtx* dc, const rp_place_cfg* cfg, co
   const int K = cfg->keep_at_most;
   // reads per H2D / kernel / D2H pipeline step (two streams alternate); RP_CHUNK_READS overrides for tuning
   int64_t kChunk = out_dump ? 4096 : (1 << 16);  // tools/sweep_chunk.sh: 32k-128k reads are equivalent, 256k+ exposes the first H2D
+  // Sliced trees: a chunk is three launches (character count, the two builds of the kernel), and the build that
+  // returns at once still needs every SM once -- the next chunk starts only when the previous one has drained,
+  // ~0.2 ms per chunk.  Larger chunks for large batches (config 3, 4 M reads: 64 k / 256 k / 1 M reads per chunk =
+  // 34.4 / 38.2 / 37.3 M reads/s end to end, 24.9 / 36.8 / 34.6 M from pageable memory; tools/gpu_call20.sh).
+  if (!out_dump && dc->geom.n_pass > 1)
+    kChunk = std::max<int64_t>(1 << 16, std::min<int64_t>(1 << 18, (((r1 - r0) / 8 + 16383) / 16384) * 16384));
   if (const char* e = getenv("RP_CHUNK_READS")) if (!out_dump && atoll(e) > 0) kChunk = atoll(e);
   const bool stage_in = !is_pinned(seq) || !is_pinned(seq_off);
   const bool stage_out = !out_dump && (!is_pinned(out_n_rows) || !is_pinned(out_node) || !is_pinned(out_score) ||
