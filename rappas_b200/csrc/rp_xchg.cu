@@ -211,13 +211,20 @@ __global__ void __launch_bounds__(256) xk_enum(const __grid_constant__ AlphabetT
   }
 }
 
-// exclusive scan of column o of cnt[n][P] (one block per column); tot[o] = its sum
+// exclusive scan of column o of cnt[n][P] (one block per column); tot[o] = its sum, or kTotOverflow when the probes a
+// batch sends one owner do not fit the 32-bit counters of this file (the host then refuses the batch)
+constexpr uint32_t kTotOverflow = 0xFFFFFFFFu;
 __global__ void __launch_bounds__(1024) xk_colscan(const uint32_t* cnt, long long n, int P, uint32_t* base, uint32_t* tot) {
   __shared__ uint32_t part[1024];
+  __shared__ unsigned long long tot64;
   const int o = blockIdx.x, t = threadIdx.x;
+  if (t == 0) tot64 = 0ull;
+  __syncthreads();
   const long long chunk = (n + 1023) / 1024, lo = std::min<long long>(n, t * chunk), hi = std::min<long long>(n, lo + chunk);
   uint32_t sum = 0;
-  for (long long r = lo; r < hi; r++) sum += cnt[r * P + o];
+  unsigned long long sum64 = 0ull;
+  for (long long r = lo; r < hi; r++) { const uint32_t c = cnt[r * P + o]; sum += c; sum64 += c; }
+  if (sum64) atomicAdd(&tot64, sum64);
   part[t] = sum;
   __syncthreads();
   for (int d = 1; d < 1024; d <<= 1) {
@@ -232,7 +239,7 @@ __global__ void __launch_bounds__(1024) xk_colscan(const uint32_t* cnt, long lon
     base[r * P + o] = run;
     run += c;
   }
-  if (t == 1023) tot[o] = part[1023];
+  if (t == 1023) tot[o] = tot64 >= (unsigned long long)kTotOverflow ? kTotOverflow : part[1023];
 }
 
 // seg[j][o] = probes of sub-batch j (reads [j*B, (j+1)*B)) for owner o
@@ -727,16 +734,21 @@ static int xchg_place(rp_xchg* x, const rp_place_cfg* cfg, const std::vector<Ran
   std::vector<std::vector<uint64_t>> v(L);
   for (int l = 0; l < L; l++) {
     XRank* r = R(l);
-    uint64_t probes = 0;
-    for (int o = 0; o < W; o++) probes += r->h_tot[o];
+    uint64_t probes = 0, too_many = 0;
+    for (int o = 0; o < W; o++) { probes += r->h_tot[o]; too_many |= r->h_tot[o] == kTotOverflow; }
     const uint64_t jl = std::max<uint64_t>(1, (probes + target - 1) / target);
     r->B = std::max<long long>(1, (r->n + (long long)jl - 1) / (long long)jl);
-    v[l] = {(uint64_t)r->n, (uint64_t)((r->n + r->B - 1) / r->B)};
+    v[l] = {(uint64_t)r->n, (uint64_t)((r->n + r->B - 1) / r->B), too_many};
   }
   std::vector<uint64_t> all;
-  if ((rc = host_allgather(x, v, 2, all))) return rc;
+  if ((rc = host_allgather(x, v, 3, all))) return rc;
   int J = 1;
-  for (int w = 0; w < W; w++) J = std::max<int>(J, (int)all[2 * w + 1]);
+  for (int w = 0; w < W; w++) {
+    // (every rank sees every rank's verdict, so all of them leave the collective together)
+    if (all[3 * w + 2])
+      return set_error(RP_E_UNSUPPORTED, "rank %d: more than 2^32 - 2 probes for one owner in one batch; place the reads in smaller batches", w);
+    J = std::max<int>(J, (int)all[3 * w + 1]);
+  }
   if (J > 2047) return set_error(RP_E_UNSUPPORTED, "more than 2047 sub-batches: raise RP_XCHG_PROBES");
   // seg[j][o] per rank, gathered: S[(w * J + j) * W + o] = probes of rank w's sub-batch j for owner o
   for (int l = 0; l < L; l++) {
