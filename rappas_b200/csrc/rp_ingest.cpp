@@ -103,35 +103,49 @@ inline size_t next_line(const uint8_t* t, size_t n, size_t pos, size_t* line_end
 
 // the records of one piece of the text (a piece starts at a header line, except possibly the first)
 struct Piece {
-  std::vector<uint8_t> hdr, seq;
+  std::vector<uint8_t> hdr, seq;   // seq: only the sequences that had to be joined from several lines
   std::vector<uint32_t> hdr_len, seq_len;
+  std::vector<uint64_t> seq_at;    // where the (joined + trimmed) sequence is: offset into the text, or kInJoined | offset into seq
   std::vector<uint64_t> hash;      // of the joined + trimmed sequence
   bool any_gap = false, data_before_header = false;
 };
+constexpr uint64_t kInJoined = 1ull << 63;
 
+// A record whose sequence is ONE line -- nearly all reads -- is not copied here: it is hashed where the text has it
+// and copied once, when the distinct sequences are gathered.  Only wrapped sequences are joined in a side buffer.
 void parse_piece(const uint8_t* t, size_t begin, size_t end, Piece* P) {
   bool in_record = false;
-  size_t rec_start = 0;  // of the current record in P->seq
+  size_t one_at = 0, one_len = 0;  // the record's only sequence line so far (text offset, length)
+  int n_lines = 0;                 // sequence lines of the record; from the second on they are joined in P->seq
+  size_t rec_start = 0;            // of the current record in P->seq
   auto close_record = [&]() {
     // String.trim(): strip code points <= U+0020 from both ends of the joined sequence (FASTAPointer.java:143-145)
-    size_t b = rec_start, e = P->seq.size();
-    while (e > b && P->seq[e - 1] <= 0x20) e--;
-    size_t s = b;
-    while (s < e && P->seq[s] <= 0x20) s++;
-    if (s > b) memmove(&P->seq[b], &P->seq[s], e - s);
-    P->seq.resize(b + (e - s));
-    P->seq_len.push_back((uint32_t)(e - s));
-    P->hash.push_back(hash_bytes(P->seq.data() + b, e - s));
-    if (!P->any_gap && memchr(P->seq.data() + b, '-', e - s)) P->any_gap = true;
+    const uint8_t* base = n_lines >= 2 ? P->seq.data() : t;
+    size_t b = n_lines >= 2 ? rec_start : one_at, e = n_lines >= 2 ? P->seq.size() : one_at + one_len;
+    while (e > b && base[e - 1] <= 0x20) e--;
+    while (b < e && base[b] <= 0x20) b++;
+    if (n_lines >= 2) {
+      if (b > rec_start) memmove(&P->seq[rec_start], &P->seq[b], e - b);
+      P->seq.resize(rec_start + (e - b));
+      P->seq_at.push_back(kInJoined | rec_start);
+      base = P->seq.data();
+      e = rec_start + (e - b);
+      b = rec_start;
+    } else {
+      P->seq_at.push_back(b);
+    }
+    P->seq_len.push_back((uint32_t)(e - b));
+    P->hash.push_back(hash_bytes(base + b, e - b));
+    if (!P->any_gap && e > b && memchr(base + b, '-', e - b)) P->any_gap = true;
   };
   P->hdr.reserve((end - begin) / 4);
-  P->seq.reserve(end - begin);
   size_t pos = begin;
   while (pos < end) {
     size_t le;
     const size_t nxt = next_line(t, end, pos, &le);
     const uint8_t* line = t + pos;
     const size_t len = le - pos;
+    const size_t at = pos;
     pos = nxt;
     if (len == 0 || line[0] == '#') continue;  // empty and '#' lines are skipped (FASTAPointer.java:82-87)
     if (line[0] == '>') {
@@ -139,11 +153,21 @@ void parse_piece(const uint8_t* t, size_t begin, size_t end, Piece* P) {
       P->hdr.insert(P->hdr.end(), line + 1, line + len);
       P->hdr_len.push_back((uint32_t)(len - 1));
       in_record = true;
-      rec_start = P->seq.size();
+      n_lines = 0;
+      one_at = one_len = 0;
       continue;
     }
     if (!in_record) { P->data_before_header = true; return; }
-    P->seq.insert(P->seq.end(), line, line + len);
+    if (n_lines == 0) {
+      one_at = at; one_len = len;
+    } else {
+      if (n_lines == 1) {  // a second line: the sequence is wrapped, join it
+        rec_start = P->seq.size();
+        P->seq.insert(P->seq.end(), t + one_at, t + one_at + one_len);
+      }
+      P->seq.insert(P->seq.end(), line, line + len);
+    }
+    n_lines++;
   }
   if (in_record) close_record();
 }
@@ -229,11 +253,12 @@ int parse(const uint8_t* t, size_t n, rp_reads* R) {
     const Piece& P = pieces[i];
     if (!P.hdr.empty()) memcpy(R->hdr.data() + hdr0[i], P.hdr.data(), P.hdr.size());
     size_t ho = hdr0[i];
-    const uint8_t* sp = P.seq.data();
     for (size_t j = 0; j < P.hdr_len.size(); j++) {
       const size_t r = rec0[i] + j;
-      R->hdr_off[r] = ho; sptr[r] = sp; slen[r] = P.seq_len[j]; hashes[r] = P.hash[j];
-      ho += P.hdr_len[j]; sp += P.seq_len[j];
+      const uint64_t at = P.seq_at[j];
+      R->hdr_off[r] = ho; slen[r] = P.seq_len[j]; hashes[r] = P.hash[j];
+      sptr[r] = (at & kInJoined) ? P.seq.data() + (at & ~kInJoined) : t + at;
+      ho += P.hdr_len[j];
     }
   });
   R->hdr_off[nrec] = hdr_bytes;
@@ -243,12 +268,23 @@ int parse(const uint8_t* t, size_t n, rp_reads* R) {
   // every distinct sequence; ids then come from a prefix count over the records that are such a first.
   std::vector<uint32_t> first_of(nrec);
   const unsigned np = nt;
+  // which thread a record's hash falls to (a byte per record: every thread reads all of them), and how many fall to each
+  std::vector<uint8_t> bucket(nrec);
+  std::vector<size_t> mine_part((size_t)nt * np, 0);
+  run_parallel(nt, [&](unsigned i) {
+    size_t* cnt = &mine_part[(size_t)i * np];
+    for (size_t r = nrec * i / nt; r < nrec * (i + 1) / nt; r++) {
+      const unsigned p = (unsigned)(((hashes[r] >> 40) * np) >> 24);  // 24 hash bits scaled to [0, np)
+      bucket[r] = (uint8_t)p;
+      cnt[p]++;
+    }
+  });
   run_parallel(np, [&](unsigned p) {
     size_t mine = 0;
-    for (size_t r = 0; r < nrec; r++) mine += (unsigned)((hashes[r] >> 40) % np) == p;
+    for (unsigned i = 0; i < nt; i++) mine += mine_part[(size_t)i * np + p];
     FlatSet set(mine);
     for (size_t r = 0; r < nrec; r++) {
-      if ((unsigned)((hashes[r] >> 40) % np) != p) continue;
+      if (bucket[r] != p) continue;
       const uint8_t* sp = sptr[r];
       const uint32_t sn = slen[r];
       bool ins;
@@ -257,17 +293,31 @@ int parse(const uint8_t* t, size_t n, rp_reads* R) {
       }, &ins);
     }
   });
+  // ids in order of first appearance: count the firsts (and their bytes) per range of records, scan, then number
   R->unique_of.resize(nrec);
   R->group_of.resize(nrec);
-  R->seq_off.assign(1, 0);
-  std::vector<uint32_t> first_rec;  // unique id -> its first record
-  for (size_t r = 0; r < nrec; r++)
-    if (first_of[r] == r) {
-      R->unique_of[r] = (uint32_t)first_rec.size();
-      first_rec.push_back((uint32_t)r);
-      R->seq_off.push_back(R->seq_off.back() + slen[r]);
-    }
-  const size_t n_unique = first_rec.size();
+  std::vector<size_t> n_first(nt + 1, 0), b_first(nt + 1, 0);
+  run_parallel(nt, [&](unsigned i) {
+    size_t c = 0, bytes = 0;
+    for (size_t r = nrec * i / nt; r < nrec * (i + 1) / nt; r++)
+      if (first_of[r] == r) { c++; bytes += slen[r]; }
+    n_first[i + 1] = c; b_first[i + 1] = bytes;
+  });
+  for (unsigned i = 0; i < nt; i++) { n_first[i + 1] += n_first[i]; b_first[i + 1] += b_first[i]; }
+  const size_t n_unique = n_first[nt];
+  std::vector<uint32_t> first_rec(n_unique);  // unique id -> its first record
+  R->seq_off.resize(n_unique + 1);
+  R->seq_off[n_unique] = b_first[nt];
+  run_parallel(nt, [&](unsigned i) {
+    size_t u = n_first[i], at = b_first[i];
+    for (size_t r = nrec * i / nt; r < nrec * (i + 1) / nt; r++)
+      if (first_of[r] == r) {
+        R->unique_of[r] = (uint32_t)u;
+        first_rec[u] = (uint32_t)r;
+        R->seq_off[u] = at;
+        u++; at += slen[r];
+      }
+  });
   if (!R->seq.resize(R->seq_off.back())) return set_error(RP_E_NOMEM, "out of memory for %zu B of sequences", (size_t)R->seq_off.back());
   run_parallel(nt, [&](unsigned i) {
     for (size_t r = nrec * i / nt; r < nrec * (i + 1) / nt; r++)
