@@ -165,3 +165,42 @@ def _plan_worker(rank, world, port, tmp):
 def test_exchange_plan_agrees_across_ranks(tmp_path, world):
     mp.spawn(_plan_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / ("plan%d" % r)).exists() for r in range(world))
+
+
+@pytest.mark.parametrize("world,J", [(8, 7), (5, 1), (1, 3)])
+def test_exchange_plan_of_every_rank_in_one_process(world, J):
+    """The plan of all `world` ranks computed side by side (no process group needed: the plan is a pure function of the
+    gathered count matrices) at the sizes the 8-GPU runs use.  What the PUSH transport relies on: owner l writes its
+    blocks of sub-batch j for home p at p's receive offset [j][l], so for every (p, j) those ranges must tile p's
+    buffer without overlap and stay under its capacity; and what l sends p is what p expects from l."""
+    from rappas_b200 import _abi
+    from rappas_b200._lib import check, load
+    fn = load()
+    rng = np.random.default_rng(7 * world + J)
+    probes = rng.integers(0, 5000, size=(world, J, world)).astype(np.uint64)   # [home w][sub-batch j][owner o]
+    probes[rng.integers(0, world), rng.integers(0, J)] = 0
+    units = np.zeros((world, world, J), np.uint64)                               # [owner o][home p][j]
+    for o in range(world):
+        units[o] = (probes[:, :, o] * np.uint64(5) // np.uint64(3)).astype(np.uint64)
+    for direct in (0, 1):
+        plans = []
+        for rank in range(world):
+            out = {k: np.zeros(n, np.uint64) for k, n in (("kso", world + 1), ("kro", world + 1), ("seg", world * J + 1),
+                                                          ("home", world * J), ("pso", J * world), ("psc", J * world),
+                                                          ("pro", J * world), ("prc", J * world), ("caps", 3))}
+            check(fn["xchg_plan"](world, J, rank, direct, _abi.ptr(np.ascontiguousarray(probes)), _abi.ptr(np.ascontiguousarray(units)),
+                                  *[_abi.ptr(out[k]) for k in ("kso", "kro", "seg", "home", "pso", "psc", "pro", "prc", "caps")]))
+            plans.append(out)
+        for l in range(world):
+            for p in range(world):
+                assert plans[l]["kso"][p + 1] - plans[l]["kso"][p] == plans[p]["kro"][l + 1] - plans[p]["kro"][l] == probes[l, :, p].sum()
+                for j in range(J):
+                    expect = 0 if (direct and l == p) else units[l, p, j]
+                    assert plans[l]["psc"][j * world + p] == plans[p]["prc"][j * world + l] == expect
+        for p in range(world):
+            for j in range(J):
+                ro, rc = plans[p]["pro"][j * world:(j + 1) * world], plans[p]["prc"][j * world:(j + 1) * world]
+                order = np.argsort(ro, kind="stable")
+                ends = (ro + rc)[order]
+                assert np.all(ro[order][1:] >= ends[:-1])          # the owners' ranges do not overlap
+                assert ends.max(initial=0) <= plans[p]["caps"][1]  # and fit the receive buffer
